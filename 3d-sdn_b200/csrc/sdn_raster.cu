@@ -1,0 +1,1174 @@
+// sdn_raster.cu -- sm_100a differentiable mesh rasteriser behind the C ABI of include/sdn_b200.h.
+//
+// Replaces the seven CuPy elementwise kernels of /root/reference/geometric/neural_renderer/rasterize.py and the
+// Chainer glue around them.  Design (DESIGN.md has the long form):
+//
+//   k_faces_forward   fill_back + camera + perspective + gather      (renderer.py:41, look.py:38-43, perspective.py:13-18,
+//                                                                     vertices_to_faces.py:16-21)
+//   k_face_setup      cull, barycentric inverse, bbox, active list   (rasterize.py:240-277)
+//   k_raster_tiles    persistent CTAs over 64x32-sample tiles: faces are streamed against the tile, coverage is
+//                     resolved FACE-parallel into a shared-memory z-buffer of packed (depth_bits<<32 | face) keys with
+//                     64-bit atomicMin -- which is exactly the safe path's "strict <, faces in index order" rule
+//                     (rasterize.py:301-341) and is order-independent, hence deterministic; then texture sampling
+//                     (rasterize.py:362-435), alpha / background (:437-462), row flip + 2x2 mean (:950-966) are
+//                     applied in registers and written once, as float2 / int4 rows.
+//   k_backward_items  one warp per (visible face, edge, axis) item of the NMR gradient (rasterize.py:514-745) plus one
+//                     "interior" item per face that gathers the depth (:791-844) and texture (:747-789) gradients
+//                     without atomics; out-sweeps run warp-wide and coalesced.
+//   k_grad_assemble   deterministic sum of the per-item partials into grad_faces.
+//   k_faces_backward* scatter onto vertices + chain rule through perspective / camera / flip.
+//
+// Arithmetic contract: everything that decides visibility is IEEE float32 in the reference's op order, compiled with
+// -fmad=false (no contraction), IEEE division and sqrt; doubles only where the reference's literals force them.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+
+#include "sdn_b200.h"
+
+namespace {
+
+constexpr int TW = 64;        // tile width  in samples
+constexpr int TH = 32;        // tile height in samples
+constexpr int NT = 256;       // threads per CTA (raster)
+constexpr int QCAP = 768;     // per-tile face queue
+constexpr unsigned FULL = 0xffffffffu;
+typedef unsigned long long u64;
+
+std::atomic<long long> g_launches{0};
+
+// ------------------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------------------
+struct Workspace {
+    int* active_count;      // [B]
+    int* vis_count;         // [B]
+    int* img_bbox;          // [B,4]  {65535-xmin, 65535-ymin, xmax+1, ymax+1}, all grown with atomicMax from 0
+    int* counters;          // [4]    {tile ticket, item ticket, -, -}
+    unsigned char* visible; // [B*F]  face won at least one sample
+    float* face_inv;        // [B*F,9]
+    short* face_bbox;       // [B*F,4] x0,y0,x1,y1 inclusive, clamped to the raster
+    int* active_ids;        // [B*F]
+    int* vis_ids;           // [B*F]
+    float* gpart;           // [B*F,12]  K6 partials [edge][axis][2]
+    float* gint;            // [B*F,6]   interior sums: S_k (3), colour grad (3)
+    size_t zero_bytes;      // leading bytes cleared at the start of every forward
+    size_t total;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+Workspace make_ws(void* base, int B, int F) {
+    Workspace w;
+    char* p = (char*)base;
+    size_t off = 0;
+    const size_t BF = (size_t)B * F;
+    w.active_count = (int*)(p + off); off += sizeof(int) * B;
+    w.vis_count = (int*)(p + off); off += sizeof(int) * B;
+    w.img_bbox = (int*)(p + off); off += sizeof(int) * 4 * B;
+    w.counters = (int*)(p + off); off += sizeof(int) * 4;
+    w.visible = (unsigned char*)(p + off); off += BF;
+    off = align_up(off, 256);
+    w.zero_bytes = off;
+    w.face_inv = (float*)(p + off); off = align_up(off + BF * 36, 256);
+    w.face_bbox = (short*)(p + off); off = align_up(off + BF * 8, 256);
+    w.active_ids = (int*)(p + off); off = align_up(off + BF * 4, 256);
+    w.vis_ids = (int*)(p + off); off = align_up(off + BF * 4, 256);
+    w.gpart = (float*)(p + off); off = align_up(off + BF * 48, 256);
+    w.gint = (float*)(p + off); off = align_up(off + BF * 24, 256);
+    w.total = off;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// shared device arithmetic (op order of rasterize.py; -fmad=false keeps it uncontracted)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_pixel(float v, int is) {     // rasterize.py:258
+    float t = v * (float)is;
+    t = t + (float)is;
+    t = t - 1.0f;
+    return 0.5f * t;
+}
+__device__ __forceinline__ bool is_backside(const float* f) {    // rasterize.py:252
+    return (f[7] - f[1]) * (f[3] - f[0]) < (f[4] - f[1]) * (f[6] - f[0]);
+}
+
+struct Clip {
+    double near_, far_;
+    float far_f;
+};
+
+// One (face, sample) evaluation of the safe kernel, rasterize.py:310-332.  Returns false when rejected.
+__device__ __forceinline__ bool eval_sample(const float* f, const float* inv, float xp, float yp, float xif,
+                                            float yif, const Clip& c, float* w, float& zp) {
+    if (((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) ||
+        ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) ||
+        ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7]))) return false;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float t = inv[3 * k + 0] * xif;
+        float u = inv[3 * k + 1] * yif;
+        t = t + u;
+        w[k] = fminf(fmaxf(t + inv[3 * k + 2], 0.0f), 1.0f);
+    }
+    float ws = w[0] + w[1];
+    ws = ws + w[2];
+    w[0] = __fdiv_rn(w[0], ws);
+    w[1] = __fdiv_rn(w[1], ws);
+    w[2] = __fdiv_rn(w[2], ws);
+    float s = __fdiv_rn(w[0], f[2]) + __fdiv_rn(w[1], f[5]);
+    s = s + __fdiv_rn(w[2], f[8]);
+    zp = __fdiv_rn(1.0f, s);
+    if ((double)zp <= c.near_ || c.far_ <= (double)zp) return false;
+    return zp < c.far_f;        // depth_min starts at (float)far, rasterize.py:297; also rejects NaN
+}
+
+// rasterize.py:399-423: the 8 trilinear corners of one covered sample.  ti[k] float index along texture axis k.
+__device__ __forceinline__ void texture_index(const float* w, float depth, const float* f, int ts, double eps,
+                                              float* tif) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float q = __fdiv_rn(depth, f[3 * k + 2]);
+        tif[k] = (float)(((double)w[k] * ((double)(ts - 1) - eps)) * (double)q);
+    }
+}
+__device__ __forceinline__ float corner_weight(const float* tif, int pn, int* tii) {
+    float w = 1.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int ti = __float2int_rz(tif[k]);
+        const float frac = tif[k] - (float)ti;
+        if (((pn >> k) & 1) == 0) { w = w * (1.0f - frac); tii[k] = ti; }
+        else { w = w * frac; tii[k] = ti + 1; }
+    }
+    return w;
+}
+
+__device__ __forceinline__ float xp_of(int xi, int Ws) { return __fdiv_rn((float)(2 * xi + 1 - Ws), (float)Ws); }
+
+// ------------------------------------------------------------------------------------------------------------
+// faces forward: fill_back + flip + camera + perspective + gather (+ normals)
+// ------------------------------------------------------------------------------------------------------------
+struct CamDev {
+    const float* rot; const float* eye; const float* wx; const float* wy; float flip;
+};
+
+__device__ __forceinline__ void cam_vertex(const float* v, int b, const CamDev& c, float* pre, float* out) {
+    float x = v[0] * c.flip, y = v[1], z = v[2];
+    pre[0] = x; pre[1] = y; pre[2] = z;
+    if (c.eye) { x = x - c.eye[b * 3 + 0]; y = y - c.eye[b * 3 + 1]; z = z - c.eye[b * 3 + 2]; }
+    if (c.rot) {
+        const float* r = c.rot + b * 9;
+        float o[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            float s = x * r[3 * i + 0] + y * r[3 * i + 1];
+            o[i] = s + z * r[3 * i + 2];
+        }
+        x = o[0]; y = o[1]; z = o[2];
+    }
+    if (c.wx) {
+        x = __fdiv_rn(__fdiv_rn(x, z), c.wx[b]);
+        y = __fdiv_rn(__fdiv_rn(y, z), c.wy[b]);
+    }
+    out[0] = x; out[1] = y; out[2] = z;
+}
+
+__global__ void k_faces_forward(const float* __restrict__ vertices, const int32_t* __restrict__ faces, int B, int nv,
+                                int nf, int faces_batched, int fill_back, CamDev cam, float* __restrict__ face_ndc,
+                                float* __restrict__ face_normal) {
+    const int F = fill_back ? 2 * nf : nf;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * F) return;
+    const int b = (int)(i / F), fn = (int)(i % F);
+    const int src = fn < nf ? fn : fn - nf;
+    const int32_t* tri = faces + ((size_t)(faces_batched ? b : 0) * nf + src) * 3;
+    int vid[3] = {tri[0], tri[1], tri[2]};
+    if (fn >= nf) { int t = vid[0]; vid[0] = vid[2]; vid[2] = t; }      // faces[:, :, ::-1]
+    float pre[3][3], ndc[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) cam_vertex(vertices + ((size_t)b * nv + vid[k]) * 3, b, cam, pre[k], ndc[k]);
+    float* o = face_ndc + (size_t)i * 9;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[3 * k] = ndc[k][0]; o[3 * k + 1] = ndc[k][1]; o[3 * k + 2] = ndc[k][2]; }
+    if (face_normal) {      // derender3d/models/renderer.py:66-73
+        const float a0 = pre[0][0] - pre[1][0], a1 = pre[0][1] - pre[1][1], a2 = pre[0][2] - pre[1][2];
+        const float b0 = pre[2][0] - pre[1][0], b1 = pre[2][1] - pre[1][1], b2 = pre[2][2] - pre[1][2];
+        const float c0 = a1 * b2 - a2 * b1, c1 = a2 * b0 - a0 * b2, c2 = a0 * b1 - a1 * b0;
+        float n2 = c0 * c0 + c1 * c1;
+        n2 = n2 + c2 * c2;
+        const float norm = __fsqrt_rn(n2) + 1e-5f;
+        float* n = face_normal + (size_t)i * 3;
+        // x is reported in the caller's (un-flipped) frame: derender3d/models/renderer.py:268-270 negates it again
+        n[0] = __fdiv_rn(c0, norm) * cam.flip; n[1] = __fdiv_rn(c1, norm); n[2] = __fdiv_rn(c2, norm);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// face setup (K1a) + active list + image bbox
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_face_setup(const float* __restrict__ faces, int B, int F, int Hs, int Ws, Workspace ws) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i < (long)B * F;
+    const int b = in_range ? (int)(i / F) : 0;
+    const int fn = in_range ? (int)(i % F) : 0;
+    bool active = false;
+    int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+    if (in_range) {
+        float f[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) f[k] = faces[(size_t)i * 9 + k];
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < 9; k++) finite = finite && (fabsf(f[k]) <= 3.0e38f);
+        float inv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (finite && !is_backside(f)) {
+            float p[3][2];
+#pragma unroll
+            for (int n = 0; n < 3; n++) { p[n][0] = to_pixel(f[3 * n], Ws); p[n][1] = to_pixel(f[3 * n + 1], Hs); }
+            const float fi[9] = {
+                p[1][1] - p[2][1], p[2][0] - p[1][0], p[1][0] * p[2][1] - p[2][0] * p[1][1],
+                p[2][1] - p[0][1], p[0][0] - p[2][0], p[2][0] * p[0][1] - p[0][0] * p[2][1],
+                p[0][1] - p[1][1], p[1][0] - p[0][0], p[0][0] * p[1][1] - p[1][0] * p[0][1]};
+            const float den = (p[2][0] * (p[0][1] - p[1][1]) + p[0][0] * (p[1][1] - p[2][1])) +
+                              p[1][0] * (p[2][1] - p[0][1]);
+#pragma unroll
+            for (int k = 0; k < 9; k++) inv[k] = __fdiv_rn(fi[k], den);
+            // a zero / non-finite denominator can never produce a finite depth (w -> NaN): never drawn.
+            if (den != 0.0f && fabsf(den) <= 3.0e38f) {
+                const float mxa = fmaxf(fmaxf(fabsf(f[0]), fabsf(f[3])), fabsf(f[6]));
+                const float mya = fmaxf(fmaxf(fabsf(f[1]), fabsf(f[4])), fabsf(f[7]));
+                if (mxa > 64.0f || mya > 64.0f) {       // rounding error may exceed a sample: no bbox culling
+                    x0 = 0; y0 = 0; x1 = Ws - 1; y1 = Hs - 1;
+                } else {                                // conservative by one sample on each side
+                    const float pxmin = fminf(fminf(p[0][0], p[1][0]), p[2][0]);
+                    const float pxmax = fmaxf(fmaxf(p[0][0], p[1][0]), p[2][0]);
+                    const float pymin = fminf(fminf(p[0][1], p[1][1]), p[2][1]);
+                    const float pymax = fmaxf(fmaxf(p[0][1], p[1][1]), p[2][1]);
+                    x0 = max(__float2int_rd(pxmin) - 1, 0);
+                    y0 = max(__float2int_rd(pymin) - 1, 0);
+                    x1 = min(__float2int_ru(pxmax) + 1, Ws - 1);
+                    y1 = min(__float2int_ru(pymax) + 1, Hs - 1);
+                }
+                active = (x0 <= x1) && (y0 <= y1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) ws.face_inv[(size_t)i * 9 + k] = inv[k];
+        short* bb = ws.face_bbox + (size_t)i * 4;
+        if (active) { bb[0] = (short)x0; bb[1] = (short)y0; bb[2] = (short)x1; bb[3] = (short)y1; }
+        else { bb[0] = 1; bb[1] = 1; bb[2] = 0; bb[3] = 0; }
+    }
+    // warp-aggregated append + bbox growth.  A warp may straddle two images: handle per distinct b.
+    const unsigned lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(FULL, active);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int lb = __shfl_sync(FULL, b, leader);
+        const unsigned same = __ballot_sync(FULL, active && b == lb);
+        if (active && b == lb) {
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(&ws.active_count[lb], __popc(same));
+            base = __shfl_sync(same, base, leader);
+            ws.active_ids[(size_t)lb * F + base + __popc(same & ((1u << lane) - 1))] = fn;
+            int a0 = 65535 - x0, a1 = 65535 - y0, a2 = x1 + 1, a3 = y1 + 1;
+            a0 = __reduce_max_sync(same, a0); a1 = __reduce_max_sync(same, a1);
+            a2 = __reduce_max_sync(same, a2); a3 = __reduce_max_sync(same, a3);
+            if ((int)lane == leader) {
+                atomicMax(&ws.img_bbox[lb * 4 + 0], a0); atomicMax(&ws.img_bbox[lb * 4 + 1], a1);
+                atomicMax(&ws.img_bbox[lb * 4 + 2], a2); atomicMax(&ws.img_bbox[lb * 4 + 3], a3);
+            }
+        }
+        todo &= ~same;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tiled forward
+// ------------------------------------------------------------------------------------------------------------
+struct FwdParams {
+    int B, F, H, W, ss, Hs, Ws, flags, ts, batch_bug;
+    Clip clip;
+    double eps;
+    float bg[3];
+    const float* bg_b;
+    const float* faces;
+    const float* textures;
+    float* rgb; float* alpha; float* depth; int32_t* face_index; float* rgb_ss;
+    int tiles_x, tiles_y, num_tiles;
+};
+
+__device__ __forceinline__ void load_bg(const FwdParams& P, int b, float* bg) {
+    if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+    else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+}
+
+// colour of a covered sample (rasterize.py:378-423).  The barycentric weights are recomputed with the visibility
+// arithmetic, so they equal the reference's weight_map entry bit for bit.
+__device__ __forceinline__ void shade_sample(const FwdParams& P, const float* __restrict__ face_inv, int b, int fn,
+                                             int xi, int yi, float depth, float* rgb) {
+    const float* f = P.faces + ((size_t)(P.batch_bug ? 0 : b) * P.F + fn) * 9;   // rasterize.py:390
+    const float* ff = P.faces + ((size_t)b * P.F + fn) * 9;
+    const float* iv = face_inv + ((size_t)b * P.F + fn) * 9;
+    float fr[9], inv[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { fr[k] = __ldg(ff + k); inv[k] = __ldg(iv + k); }
+    float w[3];
+    const float xif = (float)xi, yif = (float)yi;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float t = inv[3 * k + 0] * xif;
+        float u = inv[3 * k + 1] * yif;
+        t = t + u;
+        w[k] = fminf(fmaxf(t + inv[3 * k + 2], 0.0f), 1.0f);
+    }
+    float wsum = w[0] + w[1];
+    wsum = wsum + w[2];
+    w[0] = __fdiv_rn(w[0], wsum); w[1] = __fdiv_rn(w[1], wsum); w[2] = __fdiv_rn(w[2], wsum);
+
+    const int ts = P.ts == 1 ? 2 : P.ts;
+    float zf[9];
+    if (P.batch_bug) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) zf[k] = __ldg(f + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; k++) zf[k] = fr[k];
+    }
+    float tif[3];
+    texture_index(w, depth, zf, ts, P.eps, tif);
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+    if (P.ts == 1) {
+        const float* c = P.textures + ((size_t)b * P.F + fn) * 3;
+        const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) {
+            int tii[3];
+            const float cw = corner_weight(tif, pn, tii);
+            acc[0] = acc[0] + cw * c0; acc[1] = acc[1] + cw * c1; acc[2] = acc[2] + cw * c2;
+        }
+    } else {
+        const float* tex = P.textures + ((size_t)b * P.F + fn) * ts * ts * ts * 3;
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) {
+            int tii[3];
+            const float cw = corner_weight(tif, pn, tii);
+            const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
+            acc[0] = acc[0] + cw * __ldg(tex + isc * 3 + 0);
+            acc[1] = acc[1] + cw * __ldg(tex + isc * 3 + 1);
+            acc[2] = acc[2] + cw * __ldg(tex + isc * 3 + 2);
+        }
+    }
+    rgb[0] = acc[0]; rgb[1] = acc[1]; rgb[2] = acc[2];
+}
+
+__global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) {
+    __shared__ u64 s_key[TH * TW];
+    __shared__ int s_queue[QCAP];
+    __shared__ float s_xp[TW], s_yp[TH];
+    __shared__ int s_qn, s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float far_f = P.clip.far_f;
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(&ws.counters[0], 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= P.num_tiles) break;
+        const int b = tile / (P.tiles_x * P.tiles_y);
+        const int trem = tile % (P.tiles_x * P.tiles_y);
+        const int ty = trem / P.tiles_x, tx = trem % P.tiles_x;
+        const int sx0 = tx * TW, sy0 = ty * TH;
+        const int sx1 = min(sx0 + TW, P.Ws) - 1, sy1 = min(sy0 + TH, P.Hs) - 1;
+
+        const int count = ws.active_count[b];
+        const int ixmin = 65535 - ws.img_bbox[b * 4 + 0], iymin = 65535 - ws.img_bbox[b * 4 + 1];
+        const int ixmax = ws.img_bbox[b * 4 + 2] - 1, iymax = ws.img_bbox[b * 4 + 3] - 1;
+        const bool empty = (count == 0) || ixmin > sx1 || ixmax < sx0 || iymin > sy1 || iymax < sy0;
+
+        if (!empty) {
+            for (int k = tid; k < TH * TW; k += NT) s_key[k] = ~0ull;
+            if (tid < TW) s_xp[tid] = xp_of(sx0 + tid, P.Ws);
+            if (tid < TH) s_yp[tid] = xp_of(sy0 + tid, P.Hs);
+            if (tid == 0) s_qn = 0;
+            __syncthreads();
+            const int* ids = ws.active_ids + (size_t)b * P.F;
+            for (int base = 0; base < count; base += NT) {
+                const int e = base + tid;
+                bool hit = false;
+                int id = -1;
+                if (e < count) {
+                    id = ids[e];
+                    const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + ((size_t)b * P.F + id) * 4);
+                    hit = !(bb.x > sx1 || bb.z < sx0 || bb.y > sy1 || bb.w < sy0);
+                }
+                const unsigned m = __ballot_sync(FULL, hit);
+                int wb = 0;
+                if (lane == 0 && m) wb = atomicAdd(&s_qn, __popc(m));
+                wb = __shfl_sync(FULL, wb, 0);
+                if (hit) s_queue[wb + __popc(m & ((1u << lane) - 1))] = id;
+                __syncthreads();
+                const int qn = s_qn;
+                const bool last = base + NT >= count;
+                if (qn > QCAP - NT || last) {
+                    // ---- face-parallel coverage: one warp per queued face, lanes over an 8x4 sample footprint
+                    for (int q = warp; q < qn; q += NT / 32) {
+                        const int fn = s_queue[q];
+                        const size_t fo = ((size_t)b * P.F + fn);
+                        float f[9], inv[9];
+#pragma unroll
+                        for (int k = 0; k < 9; k++) { f[k] = __ldg(P.faces + fo * 9 + k); inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
+                        const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+                        const int bx0 = max((int)bb.x, sx0), bx1 = min((int)bb.z, sx1);
+                        const int by0 = max((int)bb.y, sy0), by1 = min((int)bb.w, sy1);
+                        for (int yy = by0 + (lane >> 3); yy <= by1; yy += 4) {
+                            const float yp = s_yp[yy - sy0];
+                            const float yif = (float)yy;
+                            for (int xx = bx0 + (lane & 7); xx <= bx1; xx += 8) {
+                                float w[3], zp;
+                                if (eval_sample(f, inv, s_xp[xx - sx0], yp, (float)xx, yif, P.clip, w, zp)) {
+                                    const u64 key = ((u64)__float_as_uint(zp) << 32) | (unsigned)fn;
+                                    atomicMin(&s_key[(yy - sy0) * TW + (xx - sx0)], key);
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) s_qn = 0;
+                    __syncthreads();
+                }
+            }
+        }
+
+        // ---------------- resolve + write (background tiles take the same path with constant keys)
+        float bg[3];
+        load_bg(P, b, bg);
+        const bool want_rgb = (P.flags & SDN_RGB) != 0;
+        // (1) face-index map, int4 rows
+        {
+            int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+            for (int k = tid; k < TH * (TW / 4); k += NT) {
+                const int r = k / (TW / 4), c4 = (k % (TW / 4)) * 4;
+                const int yy = sy0 + r, xx = sx0 + c4;
+                if (yy > sy1 || xx > sx1) continue;
+                int v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] = empty ? -1 : (int)(unsigned)(s_key[r * TW + c4 + j] & 0xffffffffu);
+                int32_t* dst = fim + (size_t)yy * P.Ws + xx;
+                if (xx + 3 <= sx1 && ((P.Ws & 3) == 0)) *reinterpret_cast<int4*>(dst) = make_int4(v[0], v[1], v[2], v[3]);
+                else for (int j = 0; j < 4 && xx + j <= sx1; j++) dst[j] = v[j];
+                if (!empty) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (v[j] >= 0) ws.visible[(size_t)b * P.F + v[j]] = 1;
+                }
+            }
+        }
+        // (2) colour / alpha / depth, one output pixel (ss x ss samples) per thread-iteration
+        const int ss = P.ss;
+        const int ow = TW / ss, oh = TH / ss;
+        for (int k = tid; k < ow * oh; k += NT) {
+            const int orow = k / ow, ocol = k % ow;
+            const int ox = sx0 / ss + ocol, oyr = sy0 / ss + orow;    // oyr: row in raster orientation
+            if (ox >= P.W || oyr >= P.H) continue;
+            float a_sum = 0.0f, d_sum = 0.0f, c_sum[3] = {0.0f, 0.0f, 0.0f};
+            for (int j = 0; j < ss * ss; j++) {
+                const int lx = ocol * ss + (j % ss), ly = orow * ss + (j / ss);
+                int fn = -1;
+                float zp = far_f;
+                if (!empty) {
+                    const u64 key = s_key[ly * TW + lx];
+                    fn = (int)(unsigned)(key & 0xffffffffu);
+                    if (fn >= 0) zp = __uint_as_float((unsigned)(key >> 32));
+                }
+                float col[3] = {bg[0], bg[1], bg[2]};
+                if (fn >= 0) {
+                    a_sum += 1.0f;
+                    if (want_rgb) shade_sample(P, ws.face_inv, b, fn, sx0 + lx, sy0 + ly, zp, col);
+                }
+                d_sum += zp;
+                c_sum[0] += col[0]; c_sum[1] += col[1]; c_sum[2] += col[2];
+                if (want_rgb && P.rgb_ss) {
+                    float* o = P.rgb_ss + (((size_t)b * P.Hs + (sy0 + ly)) * P.Ws + (sx0 + lx)) * 3;
+                    o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
+                }
+            }
+            const float scale = (ss == 2) ? 0.25f : 1.0f;
+            const int oy = P.H - 1 - oyr;                               // rasterize.py:953-957 row flip
+            const size_t po = (size_t)oy * P.W + ox;
+            if (P.flags & SDN_ALPHA) P.alpha[(size_t)b * P.H * P.W + po] = a_sum * scale;
+            if (P.flags & SDN_DEPTH) P.depth[(size_t)b * P.H * P.W + po] = d_sum * scale;
+            if (want_rgb) {
+                P.rgb[((size_t)b * 3 + 0) * P.H * P.W + po] = c_sum[0] * scale;
+                P.rgb[((size_t)b * 3 + 1) * P.H * P.W + po] = c_sum[1] * scale;
+                P.rgb[((size_t)b * 3 + 2) * P.H * P.W + po] = c_sum[2] * scale;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// visible-face compaction for the backward
+__global__ void k_compact_visible(int B, int F, Workspace ws) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i < (long)B * F;
+    const int b = in_range ? (int)(i / F) : 0, fn = in_range ? (int)(i % F) : 0;
+    const bool vis = in_range && ws.visible[i];
+    const unsigned lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(FULL, vis);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int lb = __shfl_sync(FULL, b, leader);
+        const unsigned same = __ballot_sync(FULL, vis && b == lb);
+        if (vis && b == lb) {
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(&ws.vis_count[lb], __popc(same));
+            base = __shfl_sync(same, base, leader);
+            ws.vis_ids[(size_t)lb * F + base + __popc(same & ((1u << lane) - 1))] = fn;
+        }
+        todo &= ~same;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+struct BwdParams {
+    int B, F, H, W, ss, Hs, Ws, flags, ts, batch_bug;
+    Clip clip;
+    double eps_tex;
+    int use_alpha, use_rgb, use_depth;      // which outputs the forward had (K6 runs iff alpha|rgb)
+    int split;                              // 1: alpha and rgb are separate reference passes
+    double eps_a, eps_r;                    // K6 pads (equal unless split)
+    int fast_math;
+    float bg[3];
+    const float* bg_b;
+    const float* faces;
+    const float* textures;
+    const int32_t* face_index;
+    const float* rgb_ss;
+    const float* g_rgb; const float* g_alpha; const float* g_depth;
+    float* grad_textures;
+};
+
+// gradient of the SS raster sample (xi, yi): avg-pool backward (x 1/ss^2) + row un-flip
+__device__ __forceinline__ size_t out_index(const BwdParams& P, int xi, int yi) {
+    return (size_t)(P.H - 1 - yi / P.ss) * P.W + xi / P.ss;
+}
+
+struct PixelRef { float alpha; float c[3]; };
+
+__device__ __forceinline__ void colour_at(const BwdParams& P, int b, size_t mi, int idx, const float* bg, float* c) {
+    if (P.ts >= 2) {
+        const float* s = P.rgb_ss + mi * 3;
+        c[0] = s[0]; c[1] = s[1]; c[2] = s[2];
+    } else if (idx >= 0) {
+        const float* s = P.textures + ((size_t)b * P.F + idx) * 3;
+        c[0] = __ldg(s); c[1] = __ldg(s + 1); c[2] = __ldg(s + 2);
+    } else { c[0] = bg[0]; c[1] = bg[1]; c[2] = bg[2]; }
+}
+
+// dist of rasterize.py:646-647 for numerator a, denominator b (a/b hoisted in q)
+__device__ __forceinline__ float k6_dist(float q, float t, float isf, double eps) {
+    float d = q * t;
+    d = __fdiv_rn(d * 2.0f, isf);
+    return (0.0f < d) ? (float)((double)d + eps) : (float)((double)d - eps);
+}
+
+struct SweepCtx {
+    // per (item, d0) constants
+    float d1_cross, q0, q1;     // q0 = (p10-p00)/(p10-d0), q1 = (p10-p00)/(d0-p00)
+    bool use0, use1;            // p10 != d0, p00 != d0
+    float ref_alpha, ref_c[3];  // alpha_in / rgb_in for the out sweep, *_out for the in sweep
+};
+
+// one visited pixel of a sweep: accumulates into g0 (vertex pi[0]) and g1 (vertex pi[1])
+__device__ __forceinline__ void visit(const BwdParams& P, int b, const float* bg, size_t mi, int idx, int xi, int yi,
+                                      int d1, const SweepCtx& s, float is1f, float& g0, float& g1) {
+    const size_t oi = out_index(P, xi, yi);
+    const float sc = (P.ss == 2) ? 0.25f : 1.0f;
+    float da = 0.0f, dr = 0.0f;
+    if (P.use_alpha) {
+        const float ga = P.g_alpha ? P.g_alpha[(size_t)b * P.H * P.W + oi] * sc : 0.0f;
+        const float alpha = idx >= 0 ? 1.0f : 0.0f;
+        da = (alpha - s.ref_alpha) * ga;
+    }
+    if (P.use_rgb) {
+        float c[3];
+        colour_at(P, b, mi, idx, bg, c);
+        float g[3] = {0.0f, 0.0f, 0.0f};
+        if (P.g_rgb) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) g[k] = P.g_rgb[((size_t)b * 3 + k) * P.H * P.W + oi] * sc;
+        }
+        if (P.split || !P.use_alpha) {
+            dr = (c[0] - s.ref_c[0]) * g[0];
+            dr = dr + (c[1] - s.ref_c[1]) * g[1];
+            dr = dr + (c[2] - s.ref_c[2]) * g[2];
+        } else {        // one reference pass: alpha term first, then the three colour terms (rasterize.py:628-635)
+            da = da + (c[0] - s.ref_c[0]) * g[0];
+            da = da + (c[1] - s.ref_c[1]) * g[1];
+            da = da + (c[2] - s.ref_c[2]) * g[2];
+        }
+    }
+    const float t = (float)d1 - s.d1_cross;
+    if (da > 0.0f) {
+        const double eps = P.eps_a;
+        if (P.fast_math) {
+            if (s.use0) { float d = s.q0 * t * (2.0f / is1f); d += copysignf((float)eps, d); g0 -= da * __frcp_rn(d); }
+            if (s.use1) { float d = s.q1 * t * (2.0f / is1f); d += copysignf((float)eps, d); g1 -= da * __frcp_rn(d); }
+        } else {
+            if (s.use0) g0 -= __fdiv_rn(da, k6_dist(s.q0, t, is1f, eps));
+            if (s.use1) g1 -= __fdiv_rn(da, k6_dist(s.q1, t, is1f, eps));
+        }
+    }
+    if (dr > 0.0f) {
+        const double eps = P.eps_r;
+        if (P.fast_math) {
+            if (s.use0) { float d = s.q0 * t * (2.0f / is1f); d += copysignf((float)eps, d); g0 -= dr * __frcp_rn(d); }
+            if (s.use1) { float d = s.q1 * t * (2.0f / is1f); d += copysignf((float)eps, d); g1 -= dr * __frcp_rn(d); }
+        } else {
+            if (s.use0) g0 -= __fdiv_rn(dr, k6_dist(s.q0, t, is1f, eps));
+            if (s.use1) g1 -= __fdiv_rn(dr, k6_dist(s.q1, t, is1f, eps));
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// items per visible face: 0..5 = (edge, axis) of K6, 6 = interior gather (K8 + texture gradient)
+constexpr int ITEMS = 7;
+constexpr int BWD_WARPS = 8;
+
+__global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, Workspace ws) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int nvis = ws.vis_count[b];
+    const int nitems = nvis * ITEMS;
+    const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+    const size_t base_px = (size_t)b * P.Hs * P.Ws;
+    float bg[3];
+    if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+    else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+
+    for (int it = blockIdx.x * BWD_WARPS + (threadIdx.x >> 5); it < nitems; it += gridDim.x * BWD_WARPS) {
+        const int fn = ws.vis_ids[(size_t)b * P.F + it / ITEMS];
+        const int kind = it % ITEMS;
+        const size_t fo = (size_t)b * P.F + fn;
+        float f[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) f[k] = __ldg(P.faces + fo * 9 + k);
+
+        if (kind == 6) {
+            // ---------------- interior gather: samples this face won
+            float S[3] = {0.0f, 0.0f, 0.0f}, G[3] = {0.0f, 0.0f, 0.0f};
+            const bool need_depth = P.use_depth && P.g_depth;
+            const bool need_tex = P.use_rgb && P.g_rgb && P.grad_textures;
+            if (need_depth || need_tex) {
+                float inv[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) inv[k] = __ldg(ws.face_inv + fo * 9 + k);
+                const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+                const float sc = (P.ss == 2) ? 0.25f : 1.0f;
+                const int ts = P.ts == 1 ? 2 : P.ts;
+                float zf[9];
+                const float* zsrc = P.faces + ((size_t)(P.batch_bug ? 0 : b) * P.F + fn) * 9;
+#pragma unroll
+                for (int k = 0; k < 9; k++) zf[k] = __ldg(zsrc + k);
+                for (int yy = bb.y + (lane >> 3); yy <= bb.w; yy += 4) {
+                    const float yp = xp_of(yy, P.Hs);
+                    for (int xx = bb.x + (lane & 7); xx <= bb.z; xx += 8) {
+                        if (fim[(size_t)yy * P.Ws + xx] != fn) continue;
+                        float w[3], zp;
+                        if (!eval_sample(f, inv, xp_of(xx, P.Ws), yp, (float)xx, (float)yy, P.clip, w, zp)) continue;
+                        const size_t oi = out_index(P, xx, yy);
+                        if (need_depth) {      // rasterize.py:821-824: sum_s gd * w_k * depth^2
+                            const float gd = P.g_depth[(size_t)b * P.H * P.W + oi] * sc;
+                            const float d2 = zp * zp;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) S[k] += gd * w[k] * d2;
+                        }
+                        if (need_tex) {        // rasterize.py:772-778
+                            float g[3];
+#pragma unroll
+                            for (int k = 0; k < 3; k++) g[k] = P.g_rgb[((size_t)b * 3 + k) * P.H * P.W + oi] * sc;
+                            float tif[3];
+                            texture_index(w, zp, zf, ts, P.eps_tex, tif);
+                            if (P.ts == 1) {
+                                float wsum = 0.0f;
+#pragma unroll
+                                for (int pn = 0; pn < 8; pn++) { int tii[3]; wsum += corner_weight(tif, pn, tii); }
+#pragma unroll
+                                for (int k = 0; k < 3; k++) G[k] += wsum * g[k];
+                            } else {
+                                float* gt = P.grad_textures + fo * ts * ts * ts * 3;
+#pragma unroll
+                                for (int pn = 0; pn < 8; pn++) {
+                                    int tii[3];
+                                    const float cw = corner_weight(tif, pn, tii);
+                                    const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
+#pragma unroll
+                                    for (int k = 0; k < 3; k++) atomicAdd(gt + isc * 3 + k, cw * g[k]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) { S[k] = warp_sum(S[k]); G[k] = warp_sum(G[k]); }
+            if (lane == 0) {
+                float* o = ws.gint + fo * 6;
+                o[0] = S[0]; o[1] = S[1]; o[2] = S[2]; o[3] = G[0]; o[4] = G[1]; o[5] = G[2];
+            }
+            continue;
+        }
+
+        // ---------------- K6 item (edge, axis)   rasterize.py:540-729
+        const int edge = kind >> 1, axis = kind & 1;
+        float g0 = 0.0f, g1 = 0.0f;
+        if (P.use_alpha || P.use_rgb) {
+            int pi[3];
+            float pp[3][2], p[3][2];
+#pragma unroll
+            for (int n = 0; n < 3; n++) pi[n] = (edge + n) % 3;
+#pragma unroll
+            for (int n = 0; n < 3; n++) { pp[n][0] = to_pixel(f[3 * pi[n]], P.Ws); pp[n][1] = to_pixel(f[3 * pi[n] + 1], P.Hs); }
+#pragma unroll
+            for (int n = 0; n < 3; n++) { p[n][0] = pp[n][axis]; p[n][1] = pp[n][1 - axis]; }
+            const int is0 = axis == 0 ? P.Ws : P.Hs, is1 = axis == 0 ? P.Hs : P.Ws;
+            const float is1f = (float)is1;
+            int direction;
+            if (axis == 0) direction = (p[0][0] < p[1][0]) ? -1 : 1;
+            else direction = (p[0][0] < p[1][0]) ? 1 : -1;
+            const int d0_from = __double2int_rz(fmax((double)ceilf(fminf(p[0][0], p[1][0])), 0.));
+            const int d0_to = __double2int_rz(fmin((double)fmaxf(p[0][0], p[1][0]), is0 - 1.));
+            const float slope = __fdiv_rn(p[1][1] - p[0][1], p[1][0] - p[0][0]);
+            const float dp = p[1][0] - p[0][0];
+
+            for (int sbase = d0_from; sbase <= d0_to; sbase += 32) {
+                const int d0 = sbase + lane;
+                const float d0f = (float)d0;
+                bool valid = d0 <= d0_to;
+                SweepCtx so;     // out-sweep context (refs = in pixel)
+                SweepCtx si;     // in-sweep context (refs = out pixel)
+                int d1_in = 0, d1_out = 0;
+                bool is_in_fn = false;
+                {
+                    float dc = slope * (d0f - p[0][0]);
+                    dc = dc + p[0][1];
+                    so.d1_cross = dc;
+                    d1_in = (0 < direction) ? __float2int_rz(floorf(dc)) : __float2int_rz(ceilf(dc));
+                    if (d1_in < 0 || is1 <= d1_in) valid = false;
+                    d1_out = d1_in + direction;
+                    if (valid && (d1_out < 0 || is1 <= d1_out)) valid = false;
+                    so.use0 = p[1][0] != d0f; so.use1 = p[0][0] != d0f;
+                    so.q0 = __fdiv_rn(dp, p[1][0] - d0f); so.q1 = __fdiv_rn(dp, d0f - p[0][0]);
+                    si = so;
+                }
+                if (valid) {
+                    const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
+                    const int xout = axis == 0 ? d0 : d1_out, yout = axis == 0 ? d1_out : d0;
+                    const size_t mi_in = (size_t)yin * P.Ws + xin, mi_out = (size_t)yout * P.Ws + xout;
+                    const int idx_in = fim[mi_in], idx_out = fim[mi_out];
+                    is_in_fn = idx_in == fn;
+                    so.ref_alpha = idx_in >= 0 ? 1.0f : 0.0f;
+                    si.ref_alpha = idx_out >= 0 ? 1.0f : 0.0f;
+                    if (P.use_rgb) {
+                        colour_at(P, b, base_px + mi_in, idx_in, bg, so.ref_c);
+                        colour_at(P, b, base_px + mi_out, idx_out, bg, si.ref_c);
+                    }
+                    // ---- in sweep (short, lane-serial)   rasterize.py:659-727
+                    float dc2;
+                    if ((d0f - p[0][0]) * (d0f - p[2][0]) < 0) {
+                        dc2 = __fdiv_rn(p[2][1] - p[0][1], p[2][0] - p[0][0]);
+                        dc2 = dc2 * (d0f - p[0][0]);
+                        dc2 = dc2 + p[0][1];
+                    } else {
+                        dc2 = __fdiv_rn(p[1][1] - p[2][1], p[1][0] - p[2][0]);
+                        dc2 = dc2 * (d0f - p[2][0]);
+                        dc2 = dc2 + p[2][1];
+                    }
+                    const int d1_limit = (0 < direction) ? __float2int_rz(ceilf(dc2)) : __float2int_rz(floorf(dc2));
+                    const int d1_from = max(min(d1_in, d1_limit), 0);
+                    const int d1_to = min(max(d1_in, d1_limit), is1 - 1);
+                    for (int d1 = d1_from; d1 <= d1_to; d1++) {
+                        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+                        const size_t mi = (size_t)yi * P.Ws + xi;
+                        if (fim[mi] != fn) continue;
+                        visit(P, b, bg, base_px + mi, fn, xi, yi, d1, si, is1f, g0, g1);
+                    }
+                }
+                // ---- out sweeps   rasterize.py:601-656
+                const bool sweep = valid && is_in_fn;
+                if (axis == 0) {
+                    // vertical: every lane owns a column; iterate absolute rows so loads stay coalesced
+                    const int d1_limit = (0 < direction) ? is1 - 1 : 0;
+                    int lo = max(min(d1_out, d1_limit), 0), hi = min(max(d1_out, d1_limit), is1 - 1);
+                    if (!sweep) { lo = 1; hi = 0; }
+                    int wlo = sweep ? lo : 0x7fffffff, whi = sweep ? hi : -1;
+                    wlo = __reduce_min_sync(FULL, wlo); whi = __reduce_max_sync(FULL, whi);
+                    for (int d1 = wlo; d1 <= whi; d1++) {
+                        if (d1 < lo || d1 > hi) continue;
+                        const size_t mi = (size_t)d1 * P.Ws + d0;
+                        visit(P, b, bg, base_px + mi, fim[mi], d0, d1, d1, so, is1f, g0, g1);
+                    }
+                } else {
+                    // horizontal: the warp takes the steps one at a time, lanes stride along the row
+                    unsigned todo = __ballot_sync(FULL, sweep);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        SweepCtx s;
+                        s.d1_cross = __shfl_sync(FULL, so.d1_cross, src);
+                        s.q0 = __shfl_sync(FULL, so.q0, src); s.q1 = __shfl_sync(FULL, so.q1, src);
+                        s.use0 = __shfl_sync(FULL, (int)so.use0, src); s.use1 = __shfl_sync(FULL, (int)so.use1, src);
+                        s.ref_alpha = __shfl_sync(FULL, so.ref_alpha, src);
+#pragma unroll
+                        for (int k = 0; k < 3; k++) s.ref_c[k] = __shfl_sync(FULL, so.ref_c[k], src);
+                        const int row = sbase + src;
+                        const int dout = __shfl_sync(FULL, d1_out, src);
+                        const int d1_limit = (0 < direction) ? is1 - 1 : 0;
+                        const int lo = max(min(dout, d1_limit), 0), hi = min(max(dout, d1_limit), is1 - 1);
+                        for (int d1 = lo + lane; d1 <= hi; d1 += 32) {
+                            const size_t mi = (size_t)row * P.Ws + d1;
+                            visit(P, b, bg, base_px + mi, fim[mi], d1, row, d1, s, is1f, g0, g1);
+                        }
+                    }
+                }
+            }
+        }
+        g0 = warp_sum(g0); g1 = warp_sum(g1);
+        if (lane == 0) { ws.gpart[fo * 12 + kind * 2 + 0] = g0; ws.gpart[fo * 12 + kind * 2 + 1] = g1; }
+    }
+}
+
+// deterministic assembly of grad_faces [B,F,9] (+ per-face colour gradient when ts == 1)
+__global__ void k_grad_assemble(BwdParams P, Workspace ws, float* __restrict__ grad_faces) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)P.B * P.F) return;
+    float g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float gc[3] = {0, 0, 0};
+    if (ws.visible[i]) {
+        const float* part = ws.gpart + (size_t)i * 12;
+        if (P.use_alpha || P.use_rgb) {
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int axis = 1 - c;
+                    // vertex v is pi[0] of edge v and pi[1] of edge (v+2)%3   (rasterize.py:544,648,653)
+                    g[3 * v + c] = part[(v * 2 + axis) * 2 + 0] + part[(((v + 2) % 3) * 2 + axis) * 2 + 1];
+                }
+            }
+        }
+        const float* in = ws.gint + (size_t)i * 6;
+        if (P.use_depth && P.g_depth) {     // rasterize.py:820-834 with the per-face constants factored out
+            const float* f = P.faces + (size_t)i * 9;
+            const float* inv = ws.face_inv + (size_t)i * 9;
+            float tmp[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int l = 0; l < 3; l++) tmp[k] += -inv[3 * l + k] / f[3 * l + 2];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float zk = f[3 * k + 2];
+                g[3 * k + 2] += in[k] / (zk * zk);
+                g[3 * k + 0] += -tmp[0] * in[k] * (float)P.Ws / 2.0f;
+                g[3 * k + 1] += -tmp[1] * in[k] * (float)P.Hs / 2.0f;
+            }
+        }
+        gc[0] = in[3]; gc[1] = in[4]; gc[2] = in[5];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) grad_faces[(size_t)i * 9 + k] = g[k];
+    if (P.ts == 1 && P.grad_textures && P.use_rgb) {
+        P.grad_textures[(size_t)i * 3 + 0] = gc[0];
+        P.grad_textures[(size_t)i * 3 + 1] = gc[1];
+        P.grad_textures[(size_t)i * 3 + 2] = gc[2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// faces backward: scatter onto vertices, then chain rule
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_faces_backward_scatter(const float* __restrict__ g_ndc, const float* __restrict__ g_nrm,
+                                         const float* __restrict__ vertices, const int32_t* __restrict__ faces,
+                                         int B, int nv, int nf, int faces_batched, int fill_back, float flip,
+                                         float* __restrict__ acc_ndc, float* __restrict__ acc_pre) {
+    const int F = fill_back ? 2 * nf : nf;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * F) return;
+    const int b = (int)(i / F), fn = (int)(i % F);
+    const int src = fn < nf ? fn : fn - nf;
+    const int32_t* tri = faces + ((size_t)(faces_batched ? b : 0) * nf + src) * 3;
+    int vid[3] = {tri[0], tri[1], tri[2]};
+    if (fn >= nf) { int t = vid[0]; vid[0] = vid[2]; vid[2] = t; }
+    if (g_ndc) {
+        const float* g = g_ndc + (size_t)i * 9;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float* a = acc_ndc + ((size_t)b * nv + vid[k]) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { const float v = g[3 * k + c]; if (v != 0.0f) atomicAdd(a + c, v); }
+        }
+    }
+    if (g_nrm) {
+        const float gn[3] = {g_nrm[(size_t)i * 3] * flip, g_nrm[(size_t)i * 3 + 1], g_nrm[(size_t)i * 3 + 2]};
+        if (gn[0] != 0.0f || gn[1] != 0.0f || gn[2] != 0.0f) {
+            float pre[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float* v = vertices + ((size_t)b * nv + vid[k]) * 3;
+                pre[k][0] = v[0] * flip; pre[k][1] = v[1]; pre[k][2] = v[2];
+            }
+            const float a[3] = {pre[0][0] - pre[1][0], pre[0][1] - pre[1][1], pre[0][2] - pre[1][2]};
+            const float bb[3] = {pre[2][0] - pre[1][0], pre[2][1] - pre[1][1], pre[2][2] - pre[1][2]};
+            const float c[3] = {a[1] * bb[2] - a[2] * bb[1], a[2] * bb[0] - a[0] * bb[2], a[0] * bb[1] - a[1] * bb[0]};
+            const float len = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+            const float norm = len + 1e-5f;
+            // y = c / (|c| + eps):  gc = gn/norm - c * (gn.c) / (|c| * norm^2)
+            const float dot = gn[0] * c[0] + gn[1] * c[1] + gn[2] * c[2];
+            const float k2 = len > 0.0f ? dot / (len * norm * norm) : 0.0f;
+            const float gc[3] = {gn[0] / norm - c[0] * k2, gn[1] / norm - c[1] * k2, gn[2] / norm - c[2] * k2};
+            // c = a x b : ga = b x gc, gb = gc x a      (cross.py:53-57)
+            const float ga[3] = {bb[1] * gc[2] - bb[2] * gc[1], bb[2] * gc[0] - bb[0] * gc[2], bb[0] * gc[1] - bb[1] * gc[0]};
+            const float gb[3] = {gc[1] * a[2] - gc[2] * a[1], gc[2] * a[0] - gc[0] * a[2], gc[0] * a[1] - gc[1] * a[0]};
+            float* p0 = acc_pre + ((size_t)b * nv + vid[0]) * 3;
+            float* p1 = acc_pre + ((size_t)b * nv + vid[1]) * 3;
+            float* p2 = acc_pre + ((size_t)b * nv + vid[2]) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                atomicAdd(p0 + k, ga[k]);
+                atomicAdd(p2 + k, gb[k]);
+                atomicAdd(p1 + k, -(ga[k] + gb[k]));
+            }
+        }
+    }
+}
+
+__global__ void k_faces_backward_vertex(const float* __restrict__ vertices, int B, int nv, CamDev cam,
+                                        const float* __restrict__ acc_ndc, const float* __restrict__ acc_pre,
+                                        float* __restrict__ grad_vertices) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * nv) return;
+    const int b = (int)(i / nv);
+    const float* v = vertices + (size_t)i * 3;
+    // recompute the camera-space position (needed by the quotient rule)
+    float x = v[0] * cam.flip, y = v[1], z = v[2];
+    if (cam.eye) { x -= cam.eye[b * 3]; y -= cam.eye[b * 3 + 1]; z -= cam.eye[b * 3 + 2]; }
+    if (cam.rot) {
+        const float* r = cam.rot + b * 9;
+        const float ox = x * r[0] + y * r[1] + z * r[2];
+        const float oy = x * r[3] + y * r[4] + z * r[5];
+        const float oz = x * r[6] + y * r[7] + z * r[8];
+        x = ox; y = oy; z = oz;
+    }
+    float gx = acc_ndc[(size_t)i * 3], gy = acc_ndc[(size_t)i * 3 + 1], gz = acc_ndc[(size_t)i * 3 + 2];
+    if (cam.wx) {       // x' = x / z / wx
+        const float wx = cam.wx[b], wy = cam.wy[b];
+        const float ix = 1.0f / (z * wx), iy = 1.0f / (z * wy);
+        const float ngx = gx * ix, ngy = gy * iy;
+        gz = gz - (gx * x * ix + gy * y * iy) / z;
+        gx = ngx; gy = ngy;
+    }
+    if (cam.rot) {      // v' = R v  ->  g = R^T g'
+        const float* r = cam.rot + b * 9;
+        const float ox = r[0] * gx + r[3] * gy + r[6] * gz;
+        const float oy = r[1] * gx + r[4] * gy + r[7] * gz;
+        const float oz = r[2] * gx + r[5] * gy + r[8] * gz;
+        gx = ox; gy = oy; gz = oz;
+    }
+    gx += acc_pre[(size_t)i * 3]; gy += acc_pre[(size_t)i * 3 + 1]; gz += acc_pre[(size_t)i * 3 + 2];
+    grad_vertices[(size_t)i * 3] = gx * cam.flip;
+    grad_vertices[(size_t)i * 3 + 1] = gy;
+    grad_vertices[(size_t)i * 3 + 2] = gz;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------------------
+inline int check_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaPeekAtLastError();
+}
+
+Clip make_clip(double near_, double far_) {
+    Clip c;
+    c.near_ = near_; c.far_ = far_; c.far_f = (float)far_;
+    return c;
+}
+
+int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+}
+
+CamDev make_cam(const sdn_camera* cam) {
+    CamDev c;
+    c.rot = cam ? cam->rot : nullptr; c.eye = cam ? cam->eye : nullptr;
+    c.wx = cam ? cam->width_x : nullptr; c.wy = cam ? cam->width_y : nullptr;
+    c.flip = cam ? cam->flip_x : 1.0f;
+    return c;
+}
+
+int validate(const sdn_raster* r, bool need_outputs = true) {
+    if (!r || r->B <= 0 || r->F <= 0 || r->H <= 0 || r->W <= 0) return SDN_E_ARG;
+    if (r->ss != 1 && r->ss != 2) return SDN_E_ARG;
+    if ((r->flags & (SDN_RGB | SDN_ALPHA | SDN_DEPTH)) == 0) return SDN_E_NOTHING;
+    if (!r->faces || !r->face_index || !r->workspace) return SDN_E_ARG;
+    if ((r->flags & SDN_RGB) && (!r->textures || r->texture_size < 1)) return SDN_E_ARG;
+    if (need_outputs) {
+        if ((r->flags & SDN_RGB) && !r->rgb) return SDN_E_ARG;
+        if ((r->flags & SDN_ALPHA) && !r->alpha) return SDN_E_ARG;
+        if ((r->flags & SDN_DEPTH) && !r->depth) return SDN_E_ARG;
+    }
+    if ((long)r->H * r->ss > 32767 || (long)r->W * r->ss > 32767) return SDN_E_ARG;
+    if (r->workspace_bytes < sdn_workspace_bytes(r->B, r->F, r->H * r->ss, r->W * r->ss)) return SDN_E_WORKSPACE;
+    return 0;
+}
+
+int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, double eps_a, double eps_r, void* stream_) {
+    int rc = validate(r, false);
+    if (rc) return rc;
+    if (!g || !g->grad_faces) return SDN_E_ARG;
+    if ((r->flags & SDN_RGB) && r->texture_size >= 2 && !r->rgb_ss) return SDN_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    Workspace ws = make_ws(r->workspace, r->B, r->F);
+    BwdParams P;
+    P.B = r->B; P.F = r->F; P.H = r->H; P.W = r->W; P.ss = r->ss; P.Hs = r->H * r->ss; P.Ws = r->W * r->ss;
+    P.flags = r->flags; P.ts = r->texture_size; P.batch_bug = r->batch_bug;
+    P.clip = make_clip(r->near, r->far);
+    P.eps_tex = r->eps;
+    P.use_alpha = (r->flags & SDN_ALPHA) ? 1 : 0; P.use_rgb = (r->flags & SDN_RGB) ? 1 : 0;
+    P.use_depth = (r->flags & SDN_DEPTH) ? 1 : 0;
+    P.split = split; P.eps_a = eps_a; P.eps_r = eps_r; P.fast_math = g->fast_math;
+    P.bg[0] = r->background[0]; P.bg[1] = r->background[1]; P.bg[2] = r->background[2]; P.bg_b = r->background_b;
+    P.faces = r->faces; P.textures = r->textures; P.face_index = r->face_index; P.rgb_ss = r->rgb_ss;
+    P.g_rgb = P.use_rgb ? g->grad_rgb : nullptr;
+    P.g_alpha = P.use_alpha ? g->grad_alpha : nullptr;
+    P.g_depth = P.use_depth ? g->grad_depth : nullptr;
+    P.grad_textures = P.use_rgb ? g->grad_textures : nullptr;
+
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(ws.vis_count, 0, sizeof(int) * r->B, st)) != cudaSuccess) return (int)e;
+    if (P.grad_textures && P.ts >= 2) {
+        const size_t nb = (size_t)r->B * r->F * P.ts * P.ts * P.ts * 3 * sizeof(float);
+        if ((e = cudaMemsetAsync(P.grad_textures, 0, nb, st)) != cudaSuccess) return (int)e;
+    }
+    const long BF = (long)r->B * r->F;
+    k_compact_visible<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(r->B, r->F, ws);
+    if ((rc = check_launch())) return rc;
+    dim3 grid((unsigned)max(1, sm_count() * 4 / max(1, min(r->B, sm_count() * 4))), (unsigned)r->B);
+    k_backward_items<<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+    if ((rc = check_launch())) return rc;
+    k_grad_assemble<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(P, ws, g->grad_faces);
+    return check_launch();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sdn_version(void) { return SDN_VERSION; }
+
+long long sdn_launch_count(void) { return g_launches.load(); }
+
+const char* sdn_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == SDN_E_ARG) return "sdn: invalid argument";
+    if (code == SDN_E_WORKSPACE) return "sdn: workspace too small";
+    if (code == SDN_E_NOTHING) return "sdn: nothing to draw (no SDN_RGB/SDN_ALPHA/SDN_DEPTH flag)";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "sdn: unknown error";
+}
+
+size_t sdn_workspace_bytes(int B, int F, int Hs, int Ws) {
+    (void)Hs; (void)Ws;
+    if (B <= 0 || F <= 0) return 0;
+    return make_ws(nullptr, B, F).total;
+}
+
+int sdn_faces_forward(const float* vertices, const int32_t* faces, int B, int nv, int nf, int faces_batched,
+                      int fill_back, const sdn_camera* cam, float* face_ndc, float* face_normal, void* stream) {
+    if (!vertices || !faces || !face_ndc || B <= 0 || nv <= 0 || nf <= 0) return SDN_E_ARG;
+    if (cam && cam->width_x && !cam->width_y) return SDN_E_ARG;
+    const long n = (long)B * (fill_back ? 2 * nf : nf);
+    k_faces_forward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        vertices, faces, B, nv, nf, faces_batched, fill_back, make_cam(cam), face_ndc, face_normal);
+    return check_launch();
+}
+
+int sdn_faces_backward(const float* grad_face_ndc, const float* grad_face_normal, const float* vertices,
+                       const int32_t* faces, int B, int nv, int nf, int faces_batched, int fill_back,
+                       const sdn_camera* cam, float* grad_vertices, void* scratch, size_t scratch_bytes,
+                       void* stream) {
+    if (!vertices || !faces || !grad_vertices || !scratch || B <= 0 || nv <= 0 || nf <= 0) return SDN_E_ARG;
+    const size_t need = (size_t)2 * B * nv * 3 * sizeof(float);
+    if (scratch_bytes < need) return SDN_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, need, st);
+    if (e != cudaSuccess) return (int)e;
+    float* acc_ndc = (float*)scratch;
+    float* acc_pre = acc_ndc + (size_t)B * nv * 3;
+    const CamDev c = make_cam(cam);
+    const long n = (long)B * (fill_back ? 2 * nf : nf);
+    int rc;
+    if (grad_face_ndc || grad_face_normal) {
+        k_faces_backward_scatter<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            grad_face_ndc, grad_face_normal, vertices, faces, B, nv, nf, faces_batched, fill_back, c.flip, acc_ndc,
+            acc_pre);
+        if ((rc = check_launch())) return rc;
+    }
+    const long nvt = (long)B * nv;
+    k_faces_backward_vertex<<<(unsigned)((nvt + 255) / 256), 256, 0, st>>>(vertices, B, nv, c, acc_ndc, acc_pre,
+                                                                           grad_vertices);
+    return check_launch();
+}
+
+int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
+    int rc = validate(r);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream_;
+    Workspace ws = make_ws(r->workspace, r->B, r->F);
+    cudaError_t e = cudaMemsetAsync(r->workspace, 0, ws.zero_bytes, st);
+    if (e != cudaSuccess) return (int)e;
+    const int Hs = r->H * r->ss, Wss = r->W * r->ss;
+    const long BF = (long)r->B * r->F;
+    k_face_setup<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(r->faces, r->B, r->F, Hs, Wss, ws);
+    if ((rc = check_launch())) return rc;
+
+    FwdParams P;
+    P.B = r->B; P.F = r->F; P.H = r->H; P.W = r->W; P.ss = r->ss; P.Hs = Hs; P.Ws = Wss;
+    P.flags = r->flags; P.ts = r->texture_size; P.batch_bug = r->batch_bug;
+    P.clip = make_clip(r->near, r->far);
+    P.eps = r->eps;
+    P.bg[0] = r->background[0]; P.bg[1] = r->background[1]; P.bg[2] = r->background[2]; P.bg_b = r->background_b;
+    P.faces = r->faces; P.textures = r->textures;
+    P.rgb = r->rgb; P.alpha = r->alpha; P.depth = r->depth; P.face_index = r->face_index; P.rgb_ss = r->rgb_ss;
+    P.tiles_x = (Wss + TW - 1) / TW; P.tiles_y = (Hs + TH - 1) / TH;
+    P.num_tiles = P.tiles_x * P.tiles_y * r->B;
+    const int grid = min(P.num_tiles, sm_count() * 6);
+    k_raster_tiles<<<grid, NT, 0, st>>>(P, ws);
+    return check_launch();
+}
+
+int sdn_rasterize_backward(const sdn_raster* r, const sdn_raster_grad* g, void* stream) {
+    return backward_impl(r, g, 0, r ? r->eps : 0.0, r ? r->eps : 0.0, stream);
+}
+
+int sdn_rasterize_backward_split(const sdn_raster* r, const sdn_raster_grad* g, double eps_alpha, double eps_rgb,
+                                 void* stream) {
+    return backward_impl(r, g, 1, eps_alpha, eps_rgb, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+import math
+
+import numpy as np
+import torch
+
+import sdn_b200
+from . import _ops
+from .lighting import lighting
+from .perspective import perspective_width
+from .vertices_to_faces import vertices_to_faces
+from .rasterize import (DEFAULT_EPS, rasterize as _rasterize, rasterize_depth as _rasterize_depth,
+                        rasterize_silhouettes as _rasterize_silhouettes)
+
+
+class Renderer(object):
+    """Mesh renderer with the attribute set and methods of the reference (renderer.py:11-110):
+    render_silhouettes / render_depth / render, plus render_normal and render_multi used by the derender3d bridge.
+
+    Camera + perspective + face gather run fused in one kernel (sdn_faces_forward); gradients flow to `vertices`
+    and `textures` (not to eye / direction / viewing_angle, like derender3d/models/renderer.py:213)."""
+
+    def __init__(self):
+        # rendering
+        self.image_size = 256           # int, or (H, W): this repo's rectangular extension
+        self.anti_aliasing = True
+        self.background_color = [0, 0, 0]
+        self.fill_back = True
+        # camera
+        self.perspective = True
+        self.viewing_angle = 30
+        self.eye = [0, 0, -(1. / math.tan(math.radians(self.viewing_angle)) + 1)]
+        self.camera_mode = 'look_at'
+        self.camera_direction = [0, 0, 1]
+        self.up = None
+        self.near = 0.1
+        self.far = 100
+        # light
+        self.light_intensity_ambient = 0.5
+        self.light_intensity_directional = 0.5
+        self.light_color_ambient = [1, 1, 1]
+        self.light_color_directional = [1, 1, 1]
+        self.light_direction = [0, 1, 0]
+        # rasterization
+        self.rasterizer_eps = 1e-3
+        # derender3d bridge: x is mirrored before the camera (derender3d/models/renderer.py:243)
+        self.flip_x = 1.0
+
+    # -- camera ------------------------------------------------------------------------------------------------
+    def _camera(self, vertices):
+        bs = vertices.shape[0]
+        rot = eye = None
+        if self.camera_mode in ('look_at', 'look'):
+            eye = _ops.as_tensor(self.eye, vertices)
+            up = _ops.as_tensor([0, 1, 0] if self.up is None else self.up, vertices)
+            eye, up = (t.unsqueeze(0) if t.dim() == 1 else t for t in (eye, up))
+            if self.camera_mode == 'look_at':
+                z_dir = _ops.as_tensor([0, 0, 0], vertices).unsqueeze(0) - eye
+            else:
+                z_dir = _ops.as_tensor(self.camera_direction, vertices)
+                z_dir = z_dir.unsqueeze(0) if z_dir.dim() == 1 else z_dir
+            n = max(eye.shape[0], up.shape[0], z_dir.shape[0])
+            rot = _ops.camera_rotation(z_dir.expand(n, 3), up.expand(n, 3)).expand(bs, 3, 3)
+            eye = eye.expand(bs, 3)
+        wx = wy = None
+        if self.perspective:
+            H, W = sdn_b200.hw(self.image_size)
+            angle = self.viewing_angle
+            if isinstance(angle, torch.Tensor) and angle.numel() > 1:
+                tan = [perspective_width(a) for a in angle.detach().cpu().tolist()]
+            else:
+                tan = [perspective_width(float(angle))] * bs
+            wy_np = np.asarray(tan, np.float32)
+            wx_np = wy_np if H == W else (wy_np * np.float32(W / H)).astype(np.float32)
+            wy = torch.from_numpy(wy_np).to(vertices.device)
+            wx = torch.from_numpy(wx_np).to(vertices.device)
+        return sdn_b200.Camera(rot, eye, wx, wy, self.flip_x)
+
+    def _faces(self, vertices, faces, want_normals=False):
+        return sdn_b200.FacesFunction.apply(vertices, faces, self._camera(vertices), self.fill_back, want_normals)
+
+    # -- reference methods ---------------------------------------------------------------------------------------
+    def render_silhouettes(self, vertices, faces):
+        """[B,H,W] alpha (renderer.py:38-56)."""
+        f, _ = self._faces(vertices, faces)
+        return _rasterize_silhouettes(f, self.image_size, self.anti_aliasing)
+
+    def render_depth(self, vertices, faces):
+        """[B,H,W] depth, background = far (renderer.py:58-76)."""
+        f, _ = self._faces(vertices, faces)
+        return _rasterize_depth(f, self.image_size, self.anti_aliasing)
+
+    def render(self, vertices, faces, textures):
+        """[B,3,H,W] lit RGB (renderer.py:78-110)."""
+        idx = faces
+        if self.fill_back:
+            idx = torch.cat((faces, faces.flip(-1)), dim=-2)
+            textures = torch.cat((textures, textures.permute(0, 1, 4, 3, 2, 5)), dim=1)
+        v = vertices * vertices.new_tensor([self.flip_x, 1., 1.]) if self.flip_x != 1.0 else vertices
+        if idx.dim() == 2:
+            idx = idx.unsqueeze(0).expand(v.shape[0], -1, -1)
+        textures = lighting(vertices_to_faces(v, idx), textures, self.light_intensity_ambient,
+                            self.light_intensity_directional, self.light_color_ambient,
+                            self.light_color_directional, self.light_direction)
+        f, _ = self._faces(vertices, faces)
+        return _rasterize(f, textures, self.image_size, self.anti_aliasing, self.near, self.far,
+                               self.rasterizer_eps, self.background_color)
+
+    def render_normal(self, vertices, faces):
+        """[B,3,H,W] per-face normals rasterised as a constant texture (derender3d/models/renderer.py:60-93)."""
+        f, n = self._faces(vertices, faces, want_normals=True)
+        return _rasterize(f, n, self.image_size, self.anti_aliasing, self.near, self.far,
+                               self.rasterizer_eps, self.background_color)
+
+    def render_multi(self, vertices, faces, silhouette=True, depth=True, normal=True, fast_math=False):
+        """One pass for what the reference needs three rasterisations for (derender3d/models/__init__.py:203-224).
+        Returns dict(silhouette [B,H,W], depth [B,H,W], normal [B,3,H,W]); gradients equal the sum of the three
+        reference graphs (alpha with eps 1e-4, rgb with rasterizer_eps)."""
+        f, n = self._faces(vertices, faces, want_normals=normal)
+        cfg = sdn_b200.RasterConfig(self.image_size, self.anti_aliasing, self.near, self.far, self.rasterizer_eps,
+                                    self.background_color, return_rgb=normal, return_alpha=silhouette,
+                                    return_depth=depth, split_eps=(DEFAULT_EPS, self.rasterizer_eps),
+                                    fast_math=fast_math)
+        rgb, alpha, dep = sdn_b200.RasterizeFunction.apply(f, n if normal else None, cfg)
+        self.last_face_index = cfg.last_face_index
+        return {'silhouette': alpha if silhouette else None, 'depth': dep if depth else None,
+                'normal': rgb if normal else None}

@@ -1,0 +1,279 @@
+"""sdn_b200 -- thin host layer over the C ABI of include/sdn_b200.h (libsdn_b200.so, sm_100a).
+
+PyTorch is used for device memory, streams and autograd plumbing only; every pixel is produced by the
+hand-written CUDA library.  There is NO CPU or eager fallback: if the shared library is missing, or a tensor is
+not on a CUDA device, the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libsdn_b200.so')
+
+SDN_RGB, SDN_ALPHA, SDN_DEPTH = 1, 2, 4
+
+_lib = None
+
+
+class SdnError(RuntimeError):
+    pass
+
+
+class _Camera(ctypes.Structure):
+    _fields_ = [('rot', ctypes.c_void_p), ('eye', ctypes.c_void_p), ('width_x', ctypes.c_void_p),
+                ('width_y', ctypes.c_void_p), ('flip_x', ctypes.c_float)]
+
+
+class _Raster(ctypes.Structure):
+    _fields_ = [('B', ctypes.c_int), ('F', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int),
+                ('ss', ctypes.c_int), ('flags', ctypes.c_int), ('texture_size', ctypes.c_int),
+                ('batch_bug', ctypes.c_int), ('near', ctypes.c_double), ('far', ctypes.c_double),
+                ('eps', ctypes.c_double), ('background', ctypes.c_float * 3), ('background_b', ctypes.c_void_p),
+                ('faces', ctypes.c_void_p), ('textures', ctypes.c_void_p), ('rgb', ctypes.c_void_p),
+                ('alpha', ctypes.c_void_p), ('depth', ctypes.c_void_p), ('face_index', ctypes.c_void_p),
+                ('rgb_ss', ctypes.c_void_p), ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_size_t)]
+
+
+class _RasterGrad(ctypes.Structure):
+    _fields_ = [('grad_rgb', ctypes.c_void_p), ('grad_alpha', ctypes.c_void_p), ('grad_depth', ctypes.c_void_p),
+                ('grad_faces', ctypes.c_void_p), ('grad_textures', ctypes.c_void_p), ('fast_math', ctypes.c_int)]
+
+
+def lib():
+    """Load libsdn_b200.so (built by __graft_entry__.build() / csrc/build.py).  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise SdnError('%s is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). '
+                           'There is no CPU fallback.' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.sdn_version.restype = ctypes.c_int
+        L.sdn_error_string.restype = ctypes.c_char_p
+        L.sdn_error_string.argtypes = [ctypes.c_int]
+        L.sdn_workspace_bytes.restype = ctypes.c_size_t
+        L.sdn_workspace_bytes.argtypes = [ctypes.c_int] * 4
+        L.sdn_launch_count.restype = ctypes.c_longlong
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.sdn_faces_forward.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(_Camera), vp, vp, vp]
+        L.sdn_faces_backward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(_Camera), vp, vp,
+                                         ctypes.c_size_t, vp]
+        L.sdn_rasterize_forward.argtypes = [ctypes.POINTER(_Raster), vp]
+        L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
+        L.sdn_rasterize_backward_split.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad),
+                                                   ctypes.c_double, ctypes.c_double, vp]
+        _lib = L
+    return _lib
+
+
+def launch_count():
+    return int(lib().sdn_launch_count())
+
+
+def _check(rc):
+    if rc != 0:
+        raise SdnError('libsdn_b200: %s (code %d)' % (lib().sdn_error_string(rc).decode(), rc))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SdnError('sdn_b200 runs on CUDA tensors only (no CPU fallback); got a %s tensor' % t.device)
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def hw(image_size):
+    if isinstance(image_size, (tuple, list)):
+        return int(image_size[0]), int(image_size[1])
+    return int(image_size), int(image_size)
+
+
+class Camera(object):
+    """Per-image camera handed to the face kernels (device tensors or None)."""
+
+    def __init__(self, rot=None, eye=None, width_x=None, width_y=None, flip_x=1.0):
+        self.rot, self.eye = _f32c(rot), _f32c(eye)
+        self.width_x, self.width_y = _f32c(width_x), _f32c(width_y)
+        self.flip_x = float(flip_x)
+
+    def c(self):
+        return _Camera(_ptr(self.rot), _ptr(self.eye), _ptr(self.width_x), _ptr(self.width_y), self.flip_x)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# vertices -> NDC faces (+ normals)
+# --------------------------------------------------------------------------------------------------------------
+class FacesFunction(torch.autograd.Function):
+    """fill_back + camera + perspective + vertices_to_faces in one launch (sdn_faces_forward / _backward).
+
+    forward(vertices [B,nv,3] f32, faces [B,nf,3] or [nf,3] i32, camera, fill_back, want_normals)
+      -> face_ndc [B,F,3,3], face_normal [B,F,3] (zeros-size tensor when not requested)"""
+
+    @staticmethod
+    def forward(ctx, vertices, faces, camera, fill_back, want_normals):
+        _need_cuda(vertices, faces)
+        v = _f32c(vertices)
+        f = faces.detach().to(torch.int32).contiguous()
+        B, nv = v.shape[0], v.shape[1]
+        batched = 1 if f.dim() == 3 else 0
+        nf = f.shape[-2]
+        if batched and f.shape[0] != B:
+            raise SdnError('faces batch %d != vertices batch %d' % (f.shape[0], B))
+        F = 2 * nf if fill_back else nf
+        face_ndc = torch.empty(B, F, 3, 3, device=v.device, dtype=torch.float32)
+        face_normal = torch.empty(B, F, 3, device=v.device, dtype=torch.float32) if want_normals else None
+        cam = camera.c()
+        with torch.cuda.device(v.device):
+            _check(lib().sdn_faces_forward(_ptr(v), _ptr(f), B, nv, nf, batched, int(bool(fill_back)),
+                                           ctypes.byref(cam), _ptr(face_ndc), _ptr(face_normal), _stream()))
+        ctx.save_for_backward(v, f)
+        ctx.camera, ctx.fill_back, ctx.dims = camera, int(bool(fill_back)), (B, nv, nf, batched)
+        if face_normal is None:
+            face_normal = torch.empty(0, device=v.device)
+            ctx.mark_non_differentiable(face_normal)
+        return face_ndc, face_normal
+
+    @staticmethod
+    def backward(ctx, g_ndc, g_nrm):
+        v, f = ctx.saved_tensors
+        B, nv, nf, batched = ctx.dims
+        g_ndc = _f32c(g_ndc)
+        g_nrm = _f32c(g_nrm) if (g_nrm is not None and g_nrm.numel() > 0) else None
+        grad_v = torch.empty_like(v)
+        scratch = torch.empty(2 * B * nv * 3, device=v.device, dtype=torch.float32)
+        cam = ctx.camera.c()
+        with torch.cuda.device(v.device):
+            _check(lib().sdn_faces_backward(_ptr(g_ndc), _ptr(g_nrm), _ptr(v), _ptr(f), B, nv, nf, batched,
+                                            ctx.fill_back, ctypes.byref(cam), _ptr(grad_v), _ptr(scratch),
+                                            scratch.numel() * 4, _stream()))
+        return grad_v, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------------------------
+# NDC faces (+ textures) -> images
+# --------------------------------------------------------------------------------------------------------------
+class RasterConfig(object):
+    """Everything a reference `Rasterize` instance is constructed with (rasterize.py:20-37) plus SSAA."""
+
+    def __init__(self, image_size, anti_aliasing=True, near=0.1, far=100, eps=1e-4, background_color=(0, 0, 0),
+                 return_rgb=False, return_alpha=False, return_depth=False, batch_bug=False, split_eps=None,
+                 fast_math=False):
+        self.H, self.W = hw(image_size)
+        self.ss = 2 if anti_aliasing else 1
+        self.near, self.far, self.eps = float(near), float(far), float(eps)
+        self.background_color = background_color
+        self.return_rgb, self.return_alpha, self.return_depth = bool(return_rgb), bool(return_alpha), bool(return_depth)
+        self.batch_bug = bool(batch_bug)
+        self.split_eps = split_eps      # (eps_alpha, eps_rgb): three-Rasterize semantics of the derender3d bridge
+        self.fast_math = bool(fast_math)
+
+    @property
+    def flags(self):
+        return (SDN_RGB if self.return_rgb else 0) | (SDN_ALPHA if self.return_alpha else 0) | \
+               (SDN_DEPTH if self.return_depth else 0)
+
+
+class RasterizeFunction(torch.autograd.Function):
+    """sdn_rasterize_forward / _backward.
+
+    forward(faces [B,F,3,3], textures, cfg) -> rgb [B,3,H,W], alpha [B,H,W], depth [B,H,W]
+    textures: None, [B,F,ts,ts,ts,3] (ts >= 2) or [B,F,3] (one colour per face).
+    The int32 face-index map of the last call is kept on `cfg.last_face_index` for inspection / tests."""
+
+    @staticmethod
+    def forward(ctx, faces, textures, cfg):
+        if cfg.flags == 0:
+            raise Exception('nothing to draw')      # rasterize.py:25-27
+        _need_cuda(faces, textures)
+        fc = _f32c(faces)
+        assert fc.dim() == 4 and fc.shape[2] == 3 and fc.shape[3] == 3
+        B, F = fc.shape[0], fc.shape[1]
+        dev = fc.device
+        ts = 0
+        tex = None
+        if cfg.return_rgb:
+            tex = _f32c(textures)
+            if tex.dim() == 3:
+                assert tex.shape == (B, F, 3)
+                ts = 1
+            else:
+                assert tex.dim() == 6 and tex.shape[0] == B and tex.shape[1] == F and tex.shape[5] == 3
+                ts = tex.shape[2]
+                assert ts >= 2 and tex.shape[3] == ts and tex.shape[4] == ts
+        H, W, ss = cfg.H, cfg.W, cfg.ss
+        rgb = torch.empty(B, 3, H, W, device=dev) if cfg.return_rgb else None
+        alpha = torch.empty(B, H, W, device=dev) if cfg.return_alpha else None
+        depth = torch.empty(B, H, W, device=dev) if cfg.return_depth else None
+        face_index = torch.empty(B, H * ss, W * ss, device=dev, dtype=torch.int32)
+        rgb_ss = torch.empty(B, H * ss, W * ss, 3, device=dev) if (cfg.return_rgb and ts >= 2) else None
+        nbytes = lib().sdn_workspace_bytes(B, F, H * ss, W * ss)
+        workspace = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        bg = cfg.background_color
+        bg_b = None
+        bg3 = (0.0, 0.0, 0.0)
+        if cfg.return_rgb and bg is not None:
+            if isinstance(bg, torch.Tensor) and bg.dim() == 2:
+                bg_b = _f32c(bg.to(dev))
+            else:
+                bg3 = tuple(float(x) for x in (bg.tolist() if isinstance(bg, torch.Tensor) else bg))
+        r = _Raster(B, F, H, W, ss, cfg.flags, ts, int(cfg.batch_bug), cfg.near, cfg.far, cfg.eps,
+                    (ctypes.c_float * 3)(*bg3), _ptr(bg_b), _ptr(fc), _ptr(tex), _ptr(rgb), _ptr(alpha), _ptr(depth),
+                    _ptr(face_index), _ptr(rgb_ss), _ptr(workspace), nbytes)
+        with torch.cuda.device(dev):
+            _check(lib().sdn_rasterize_forward(ctypes.byref(r), _stream()))
+        ctx.cfg, ctx.ts = cfg, ts
+        ctx.keep = (fc, tex, face_index, rgb_ss, workspace, bg_b)
+        ctx.bg3 = bg3
+        ctx.tex_shape = None if textures is None else tuple(textures.shape)
+        cfg.last_face_index = face_index
+        outs = []
+        for t in (rgb, alpha, depth):
+            if t is None:
+                t = torch.empty(0, device=dev)
+                ctx.mark_non_differentiable(t)
+            outs.append(t)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_alpha, g_depth):
+        cfg, ts = ctx.cfg, ctx.ts
+        fc, tex, face_index, rgb_ss, workspace, bg_b = ctx.keep
+        B, F = fc.shape[0], fc.shape[1]
+        dev = fc.device
+        g_rgb = _f32c(g_rgb) if cfg.return_rgb else None
+        g_alpha = _f32c(g_alpha) if cfg.return_alpha else None
+        g_depth = _f32c(g_depth) if cfg.return_depth else None
+        grad_faces = torch.empty_like(fc)
+        grad_tex = torch.empty_like(tex) if (tex is not None and ctx.needs_input_grad[1]) else None
+        r = _Raster(B, F, cfg.H, cfg.W, cfg.ss, cfg.flags, ts, int(cfg.batch_bug), cfg.near, cfg.far, cfg.eps,
+                    (ctypes.c_float * 3)(*ctx.bg3), _ptr(bg_b), _ptr(fc), _ptr(tex), None, None,
+                    None, _ptr(face_index), _ptr(rgb_ss), _ptr(workspace), workspace.numel())
+        g = _RasterGrad(_ptr(g_rgb), _ptr(g_alpha), _ptr(g_depth), _ptr(grad_faces), _ptr(grad_tex),
+                        int(cfg.fast_math))
+        with torch.cuda.device(dev):
+            if cfg.split_eps is not None:
+                _check(lib().sdn_rasterize_backward_split(ctypes.byref(r), ctypes.byref(g),
+                                                          float(cfg.split_eps[0]), float(cfg.split_eps[1]),
+                                                          _stream()))
+            else:
+                _check(lib().sdn_rasterize_backward(ctypes.byref(r), ctypes.byref(g), _stream()))
+        return grad_faces, grad_tex, None
+
+
+def rasterize_faces(faces, textures, cfg):
+    """-> dict(rgb, alpha, depth) with None for what was not requested."""
+    rgb, alpha, depth = RasterizeFunction.apply(faces, textures, cfg)
+    return {'rgb': rgb if cfg.return_rgb else None, 'alpha': alpha if cfg.return_alpha else None,
+            'depth': depth if cfg.return_depth else None}

@@ -1,0 +1,136 @@
+/*
+ * sdn_b200.h -- C ABI of the B200-native (sm_100a) differentiable mesh rasteriser that replaces the
+ * render hot path of ysymyth/3D-SDN (geometric/neural_renderer + the bridge in geometric/derender3d).
+ *
+ * Boundary contract:
+ *   - extern "C", raw DEVICE pointers, row-major, float32 / int32, explicit cudaStream_t (passed as void*),
+ *   - every function returns int: 0 = ok, >0 = cudaError_t, <0 = SDN_E_* argument error; nothing throws or exits,
+ *   - the library never allocates, frees or keeps global state; scratch comes in as (workspace, bytes),
+ *     sized by sdn_workspace_bytes(); the SAME workspace that served a forward must be handed to its backward,
+ *   - re-entrant: works on the caller's current device and the stream given; no device-wide synchronisation.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to /root/reference/geometric/).
+ * Rasters are H rows x W columns (reference: image_size x image_size); "ss" is the super-sampling factor
+ * (2 when anti_aliasing, rasterize.py:942-945, else 1).  F is the EFFECTIVE face count (2*nf with fill_back).
+ */
+#ifndef SDN_B200_H
+#define SDN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDN_VERSION 100            /* 0.1.0 */
+
+/* what to render: rasterize.py:21-22 return_rgb / return_alpha / return_depth */
+#define SDN_RGB    1
+#define SDN_ALPHA  2
+#define SDN_DEPTH  4
+
+/* argument errors */
+#define SDN_E_ARG        (-1)
+#define SDN_E_WORKSPACE  (-2)
+#define SDN_E_NOTHING    (-3)      /* nothing to draw: rasterize.py:25-27 raises */
+
+/* Camera applied per image by sdn_faces_forward / sdn_faces_backward.  All pointers are device pointers and may
+ * be NULL (= that step is skipped).  rot rows are x_axis, y_axis, z_axis (look.py:33-35, look_at.py:34-36);
+ * width_x / width_y are tan(viewing half-angle) per image (perspective.py:13); flip_x multiplies x first
+ * (derender3d/models/renderer.py:243 uses -1). */
+typedef struct sdn_camera {
+    const float* rot;       /* [B,3,3] or NULL */
+    const float* eye;       /* [B,3]   or NULL */
+    const float* width_x;   /* [B]     or NULL: no perspective division */
+    const float* width_y;   /* [B]     (required when width_x is set) */
+    float flip_x;           /* +1 or -1 */
+} sdn_camera;
+
+/* One rasterisation call == one reference `Rasterize` instance (rasterize.py:19-64) plus the SSAA / flip /
+ * transpose wrapper rasterize_rgbad (rasterize.py:897-974). */
+typedef struct sdn_raster {
+    int B, F;               /* batch, effective faces */
+    int H, W;               /* OUTPUT rows, cols */
+    int ss;                 /* 1 or 2 */
+    int flags;              /* SDN_RGB | SDN_ALPHA | SDN_DEPTH */
+    int texture_size;       /* ts >= 2: textures [B,F,ts,ts,ts,3];  1: one colour per face [B,F,3]
+                               (the constant 2^3 cube of derender3d/models/renderer.py:75-76) */
+    int batch_bug;          /* 1 reproduces rasterize.py:390 (face pointer without bn*nf) for B > 1 */
+    double near, far;       /* rasterize.py:353-354: substituted as C double literals */
+    double eps;             /* rasterize.py:401 (texture index) and :647 (K6 distance pad) */
+    float background[3];    /* rasterize.py:457-460, used when background_b == NULL */
+    const float* background_b;  /* [B,3] or NULL (rasterize.py:461-462) */
+
+    const float* faces;     /* [B,F,3,3] NDC faces (vertices_to_faces output) */
+    const float* textures;  /* see texture_size; NULL unless SDN_RGB */
+
+    /* outputs, caller-allocated; NULL when not requested */
+    float* rgb;             /* [B,3,H,W] */
+    float* alpha;           /* [B,H,W]   */
+    float* depth;           /* [B,H,W]   */
+    int32_t* face_index;    /* [B,H*ss,W*ss]  raster orientation (row 0 = bottom), -1 = background; REQUIRED */
+    float* rgb_ss;          /* [B,H*ss,W*ss,3] pre-resolve colours; required for backward when texture_size >= 2 */
+
+    void* workspace;        /* sdn_workspace_bytes(B, F, H*ss, W*ss) */
+    size_t workspace_bytes;
+} sdn_raster;
+
+/* Gradients of one rasterisation.  Mirrors Rasterize.backward_gpu (rasterize.py:846-886) including the
+ * avg-pool / flip / transpose backward of rasterize_rgbad.  A NULL grad_* means "no gradient from that output"
+ * (rasterize.py:856-875 substitute zeros). */
+typedef struct sdn_raster_grad {
+    const float* grad_rgb;      /* [B,3,H,W] or NULL */
+    const float* grad_alpha;    /* [B,H,W]   or NULL */
+    const float* grad_depth;    /* [B,H,W]   or NULL */
+    float* grad_faces;          /* [B,F,3,3] OUT (fully written) */
+    float* grad_textures;       /* same shape as textures, OUT (fully written) or NULL */
+    int fast_math;              /* 0: IEEE divisions in the op order of rasterize.py:646-653;
+                                   1: reciprocal-multiply distance math (<= 1e-6 relative, not bit-faithful) */
+} sdn_raster_grad;
+
+int sdn_version(void);
+const char* sdn_error_string(int code);
+
+/* bytes of scratch for one (B, F, Hs = H*ss, Ws = W*ss) rasterisation */
+size_t sdn_workspace_bytes(int B, int F, int Hs, int Ws);
+
+/* Replaces fill_back (neural_renderer/renderer.py:41), look / look_at (look.py:38-43, look_at.py:39-44),
+ * perspective (perspective.py:13-18), vertices_to_faces (vertices_to_faces.py:16-21) and, when face_normal is
+ * given, the per-face normals of derender3d/models/renderer.py:66-73 (taken BEFORE the camera, AFTER flip_x; their x
+ * component is multiplied by flip_x again, i.e. reported in the caller's frame -- the negation of renderer.py:268-270).
+ *   vertices [B,nv,3]; faces [B,nf,3] (faces_batched=1) or [nf,3] shared by the batch (0)
+ *   face_ndc [B,F,3,3], face_normal [B,F,3] or NULL;  F = fill_back ? 2*nf : nf */
+int sdn_faces_forward(const float* vertices, const int32_t* faces, int B, int nv, int nf, int faces_batched,
+                      int fill_back, const sdn_camera* cam, float* face_ndc, float* face_normal, void* stream);
+
+/* Backward of the above: scatter-add of grad_face_ndc / grad_face_normal onto the vertices, then the chain rule
+ * through perspective, the camera rotation and flip_x.  grad_vertices [B,nv,3] is fully written.
+ * scratch: 2*B*nv*3 floats. */
+int sdn_faces_backward(const float* grad_face_ndc, const float* grad_face_normal, const float* vertices,
+                       const int32_t* faces, int B, int nv, int nf, int faces_batched, int fill_back,
+                       const sdn_camera* cam, float* grad_vertices, void* scratch, size_t scratch_bytes,
+                       void* stream);
+
+/* Replaces Rasterize.forward_gpu (rasterize.py:464-510: K1a+K1b visibility, K2 texture sampling, alpha map,
+ * background) and rasterize_rgbad's transpose / row flip / 2x2 mean (rasterize.py:950-966). */
+int sdn_rasterize_forward(const sdn_raster* r, void* stream);
+
+/* Replaces Rasterize.backward_gpu (rasterize.py:846-886: K6 pixel-map gradient, K7 texture gradient,
+ * K8 depth gradient).  `r` must be the descriptor (same buffers, same workspace contents) of the forward. */
+int sdn_rasterize_backward(const sdn_raster* r, const sdn_raster_grad* g, void* stream);
+
+/* Fused multi-output backward used by the derender3d bridge, where silhouette, depth and normal images of the
+ * same faces come from three reference Rasterize instances with different eps: the alpha
+ * gradient uses eps_alpha with alpha only, the rgb gradient uses eps_rgb with rgb only (each with its own
+ * `diff_grad > 0` test, rasterize.py:644,714), and the results add. */
+int sdn_rasterize_backward_split(const sdn_raster* r, const sdn_raster_grad* g, double eps_alpha, double eps_rgb,
+                                 void* stream);
+
+/* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
+long long sdn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDN_B200_H */
