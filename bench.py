@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of render forward+backward at 375x1242 (BASELINE.json metric, config 2).
+
+One "step" = forward (silhouette + depth + normal, 2x SSAA) and backward (N(0,1) upstream gradients) of ONE batch of
+32 synthetic VKITTI-shaped scenes per GPU.  See DESIGN.md section "Measurement" for the algorithmic-byte model.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 32]
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, '3d-sdn_b200')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+H, W, SS = 375, 1242, 2
+NF_EFF = 2 * 1984
+C_OUT = 5
+
+
+def algorithmic_bytes(c_out=C_OUT, f_eff=NF_EFF):
+    """per image."""
+    P = H * W
+    fwd = 36 * f_eff + 4 * c_out * P + 4 * SS * SS * P
+    bwd = 4 * c_out * P + 4 * SS * SS * P + 36 * f_eff + 36 * f_eff
+    return fwd, bwd
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v == 'Active'})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def make_inputs(batch, seed, dev):
+    from sdn_b200 import workloads as wl
+    verts, faces = wl.vkitti_scene_batch(batch, seed=seed)
+    gen = torch.Generator().manual_seed(1000 + seed)
+    grads = {'silhouette': torch.randn(batch, 1, H, W, generator=gen),
+             'depth': torch.randn(batch, 1, H, W, generator=gen),
+             'normal': torch.randn(batch, 3, H, W, generator=gen)}
+    return verts, faces, grads
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import sdn_b200
+    from sdn_b200 import workloads as wl
+    from derender3d.models.renderer import Renderer
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device; there is no CPU fallback'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    sdn_b200.lib()
+
+    B = args.batch
+    verts, faces, grads = make_inputs(B, rank, dev)
+    renderer = Renderer(image_size=(H, W), viewing_angle=wl.vkitti_viewing_angle())
+    fast = not args.exact
+    v_dev = verts.to(dev).requires_grad_(True)
+    f_dev = faces.to(dev).int()
+    g_dev = {k: v.to(dev) for k, v in grads.items()}
+    v_pin = verts.pin_memory()
+    gv_host = torch.empty_like(verts).pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+
+    def step_resident():
+        out = renderer.forward_multi(v_dev, f_dev, fast_math=fast)
+        torch.autograd.backward([out['silhouette'], out['depth'], out['normal']],
+                                [g_dev['silhouette'], g_dev['depth'], g_dev['normal']])
+        v_dev.grad = None
+
+    def step_e2e():
+        # the call a user makes: host vertices in, loss + vertex gradients back on the host
+        v = v_pin.to(dev, non_blocking=True).requires_grad_(True)
+        out = renderer.forward_multi(v, f_dev, fast_math=fast)
+        loss = (out['silhouette'] * g_dev['silhouette']).sum() + (out['depth'] * g_dev['depth']).sum() + \
+               (out['normal'] * g_dev['normal']).sum()
+        loss.backward()
+        gv_host.copy_(v.grad, non_blocking=True)
+        loss_host.copy_(loss.detach().view(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = sdn_b200.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = sdn_b200.launch_count() - launches0
+    sampler.stop_flag = True
+
+    for _ in range(3):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-call device time of the four C-ABI calls (events on the launching stream = torch's current stream)
+    seg = segment_times(renderer, v_dev, f_dev, g_dev, fast, steps=max(5, min(args.steps, 20)))
+
+    images = B * world * args.steps
+    value = images / (ms * 1e-3)
+    line = {
+        'metric': 'images/sec fwd+bwd render 375x1242', 'value': round(value, 1), 'unit': 'images/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 4),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'config2: B=%d/GPU, 375x1242 (750x2484 2xSSAA), 1984-triangle superellipsoid '
+                               '(3968 with fill_back), VKITTI camera f=725, silhouette+depth+normal, N(0,1) grads'
+                               % B,
+                   'batch_per_gpu': B, 'math': 'fast' if fast else 'exact',
+                   'l2': 'inputs+outputs per step (%.0f MB) exceed the 126 MB L2' % (
+                       B * sum(algorithmic_bytes()) / 1e6),
+                   'sharding': 'by image, no data-path collective'},
+        'e2e': {'value': round(images / (ms_e2e * 1e-3), 1), 'unit': 'images/s',
+                'h2d_bytes_per_step': int(verts.numel() * 4), 'd2h_bytes_per_step': int(verts.numel() * 4 + 4)},
+        'gpu_launches': int(launches),
+        'clocks': sampler.summary(),
+    }
+    if rank == 0:
+        fwd_b, bwd_b = algorithmic_bytes()
+        peak, how = measured_peaks()
+        dom = max(seg, key=lambda k: seg[k])
+        algo = {'rasterize_forward': fwd_b * B, 'rasterize_backward': bwd_b * B}.get(dom, (fwd_b + bwd_b) * B)
+        achieved = algo / (seg[dom] * 1e-3) / 1e9
+        line['roofline'] = {'bound': 'hbm', 'kernel': {'rasterize_forward': 'k_raster_tiles',
+                                                       'rasterize_backward': 'k_backward_items'}.get(dom, dom),
+                            'achieved': round(achieved, 1), 'peak': peak, 'peak_source': how, 'unit': 'GB/s',
+                            'frac': round(achieved / peak, 4), 'traffic': None,
+                            'algorithmic_bytes_per_launch': int(algo), 'launch_ms': round(seg[dom], 4),
+                            'segments_ms': {k: round(v, 4) for k, v in seg.items()},
+                            'whole_step_frac': round(value / world * sum(algorithmic_bytes()) / 1e9 / peak, 4)}
+        if world == 1 and not args.no_cpu:
+            line['cpu_baseline'] = cpu_baseline(sample_images=1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def segment_times(renderer, v_dev, f_dev, g_dev, fast, steps):
+    """CUDA-event time of each C-ABI call (faces fwd, rasterise fwd, rasterise bwd, faces bwd)."""
+    import sdn_b200
+    r = renderer._native()
+    r.eye, r.camera_mode, r.camera_direction, r.up = renderer._camera_args(v_dev)
+    cam = r._camera(v_dev)
+    acc = {'faces_forward': 0.0, 'rasterize_forward': 0.0, 'rasterize_backward': 0.0, 'faces_backward': 0.0}
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+    for _ in range(steps):
+        v = v_dev.detach().requires_grad_(True)
+        e0 = ev()
+        f, n = sdn_b200.FacesFunction.apply(v, f_dev, cam, True, True)
+        e1 = ev()
+        fd, nd = f.detach().requires_grad_(True), n.detach().requires_grad_(True)
+        cfg = sdn_b200.RasterConfig((H, W), True, 0.1, 100, 1e-3, (0, 0, 0), True, True, True,
+                                    split_eps=(1e-4, 1e-3), fast_math=fast)
+        e2 = ev()
+        rgb, alpha, dep = sdn_b200.RasterizeFunction.apply(fd, nd, cfg)
+        e3 = ev()
+        torch.autograd.backward([alpha, dep, rgb], [g_dev['silhouette'][:, 0], g_dev['depth'][:, 0], g_dev['normal']])
+        e4 = ev()
+        torch.autograd.backward([f, n], [fd.grad, nd.grad])
+        e5 = ev()
+        torch.cuda.synchronize()
+        acc['faces_forward'] += e0.elapsed_time(e1)
+        acc['rasterize_forward'] += e2.elapsed_time(e3)
+        acc['rasterize_backward'] += e3.elapsed_time(e4)
+        acc['faces_backward'] += e4.elapsed_time(e5)
+    return {k: v / steps for k, v in acc.items()}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arms (the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(sample_images, seed=0):
+    """What 3D-SDN does per object on its render path (derender3d/models/__init__.py:203-224): three
+    rasterisations (silhouette, depth, normal) and their backward, here on the host with the oracle port.
+    The reference has no CPU rasteriser (rasterize.py:890-894) and renders squares only, so its own kernels
+    (oracle/_ref) cannot run the 375x1242 workload: kind = "port"."""
+    from oracle import oracle as O
+    from sdn_b200 import workloads as wl
+    verts, faces, grads = make_inputs(sample_images, seed, None)
+    fb = faces[None].expand(sample_images, -1, -1).contiguous()
+    angle = wl.vkitti_viewing_angle()
+    t0 = time.time()
+    v = verts.clone().requires_grad_(True)
+    loss = 0
+    for rt, key in ((O.RenderType.Silhouette, 'silhouette'), (O.RenderType.Depth, 'depth'),
+                    (O.RenderType.Normal, 'normal')):
+        loss = loss + (O.derender_render(v, fb, (H, W), angle, rt) * grads[key]).sum()
+    loss.backward()
+    return time.time() - t0, O.num_threads()
+
+
+def cpu_baseline(sample_images=1):
+    secs, threads = cpu_reference_step(sample_images)
+    return {'value': round(sample_images / secs, 4), 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+            'host_cores': os.cpu_count(),
+            'sample': '%d image(s) of config2, fwd+bwd, 3 rasterisations as the reference issues them, '
+                      'OpenMP over samples/faces, %.1f s' % (sample_images, secs)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    for _ in range(warm):
+        cpu_reference_step(1)
+    t, threads = 0.0, 1
+    for s in range(steps):
+        dt, threads = cpu_reference_step(1, seed=s)
+        t += dt
+    value = steps / t
+    line = {'impl': 'reference', 'metric': 'images/sec fwd+bwd render 375x1242', 'value': round(value, 4),
+            'unit': 'images/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': steps, 'warmup': warm,
+            'ms_per_step': round(t / steps * 1e3, 1), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'config2 sample: 1 image per step, 375x1242 2xSSAA, 1984-triangle superellipsoid, '
+                                   'silhouette+depth+normal fwd+bwd on the host cores'},
+            'cpu_baseline': {'value': round(value, 4), 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                             'host_cores': os.cpu_count(),
+                             'sample': '%d step(s) x 1 image; the reference has no CPU path and no rectangular raster, '
+                                       'so this is the oracle port (OpenMP)' % steps},
+            'e2e': {'value': round(value, 4), 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--exact', action='store_true', help='IEEE-division distance math in the backward (default: fast)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,230 @@
+"""Parity of the sm_100a path (through the C ABI) against the oracle and the reference-generated golden vectors.
+Bars (BASELINE.json north_star): int32 face-index buffer bit-exact; RGB / depth / alpha <= 1e-4 rel-L2 (alpha is in
+fact exact); gradients <= 1e-4 rel-L2 (a float sum in a different order)."""
+import numpy as np
+import pytest
+import torch
+
+from util import GOLDEN, load_golden, random_faces, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    import sdn_b200
+    sdn_b200.lib()
+    return torch.device('cuda:0')
+
+
+def _sdn_raster(faces, textures, H, W, ss, near, far, eps, bg, flags, dev, g=None):
+    """Run sdn_rasterize_forward (+ backward) on raw NDC faces; returns numpy maps in RASTER orientation at
+    sample resolution where that makes sense (ss == 1)."""
+    import sdn_b200
+    rgb, alpha, depth = [bool(x) for x in flags]
+    cfg = sdn_b200.RasterConfig((H, W), ss == 2, near, far, eps, bg, rgb, alpha, depth)
+    f = torch.tensor(faces, device=dev, requires_grad=True)
+    t = torch.tensor(textures, device=dev, requires_grad=True) if rgb else None
+    o_rgb, o_alpha, o_depth = sdn_b200.RasterizeFunction.apply(f, t, cfg)
+    res = {'face_index': cfg.last_face_index.cpu().numpy(), 'rgb': o_rgb, 'alpha': o_alpha, 'depth': o_depth,
+           'faces': f, 'textures': t}
+    return res
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=lambda p: p.split('/')[-1][:-4])
+def test_golden_vectors(dev, path):
+    """Vectors produced by the reference's own kernel bodies (tests/golden/make_golden.py)."""
+    g = load_golden(path)
+    S = int(g['S'])
+    flags = g['flags']
+    rgb, alpha, depth = [bool(x) for x in flags]
+    r = _sdn_raster(g['faces'], g.get('textures'), S, S, 1, float(g['near']), float(g['far']), float(g['eps']),
+                    tuple(float(x) for x in g['background']), flags, dev)
+    assert np.array_equal(r['face_index'], g['face_index_map'])
+    loss = 0
+    # outputs are row-flipped and channel-first; undo for comparison with the raster-orientation maps
+    if alpha:
+        a = r['alpha'].flip(1)
+        assert torch.equal(a.cpu(), torch.tensor(g['alpha_map']))
+        loss = loss + (a * torch.tensor(g['grad_alpha_map'], device=dev)).sum()
+    if depth:
+        d = r['depth'].flip(1)
+        assert torch.equal(d.cpu(), torch.tensor(g['depth_map']))
+        loss = loss + (d * torch.tensor(g['grad_depth_map'], device=dev)).sum()
+    if rgb:
+        c = r['rgb'].flip(2).permute(0, 2, 3, 1)
+        assert rel_l2(c, g['rgb_map']) <= 1e-6
+        loss = loss + (c * torch.tensor(g['grad_rgb_map'], device=dev)).sum()
+    loss.backward()
+    assert rel_l2(r['faces'].grad, g['grad_faces']) <= TOL
+    if rgb:
+        assert rel_l2(r['textures'].grad, g['grad_textures']) <= TOL
+
+
+@pytest.mark.parametrize('aa', [True, False])
+@pytest.mark.parametrize('size', [64, (48, 80)])
+def test_config1_cube(dev, oracle, aa, size):
+    """BASELINE config 1: 12-face cube, nr.Renderer defaults, eye from get_points_from_angles(2.732, 20, 30)."""
+    import neural_renderer as nr
+    from sdn_b200 import workloads as wl
+    v, f = wl.cube_mesh()
+    V, Fc = torch.tensor(v)[None], torch.tensor(f)[None]
+    eye = nr.get_points_from_angles(2.732, 20, 30)
+    ro, rg = oracle.NRRenderer(), nr.Renderer()
+    for r in (ro, rg):
+        r.image_size, r.eye, r.anti_aliasing = size, eye, aa
+    tex = torch.rand(1, 12, 2, 2, 2, 3, generator=torch.Generator().manual_seed(0))
+    Vo, To = V.clone().requires_grad_(True), tex.clone().requires_grad_(True)
+    Vg, Tg = V.clone().to(dev).requires_grad_(True), tex.clone().to(dev).requires_grad_(True)
+    so, do, co = ro.render_silhouettes(Vo, Fc), ro.render_depth(Vo, Fc), ro.render(Vo, Fc, To)
+    sg, dg, cg = rg.render_silhouettes(Vg, Fc.to(dev)), rg.render_depth(Vg, Fc.to(dev)), rg.render(Vg, Fc.to(dev), Tg)
+    assert torch.equal(so, sg.cpu()) and so.sum() > 100
+    assert rel_l2(dg, do) <= TOL and rel_l2(cg, co) <= TOL
+    H, W = so.shape[-2:]
+    wgt = torch.linspace(-1, 1, W)[None, None, :] * torch.linspace(0.5, 1.5, H)[None, :, None]
+    ((so * wgt).sum() + (do * 0.01 * wgt).sum() + (co * wgt[:, None]).sum()).backward()
+    wg = wgt.to(dev)
+    ((sg * wg).sum() + (dg * 0.01 * wg).sum() + (cg * wg[:, None]).sum()).backward()
+    assert rel_l2(Vg.grad, Vo.grad) <= TOL and rel_l2(Tg.grad, To.grad) <= TOL
+
+
+@pytest.mark.parametrize('seed,B,F,H,W,ss', [(0, 1, 64, 40, 40, 1), (1, 2, 200, 33, 70, 2), (2, 3, 1500, 64, 96, 1),
+                                             (3, 1, 3000, 70, 130, 2)])
+def test_random_triangle_soup_face_index_exact(dev, oracle, seed, B, F, H, W, ss):
+    """Ragged sizes (not multiples of the 64x32 tile), B > 1, more faces than the per-tile queue holds."""
+    rng = np.random.RandomState(seed)
+    faces = random_faces(rng, B, F, size=0.25 if F > 1000 else 0.5)
+    tex = rng.uniform(0, 1, (B, F, 2, 2, 2, 3)).astype(np.float32)
+    st = oracle.raster_forward(faces, tex, H * ss, W * ss, 0.1, 100, 1e-3, (0, 0, 0), True, True, True)
+    r = _sdn_raster(faces, tex, H, W, ss, 0.1, 100, 1e-3, (0, 0, 0), (1, 1, 1), dev)
+    assert np.array_equal(r['face_index'], st.face_index_map)
+    assert (st.face_index_map >= 0).mean() > 0.3
+    fo, to = torch.tensor(faces, requires_grad=True), torch.tensor(tex, requires_grad=True)
+    out = oracle.rasterize_rgbad(fo, to, (H, W), ss == 2, 0.1, 100, 1e-3, (0, 0, 0))
+    assert torch.equal(out['alpha'], r['alpha'].cpu())
+    assert rel_l2(r['depth'], out['depth']) <= TOL and rel_l2(r['rgb'], out['rgb']) <= TOL
+    gen = torch.Generator().manual_seed(seed)
+    ga, gd, gc = (torch.randn(out[k].shape, generator=gen) for k in ('alpha', 'depth', 'rgb'))
+    ((out['alpha'] * ga).sum() + (out['depth'] * gd).sum() + (out['rgb'] * gc).sum()).backward()
+    ((r['alpha'] * ga.to(dev)).sum() + (r['depth'] * gd.to(dev)).sum() + (r['rgb'] * gc.to(dev)).sum()).backward()
+    assert rel_l2(r['faces'].grad, fo.grad) <= TOL
+    assert rel_l2(r['textures'].grad, to.grad) <= TOL
+
+
+@pytest.mark.parametrize('rt', ['Silhouette', 'Depth', 'Normal'])
+def test_derender3d_bridge(dev, oracle, rt):
+    """derender3d.models.renderer.Renderer (x mirror, fixed camera, normal-x negation) at the reference's call shape."""
+    from sdn_b200 import workloads as wl
+    from derender3d.models.renderer import Renderer, RenderType
+    H, W, focal = 72, 200, 150.0
+    verts, faces = wl.vkitti_scene_batch(3, seed=11, H=H, W=W, focal=focal, z_range=(4.0, 9.0))
+    fb = faces[None].expand(3, -1, -1).contiguous()
+    angle = wl.vkitti_viewing_angle(H, focal)
+    t = getattr(RenderType, rt)
+    vo, vg = verts.clone().requires_grad_(True), verts.clone().to(dev).requires_grad_(True)
+    io = oracle.derender_render(vo, fb, (H, W), angle, t)
+    ig = Renderer(image_size=(H, W), viewing_angle=angle)(vg, fb.to(dev).int(), render_type=t)
+    assert ig.shape == io.shape and (io != io[0, :, 0, 0].view(1, -1, 1, 1)).float().mean() > 0.02
+    if rt == 'Silhouette':
+        assert torch.equal(ig.cpu(), io)
+    assert rel_l2(ig, io) <= TOL
+    g = torch.randn(io.shape, generator=torch.Generator().manual_seed(1))
+    (io * g).sum().backward()
+    (ig * g.to(dev)).sum().backward()
+    assert rel_l2(vg.grad, vo.grad) <= TOL
+
+
+def test_multi_output_equals_three_reference_passes(dev, oracle):
+    """forward_multi: one rasterisation; gradient = sum of the three reference graphs (eps 1e-4 / 1e-4 / 1e-3)."""
+    from sdn_b200 import workloads as wl
+    from derender3d.models.renderer import Renderer, RenderType
+    H, W, focal = 64, 64, 80.0
+    verts, faces = wl.vkitti_scene_batch(2, seed=4, H=H, W=W, focal=focal, z_range=(5.0, 8.0))
+    fb = faces[None].expand(2, -1, -1).contiguous()
+    angle = wl.vkitti_viewing_angle(H, focal)
+    vg = verts.clone().to(dev).requires_grad_(True)
+    out = Renderer(image_size=H, viewing_angle=angle).forward_multi(vg, fb.to(dev).int())
+    gen = torch.Generator().manual_seed(1)
+    gs, gd, gn = (torch.randn(out[k].shape, generator=gen) for k in ('silhouette', 'depth', 'normal'))
+    ((out['silhouette'] * gs.to(dev)).sum() + (out['depth'] * gd.to(dev)).sum() +
+     (out['normal'] * gn.to(dev)).sum()).backward()
+    vo = verts.clone().requires_grad_(True)
+    so = oracle.derender_render(vo, fb, H, angle, RenderType.Silhouette)
+    do = oracle.derender_render(vo, fb, H, angle, RenderType.Depth)
+    no = oracle.derender_render(vo, fb, H, angle, RenderType.Normal)
+    ((so * gs).sum() + (do * gd).sum() + (no * gn).sum()).backward()
+    assert torch.equal(out['silhouette'].cpu(), so)
+    assert rel_l2(out['depth'], do) <= TOL and rel_l2(out['normal'], no) <= TOL
+    assert rel_l2(vg.grad, vo.grad) <= TOL
+    # fast_math trades the IEEE divisions of the distance term for reciprocals: still inside the bar
+    vf = verts.clone().to(dev).requires_grad_(True)
+    of = Renderer(image_size=H, viewing_angle=angle).forward_multi(vf, fb.to(dev).int(), fast_math=True)
+    ((of['silhouette'] * gs.to(dev)).sum() + (of['depth'] * gd.to(dev)).sum() +
+     (of['normal'] * gn.to(dev)).sum()).backward()
+    assert rel_l2(vf.grad, vo.grad) <= TOL
+
+
+def test_full_size_properties_config2(dev):
+    """BASELINE config 2 shape (375x1242, 2x SSAA): size-independent properties instead of the O(S^2 F) oracle."""
+    from sdn_b200 import workloads as wl
+    from derender3d.models.renderer import Renderer
+    B = 4
+    verts, faces = wl.vkitti_scene_batch(B, seed=0)
+    angle = wl.vkitti_viewing_angle()
+    r = Renderer(image_size=(wl.VKITTI_H, wl.VKITTI_W), viewing_angle=angle)
+    vg = verts.to(dev).requires_grad_(True)
+    fg = faces.to(dev).int()
+    a = r.forward_multi(vg, fg)
+    fi1 = r.last_face_index.clone()
+    b = r.forward_multi(vg, fg)
+    assert torch.equal(fi1, r.last_face_index)                                   # deterministic
+    for k in ('silhouette', 'depth', 'normal'):
+        assert torch.equal(a[k], b[k])
+    sil = a['silhouette']
+    assert sil.shape == (B, 1, 375, 1242)
+    assert set(torch.unique(sil).tolist()) <= {0.0, 0.25, 0.5, 0.75, 1.0}
+    cov = (fi1 >= 0).view(B, 375, 2, 1242, 2).float().mean(dim=(2, 4))            # raster rows: flip to compare
+    assert torch.equal(cov.flip(1), sil[:, 0])
+    assert int(fi1.max()) < 2 * faces.shape[0] and int(fi1.min()) == -1
+    d = a['depth']
+    assert float(d.max()) == 100.0 and float(d.min()) > 5.0
+    bgmask = sil[:, 0] == 0
+    assert torch.all(d[:, 0][bgmask] == 100.0) and torch.all(a['normal'].abs().sum(1)[bgmask] == 0)
+    n = a['normal']
+    full = sil[:, 0] == 1
+    assert torch.all((n[:, :, :, :].pow(2).sum(1)[full]) <= 1.0 + 1e-4)
+    (sil.sum() + d.sum() * 1e-3 + n.sum()).backward()
+    assert torch.isfinite(vg.grad).all() and float(vg.grad.abs().sum()) > 0
+
+
+def test_full_size_single_image_against_oracle(dev, oracle):
+    """One 375x1242 image end to end against the oracle (a few seconds of host time)."""
+    from sdn_b200 import workloads as wl
+    from derender3d.models.renderer import Renderer, RenderType
+    verts, faces = wl.vkitti_scene_batch(1, seed=9, z_range=(7.0, 9.0))
+    fb = faces[None].contiguous()
+    angle = wl.vkitti_viewing_angle()
+    size = (wl.VKITTI_H, wl.VKITTI_W)
+    vg = verts.clone().to(dev).requires_grad_(True)
+    ig = Renderer(image_size=size, viewing_angle=angle)(vg, fb.to(dev).int(), render_type=RenderType.Silhouette)
+    vo = verts.clone().requires_grad_(True)
+    io = oracle.derender_render(vo, fb, size, angle, RenderType.Silhouette)
+    assert torch.equal(ig.cpu(), io) and io.sum() > 1000
+    g = torch.randn(io.shape, generator=torch.Generator().manual_seed(2))
+    (io * g).sum().backward()
+    (ig * g.to(dev)).sum().backward()
+    assert rel_l2(vg.grad, vo.grad) <= TOL
+
+
+def test_errors(dev):
+    import neural_renderer as nr
+    import sdn_b200
+    f = torch.zeros(1, 2, 3, 3, device=dev)
+    with pytest.raises(Exception):
+        nr.rasterize_rgbad(f, None, 8, True, return_rgb=False, return_alpha=False, return_depth=False)
+    with pytest.raises(sdn_b200.SdnError):
+        nr.rasterize_silhouettes(f.cpu(), 8)
+    out = nr.rasterize_silhouettes(f, 8)          # degenerate faces draw nothing
+    assert out.shape == (1, 8, 8) and float(out.abs().sum()) == 0

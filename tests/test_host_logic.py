@@ -1,0 +1,76 @@
+"""Host-side glue of the product (3d-sdn_b200/neural_renderer) against the oracle's restatement, on CPU tensors:
+these are pure elementwise float32 ops in a fixed order, so they must agree bit for bit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import neural_renderer as nr
+
+
+def _verts(seed=0, B=2, nv=50):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, nv, 3, generator=g)
+
+
+def test_camera_glue_matches_oracle(oracle):
+    v = _verts()
+    eye = [1.0, 2.0, -5.0]
+    assert torch.equal(nr.look_at(v, eye), oracle.look_at(v, eye))
+    d = torch.tensor([[0.1, -0.2, 1.0], [0.0, 0.0, -1.0]])
+    assert torch.equal(nr.look(v, eye, d), oracle.look(v, eye, d))
+    a = nr.look_at(v, eye)
+    assert torch.equal(nr.perspective(a, 30.), oracle.perspective(a, 30.))
+    assert torch.equal(nr.perspective(a, 14.5, 1242 / 375), oracle.perspective(a, 14.5, 1242 / 375))
+    assert nr.perspective_width(30.) == oracle.perspective_width(30.)
+    # the literal 3.1416 of perspective.py:10, not math.pi
+    assert abs(float(nr.perspective_width(30.)) - np.tan(30 / 180 * 3.1416)) < 1e-6
+
+
+def test_gather_cross_lighting_match_oracle(oracle):
+    v = _verts(1)
+    f = torch.randint(0, 50, (2, 30, 3), generator=torch.Generator().manual_seed(2), dtype=torch.int32)
+    fv = nr.vertices_to_faces(v, f)
+    assert fv.shape == (2, 30, 3, 3) and torch.equal(fv, oracle.vertices_to_faces(v, f))
+    a, b = v[0, :20], v[1, :20]
+    assert torch.equal(nr.cross(a, b), oracle.cross(a, b))
+    assert torch.allclose(nr.cross(a, b), torch.cross(a, b, dim=1), atol=1e-6)
+    tex = torch.rand(2, 30, 2, 2, 2, 3, generator=torch.Generator().manual_seed(3))
+    assert torch.equal(nr.lighting(fv, tex), oracle.lighting(fv, tex))
+
+
+def test_get_points_from_angles():
+    p = nr.get_points_from_angles(2.732, 20, 30)
+    assert np.allclose(p, (2.732 * np.cos(np.radians(20)) * np.sin(np.radians(30)), 2.732 * np.sin(np.radians(20)),
+                           -2.732 * np.cos(np.radians(20)) * np.cos(np.radians(30))))
+    t = nr.get_points_from_angles(torch.tensor([2.732]), torch.tensor([20.]), torch.tensor([30.]))
+    assert torch.allclose(t[0], torch.tensor(p, dtype=torch.float32), atol=1e-6)
+
+
+def test_load_save_obj_roundtrip(tmp_path):
+    v = np.array([[0, 0, 0], [2, 0, 0], [2, 1, 0], [0, 1, 0.5]], np.float32)
+    path = str(tmp_path / 'q.obj')
+    with open(path, 'w') as fh:
+        fh.write('# quad\n')
+        for p in v:
+            fh.write('v %f %f %f\n' % tuple(p))
+        fh.write('vn 0 0 1\nf 1/1/1 2/2/1 3/3/1 4/4/1\n')
+    vv, ff = nr.load_obj(path, normalization=False)
+    assert np.allclose(vv, v) and ff.tolist() == [[0, 1, 2], [0, 2, 3]] and ff.dtype == np.int32
+    vn, _ = nr.load_obj(path)
+    assert np.isclose(np.abs(vn).max(), 1.0) and np.allclose(vn.max(0) + vn.min(0), 0, atol=1e-6)
+    out = str(tmp_path / 'o.obj')
+    nr.save_obj(out, vv, ff)
+    v2, f2 = nr.load_obj(out, normalization=False)
+    assert np.allclose(v2, vv, atol=1e-4) and np.array_equal(f2, ff)
+
+
+def test_load_obj_on_reference_assets():
+    root = '/root/reference/geometric/assets/02958343'
+    if not os.path.isdir(root):
+        pytest.skip('reference assets not present on this machine')
+    path = os.path.join(root, sorted(os.listdir(root))[0], 'models', 'model_normalized.obj')
+    v, f = nr.load_obj(path)
+    assert v.dtype == np.float32 and f.dtype == np.int32 and f.min() == 0 and f.max() < len(v)
+    assert 9000 < len(v) < 20000 and 29000 < len(f) < 73000
