@@ -40,33 +40,43 @@ std::atomic<long long> g_launches{0};
 // ------------------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------------------
+struct Query;
 struct Workspace {
     int* active_count;      // [B]
-    int* vis_count;         // [B]
+    int* vis_count;         // [4]    [0] = number of visible faces in the batch
     int* img_bbox;          // [B,4]  {65535-xmin, 65535-ymin, xmax+1, ymax+1}, all grown with atomicMax from 0
     int* counters;          // [4]    {tile ticket, item ticket, -, -}
     unsigned char* visible; // [B*F]  face won at least one sample
     float* face_inv;        // [B*F,9]
     short* face_bbox;       // [B*F,4] x0,y0,x1,y1 inclusive, clamped to the raster
     int* active_ids;        // [B*F]
-    int* vis_ids;           // [B*F]
+    int* vis_ids;           // [B*F]  global face ids b*F+fn of the visible faces
     float* gpart;           // [B*F,12]  K6 partials [edge][axis][2]
     float* gint;            // [B*F,6]   interior sums: S_k (3), colour grad (3)
+    // line-sweep backward (fast path)
+    int* vis_slot;          // [B*F]     position of the face in vis_ids
+    int* scan_buf;          // [lines + 1 + B*F*7 + 1]  counts -> exclusive bases (lines first, then items)
+    int* block_sums;        // [scan blocks]
+    int* line_cursor;       // [lines]
+    int* line_items;        // [qmax]    query indices grouped by line
+    struct Query* queries;  // [qmax]
+    float2* qres;           // [qmax]    (g0, g1) of each query
+    int lines, qmax, scan_n;
     size_t zero_bytes;      // leading bytes cleared at the start of every forward
     size_t total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-Workspace make_ws(void* base, int B, int F) {
+Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     Workspace w;
     char* p = (char*)base;
     size_t off = 0;
     const size_t BF = (size_t)B * F;
     w.active_count = (int*)(p + off); off += sizeof(int) * B;
-    w.vis_count = (int*)(p + off); off += sizeof(int) * B;
     w.img_bbox = (int*)(p + off); off += sizeof(int) * 4 * B;
-    w.counters = (int*)(p + off); off += sizeof(int) * 4;
+    w.vis_count = (int*)(p + off); off += sizeof(int) * 4;      // [0] = visible faces of the whole batch
+    w.counters = (int*)(p + off); off += sizeof(int) * 4;       // contiguous with vis_count (one memset)
     w.visible = (unsigned char*)(p + off); off += BF;
     off = align_up(off, 256);
     w.zero_bytes = off;
@@ -76,6 +86,17 @@ Workspace make_ws(void* base, int B, int F) {
     w.vis_ids = (int*)(p + off); off = align_up(off + BF * 4, 256);
     w.gpart = (float*)(p + off); off = align_up(off + BF * 48, 256);
     w.gint = (float*)(p + off); off = align_up(off + BF * 24, 256);
+    w.lines = B * (Hs + Ws);
+    const size_t qm = BF * 24;
+    w.qmax = (int)(qm < 65536 ? 65536 : (qm > 6000000 ? 6000000 : qm));
+    w.scan_n = w.lines + 1 + (int)BF * 7 + 1;
+    w.vis_slot = (int*)(p + off); off = align_up(off + BF * 4, 256);
+    w.scan_buf = (int*)(p + off); off = align_up(off + (size_t)w.scan_n * 4, 256);
+    w.block_sums = (int*)(p + off); off = align_up(off + ((size_t)w.scan_n / 2048 + 2) * 4, 256);
+    w.line_cursor = (int*)(p + off); off = align_up(off + (size_t)w.lines * 4, 256);
+    w.line_items = (int*)(p + off); off = align_up(off + (size_t)w.qmax * 4, 256);
+    w.queries = (struct Query*)(p + off); off = align_up(off + (size_t)w.qmax * 32, 256);
+    w.qres = (float2*)(p + off); off = align_up(off + (size_t)w.qmax * 8, 256);
     w.total = off;
     return w;
 }
@@ -508,25 +529,21 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
     }
 }
 
-// visible-face compaction for the backward
+// visible-face compaction for the backward: one global list of b*F+fn
 __global__ void k_compact_visible(int B, int F, Workspace ws) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = i < (long)B * F;
-    const int b = in_range ? (int)(i / F) : 0, fn = in_range ? (int)(i % F) : 0;
-    const bool vis = in_range && ws.visible[i];
+    const bool vis = (i < (long)B * F) && ws.visible[i];
     const unsigned lane = threadIdx.x & 31;
-    unsigned todo = __ballot_sync(FULL, vis);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int lb = __shfl_sync(FULL, b, leader);
-        const unsigned same = __ballot_sync(FULL, vis && b == lb);
-        if (vis && b == lb) {
-            int base = 0;
-            if ((int)lane == leader) base = atomicAdd(&ws.vis_count[lb], __popc(same));
-            base = __shfl_sync(same, base, leader);
-            ws.vis_ids[(size_t)lb * F + base + __popc(same & ((1u << lane) - 1))] = fn;
-        }
-        todo &= ~same;
+    const unsigned m = __ballot_sync(FULL, vis);
+    if (!m) return;
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(&ws.vis_count[0], __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (vis) {
+        const int slot = base + __popc(m & ((1u << lane) - 1));
+        ws.vis_ids[slot] = (int)i;
+        ws.vis_slot[i] = slot;
     }
 }
 
@@ -541,6 +558,7 @@ struct BwdParams {
     int split;                              // 1: alpha and rgb are separate reference passes
     double eps_a, eps_r;                    // K6 pads (equal unless split)
     int fast_math;
+    int line_path;                          // out-sweeps were deferred to k_line_sweep
     float bg[3];
     const float* bg_b;
     const float* faces;
@@ -578,18 +596,28 @@ __device__ __forceinline__ float k6_dist(float q, float t, float isf, double eps
 struct SweepCtx {
     // per (item, d0) constants
     float d1_cross, q0, q1;     // q0 = (p10-p00)/(p10-d0), q1 = (p10-p00)/(d0-p00)
+    float k0, k1;               // q * 2 / is1 (fast path)
     bool use0, use1;            // p10 != d0, p00 != d0
     float ref_alpha, ref_c[3];  // alpha_in / rgb_in for the out sweep, *_out for the in sweep
 };
 
-// one visited pixel of a sweep: accumulates into g0 (vertex pi[0]) and g1 (vertex pi[1])
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// one visited pixel of a sweep: accumulates into g0 (vertex pi[0]) and g1 (vertex pi[1]).
+// FAST = false: the IEEE op order of rasterize.py:628-654.  FAST = true: dist = (q*2/is)*t with a hardware
+// reciprocal (relative error ~1e-7 per term, same inclusion tests).
+template <bool FAST>
 __device__ __forceinline__ void visit(const BwdParams& P, int b, const float* bg, size_t mi, int idx, int xi, int yi,
                                       int d1, const SweepCtx& s, float is1f, float& g0, float& g1) {
     const size_t oi = out_index(P, xi, yi);
     const float sc = (P.ss == 2) ? 0.25f : 1.0f;
     float da = 0.0f, dr = 0.0f;
     if (P.use_alpha) {
-        const float ga = P.g_alpha ? P.g_alpha[(size_t)b * P.H * P.W + oi] * sc : 0.0f;
+        const float ga = P.g_alpha ? __ldg(P.g_alpha + (size_t)b * P.H * P.W + oi) * sc : 0.0f;
         const float alpha = idx >= 0 ? 1.0f : 0.0f;
         da = (alpha - s.ref_alpha) * ga;
     }
@@ -599,7 +627,7 @@ __device__ __forceinline__ void visit(const BwdParams& P, int b, const float* bg
         float g[3] = {0.0f, 0.0f, 0.0f};
         if (P.g_rgb) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) g[k] = P.g_rgb[((size_t)b * 3 + k) * P.H * P.W + oi] * sc;
+            for (int k = 0; k < 3; k++) g[k] = __ldg(P.g_rgb + ((size_t)b * 3 + k) * P.H * P.W + oi) * sc;
         }
         if (P.split || !P.use_alpha) {
             dr = (c[0] - s.ref_c[0]) * g[0];
@@ -612,24 +640,24 @@ __device__ __forceinline__ void visit(const BwdParams& P, int b, const float* bg
         }
     }
     const float t = (float)d1 - s.d1_cross;
-    if (da > 0.0f) {
-        const double eps = P.eps_a;
-        if (P.fast_math) {
-            if (s.use0) { float d = s.q0 * t * (2.0f / is1f); d += copysignf((float)eps, d); g0 -= da * __frcp_rn(d); }
-            if (s.use1) { float d = s.q1 * t * (2.0f / is1f); d += copysignf((float)eps, d); g1 -= da * __frcp_rn(d); }
-        } else {
-            if (s.use0) g0 -= __fdiv_rn(da, k6_dist(s.q0, t, is1f, eps));
-            if (s.use1) g1 -= __fdiv_rn(da, k6_dist(s.q1, t, is1f, eps));
+    if (FAST) {
+        const float pa = fmaxf(da, 0.0f), pr = fmaxf(dr, 0.0f);
+        if (pa > 0.0f || pr > 0.0f) {
+            const float ea = (float)P.eps_a, er = (float)P.eps_r;
+            const float d0 = s.k0 * t, d1v = s.k1 * t;
+            const float a0 = (0.0f < d0) ? d0 + ea : d0 - ea, r0 = (0.0f < d0) ? d0 + er : d0 - er;
+            const float a1 = (0.0f < d1v) ? d1v + ea : d1v - ea, r1 = (0.0f < d1v) ? d1v + er : d1v - er;
+            if (s.use0) g0 -= __fmaf_rn(pa, rcp_approx(a0), pr * rcp_approx(r0));
+            if (s.use1) g1 -= __fmaf_rn(pa, rcp_approx(a1), pr * rcp_approx(r1));
         }
-    }
-    if (dr > 0.0f) {
-        const double eps = P.eps_r;
-        if (P.fast_math) {
-            if (s.use0) { float d = s.q0 * t * (2.0f / is1f); d += copysignf((float)eps, d); g0 -= dr * __frcp_rn(d); }
-            if (s.use1) { float d = s.q1 * t * (2.0f / is1f); d += copysignf((float)eps, d); g1 -= dr * __frcp_rn(d); }
-        } else {
-            if (s.use0) g0 -= __fdiv_rn(dr, k6_dist(s.q0, t, is1f, eps));
-            if (s.use1) g1 -= __fdiv_rn(dr, k6_dist(s.q1, t, is1f, eps));
+    } else {
+        if (da > 0.0f) {
+            if (s.use0) g0 -= __fdiv_rn(da, k6_dist(s.q0, t, is1f, P.eps_a));
+            if (s.use1) g1 -= __fdiv_rn(da, k6_dist(s.q1, t, is1f, P.eps_a));
+        }
+        if (dr > 0.0f) {
+            if (s.use0) g0 -= __fdiv_rn(dr, k6_dist(s.q0, t, is1f, P.eps_r));
+            if (s.use1) g1 -= __fdiv_rn(dr, k6_dist(s.q1, t, is1f, P.eps_r));
         }
     }
 }
@@ -640,30 +668,55 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// One out-sweep of rasterize.py:601-656, deferred to the line kernel: pixels lo..hi of raster line `line` (a row for
+// axis 1, a column for axis 0), crossing coordinate xc, distance slopes k = q*2/is of the edge's two vertices.
+struct __align__(16) Query {
+    int lo;
+    int hi_flags;       // bits 0..15 hi, 16 use0, 17 use1, 18 pad0 positive, 19 pad1 positive
+    float xc, k0, k1;
+    float c0, c1, c2;   // rgb_in
+};
+constexpr int QF_USE0 = 1 << 16, QF_USE1 = 1 << 17, QF_POS0 = 1 << 18, QF_POS1 = 1 << 19;
+
+// phases of the item kernel
+constexpr int PH_DIRECT = 0;    // everything inline (exact-math parity path)
+constexpr int PH_COUNT = 1;     // count the out-sweep queries of each item and of each raster line
+constexpr int PH_EMIT = 2;      // write the queries, run in-sweeps and interior gathers; overflow sweeps inline
+
 // items per visible face: 0..5 = (edge, axis) of K6, 6 = interior gather (K8 + texture gradient)
 constexpr int ITEMS = 7;
-constexpr int BWD_WARPS = 8;
+constexpr int BWD_WARPS = 4;
 
+template <bool FAST, int PHASE>
 __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, Workspace ws) {
     const int lane = threadIdx.x & 31;
-    const int b = blockIdx.y;
-    const int nvis = ws.vis_count[b];
-    const int nitems = nvis * ITEMS;
-    const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
-    const size_t base_px = (size_t)b * P.Hs * P.Ws;
-    float bg[3];
-    if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
-    else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+    const int nitems = ws.vis_count[0] * ITEMS;
+    const int ticket = PHASE == PH_COUNT ? 2 : 1;
+    int* item_n = ws.scan_buf + ws.lines + 1;       // counts (PH_COUNT) / exclusive bases (after the scan)
+    if (PHASE == PH_COUNT && blockIdx.x == 0 && threadIdx.x == 0) item_n[nitems] = 0;      // scan sentinel
+    // all queries fit the workspace, or none is deferred (then every sweep runs inline, slower but complete)
+    const bool defer_ok = PHASE == PH_EMIT && ws.scan_buf[ws.lines] <= ws.qmax;
 
-    for (int it = blockIdx.x * BWD_WARPS + (threadIdx.x >> 5); it < nitems; it += gridDim.x * BWD_WARPS) {
-        const int fn = ws.vis_ids[(size_t)b * P.F + it / ITEMS];
+    for (;;) {
+        // dynamic scheduling: work per item varies by orders of magnitude (edge length x sweep length)
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&ws.counters[ticket], 1);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= nitems) break;
+        const size_t fo = (size_t)ws.vis_ids[it / ITEMS];
         const int kind = it % ITEMS;
-        const size_t fo = (size_t)b * P.F + fn;
+        const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
+        const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+        const size_t base_px = (size_t)b * P.Hs * P.Ws;
+        float bg[3];
+        if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+        else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
         float f[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) f[k] = __ldg(P.faces + fo * 9 + k);
 
         if (kind == 6) {
+            if (PHASE == PH_COUNT) { if (lane == 0) item_n[it] = 0; continue; }
             // ---------------- interior gather: samples this face won
             float S[3] = {0.0f, 0.0f, 0.0f}, G[3] = {0.0f, 0.0f, 0.0f};
             const bool need_depth = P.use_depth && P.g_depth;
@@ -731,6 +784,9 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
         // ---------------- K6 item (edge, axis)   rasterize.py:540-729
         const int edge = kind >> 1, axis = kind & 1;
         float g0 = 0.0f, g1 = 0.0f;
+        int nq = 0;                                     // queries of this item so far (warp-uniform)
+        const int qbase = PHASE == PH_EMIT ? item_n[it] - item_n[0] : 0;
+        const int line0 = b * (P.Hs + P.Ws) + (axis == 0 ? P.Hs : 0);
         if (P.use_alpha || P.use_rgb) {
             int pi[3];
             float pp[3][2], p[3][2];
@@ -768,6 +824,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
                     if (valid && (d1_out < 0 || is1 <= d1_out)) valid = false;
                     so.use0 = p[1][0] != d0f; so.use1 = p[0][0] != d0f;
                     so.q0 = __fdiv_rn(dp, p[1][0] - d0f); so.q1 = __fdiv_rn(dp, d0f - p[0][0]);
+                    so.k0 = so.q0 * (2.0f / is1f); so.k1 = so.q1 * (2.0f / is1f);
                     si = so;
                 }
                 if (valid) {
@@ -778,7 +835,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
                     is_in_fn = idx_in == fn;
                     so.ref_alpha = idx_in >= 0 ? 1.0f : 0.0f;
                     si.ref_alpha = idx_out >= 0 ? 1.0f : 0.0f;
-                    if (P.use_rgb) {
+                    if (PHASE != PH_COUNT && P.use_rgb) {
                         colour_at(P, b, base_px + mi_in, idx_in, bg, so.ref_c);
                         colour_at(P, b, base_px + mi_out, idx_out, bg, si.ref_c);
                     }
@@ -795,16 +852,43 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
                     }
                     const int d1_limit = (0 < direction) ? __float2int_rz(ceilf(dc2)) : __float2int_rz(floorf(dc2));
                     const int d1_from = max(min(d1_in, d1_limit), 0);
-                    const int d1_to = min(max(d1_in, d1_limit), is1 - 1);
+                    const int d1_to = PHASE == PH_COUNT ? -1 : min(max(d1_in, d1_limit), is1 - 1);
                     for (int d1 = d1_from; d1 <= d1_to; d1++) {
                         const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
                         const size_t mi = (size_t)yi * P.Ws + xi;
                         if (fim[mi] != fn) continue;
-                        visit(P, b, bg, base_px + mi, fn, xi, yi, d1, si, is1f, g0, g1);
+                        visit<FAST>(P, b, bg, base_px + mi, fn, xi, yi, d1, si, is1f, g0, g1);
                     }
                 }
                 // ---- out sweeps   rasterize.py:601-656
-                const bool sweep = valid && is_in_fn;
+                bool sweep = valid && is_in_fn;
+                if (PHASE != PH_DIRECT) {
+                    const unsigned m = __ballot_sync(FULL, sweep);
+                    const int qi = qbase + nq + __popc(m & ((1u << lane) - 1));
+                    nq += __popc(m);
+                    if (PHASE == PH_COUNT) {
+                        if (sweep) atomicAdd(&ws.scan_buf[line0 + d0], 1);
+                        continue;
+                    }
+                    if (sweep && defer_ok) {            // defer to the line kernel
+                        const int d1_limit = (0 < direction) ? is1 - 1 : 0;
+                        Query q;
+                        q.lo = max(min(d1_out, d1_limit), 0);
+                        int hf = min(max(d1_out, d1_limit), is1 - 1);
+                        if (so.use0) hf |= QF_USE0;
+                        if (so.use1) hf |= QF_USE1;
+                        if ((so.k0 > 0.0f) == (direction > 0) && so.k0 != 0.0f) hf |= QF_POS0;
+                        if ((so.k1 > 0.0f) == (direction > 0) && so.k1 != 0.0f) hf |= QF_POS1;
+                        q.hi_flags = hf;
+                        q.xc = so.d1_cross; q.k0 = so.use0 ? so.k0 : 0.0f; q.k1 = so.use1 ? so.k1 : 0.0f;
+                        q.c0 = so.ref_c[0]; q.c1 = so.ref_c[1]; q.c2 = so.ref_c[2];
+                        ws.queries[qi] = q;
+                        const int line = line0 + d0;
+                        const int pos = atomicAdd(&ws.line_cursor[line], 1);
+                        ws.line_items[ws.scan_buf[line] + pos] = qi;
+                        sweep = false;
+                    }
+                }
                 if (axis == 0) {
                     // vertical: every lane owns a column; iterate absolute rows so loads stay coalesced
                     const int d1_limit = (0 < direction) ? is1 - 1 : 0;
@@ -815,7 +899,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
                     for (int d1 = wlo; d1 <= whi; d1++) {
                         if (d1 < lo || d1 > hi) continue;
                         const size_t mi = (size_t)d1 * P.Ws + d0;
-                        visit(P, b, bg, base_px + mi, fim[mi], d0, d1, d1, so, is1f, g0, g1);
+                        visit<FAST>(P, b, bg, base_px + mi, fim[mi], d0, d1, d1, so, is1f, g0, g1);
                     }
                 } else {
                     // horizontal: the warp takes the steps one at a time, lanes stride along the row
@@ -826,6 +910,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
                         SweepCtx s;
                         s.d1_cross = __shfl_sync(FULL, so.d1_cross, src);
                         s.q0 = __shfl_sync(FULL, so.q0, src); s.q1 = __shfl_sync(FULL, so.q1, src);
+                        s.k0 = __shfl_sync(FULL, so.k0, src); s.k1 = __shfl_sync(FULL, so.k1, src);
                         s.use0 = __shfl_sync(FULL, (int)so.use0, src); s.use1 = __shfl_sync(FULL, (int)so.use1, src);
                         s.ref_alpha = __shfl_sync(FULL, so.ref_alpha, src);
 #pragma unroll
@@ -836,14 +921,227 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
                         const int lo = max(min(dout, d1_limit), 0), hi = min(max(dout, d1_limit), is1 - 1);
                         for (int d1 = lo + lane; d1 <= hi; d1 += 32) {
                             const size_t mi = (size_t)row * P.Ws + d1;
-                            visit(P, b, bg, base_px + mi, fim[mi], d1, row, d1, s, is1f, g0, g1);
+                            visit<FAST>(P, b, bg, base_px + mi, fim[mi], d1, row, d1, s, is1f, g0, g1);
                         }
                     }
                 }
             }
         }
+        if (PHASE == PH_COUNT) { if (lane == 0) item_n[it] = nq; continue; }
         g0 = warp_sum(g0); g1 = warp_sum(g1);
         if (lane == 0) { ws.gpart[fo * 12 + kind * 2 + 0] = g0; ws.gpart[fo * 12 + kind * 2 + 1] = g1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// exclusive scan of ws.scan_buf[0 .. n) (n = lines + 1 + 7 * visible faces + 1), three small kernels
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_ELEMS = 2048;        // per block of 256 threads
+
+__device__ __forceinline__ int scan_len(const Workspace& ws) { return ws.lines + 1 + ws.vis_count[0] * ITEMS + 1; }
+
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < 8 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { const int y = __shfl_up_sync(FULL, w, o); if (lane >= o) w += y; }
+        if (lane < 8) s_warp[lane] = w;
+    }
+    __syncthreads();
+    total = s_warp[7];
+    const int before = warp > 0 ? s_warp[warp - 1] : 0;
+    __syncthreads();
+    return before + x - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_reduce(Workspace ws) {
+    __shared__ int s_warp[8];
+    const int n = scan_len(ws);
+    const int base = blockIdx.x * SCAN_ELEMS;
+    if (base >= n) return;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int i = base + threadIdx.x * 8 + k; if (i < n) v += ws.scan_buf[i]; }
+    int total;
+    block_exclusive_scan_256(v, s_warp, total);
+    if (threadIdx.x == 0) ws.block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) k_scan_sums(Workspace ws) {
+    __shared__ int s_warp[8];
+    const int n = scan_len(ws);
+    const int nb = (n + SCAN_ELEMS - 1) / SCAN_ELEMS;
+    int carry = 0;
+    for (int base = 0; base < nb; base += 256) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? ws.block_sums[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan_256(v, s_warp, total);
+        if (i < nb) ws.block_sums[i] = carry + ex;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(Workspace ws) {
+    __shared__ int s_warp[8];
+    const int n = scan_len(ws);
+    const int base = blockIdx.x * SCAN_ELEMS;
+    if (base >= n) return;
+    int v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { const int i = base + threadIdx.x * 8 + k; v[k] = i < n ? ws.scan_buf[i] : 0; sum += v[k]; }
+    int total;
+    int run = ws.block_sums[blockIdx.x] + block_exclusive_scan_256(sum, s_warp, total);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = base + threadIdx.x * 8 + k;
+        if (i < n) ws.scan_buf[i] = run;
+        run += v[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// line sweep: one warp per raster line.  The warp walks its line in passes of 256 pixels (8 per lane, kept in
+// registers) and, inside a pass, loops over the line's queries; per (pixel, query) pair the work is ~24 issue slots and
+// ONE reciprocal (the four distances of a pair share it).  No atomics; each query's result is written once.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int LM_ALPHA = 0;     // silhouette only: the positive part does not depend on the query
+constexpr int LM_SINGLE = 1;    // one reference pass (rgb, or alpha+rgb summed before the > 0 test)
+constexpr int LM_SPLIT = 2;     // alpha pass (eps_a) + rgb pass (eps_r), separate > 0 tests
+constexpr int LW = 8;           // warps (= adjacent lines) per CTA
+constexpr int LP = 8;           // pixels per lane per pass
+constexpr int LQ = 128;         // queries whose partial sums live in shared memory at a time
+
+template <int MODE>
+__global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace ws) {
+    __shared__ float2 s_acc[LW][LQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_img = P.Hs + P.Ws;
+    // lines are grouped in bundles of LW so that the 8 columns of a bundle share 32-byte sectors
+    const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
+    const int bundles = bundles_rows + bundles_cols;
+    const int b = blockIdx.x / bundles, bi = blockIdx.x % bundles;
+    int axis, d0;
+    if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
+    else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
+    const int line = b * per_img + (axis == 0 ? P.Hs : 0) + d0;
+    if (ws.scan_buf[ws.lines] > ws.qmax) return;       // nothing was deferred (see k_backward_items)
+    const int qbeg = ws.scan_buf[line], qend = ws.scan_buf[line + 1];
+    if (qbeg == qend) return;
+    const int is1 = axis == 0 ? P.Hs : P.Ws;
+    const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+    const float sc = (P.ss == 2) ? 0.25f : 1.0f;
+    float bg[3];
+    if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+    else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+    // LM_SINGLE: the rgb pass of a split backward uses eps_r, a genuine single pass has eps_a == eps_r
+    const float ea = (MODE == LM_SINGLE && (P.split || !P.use_alpha)) ? (float)P.eps_r : (float)P.eps_a;
+    const float er = (float)P.eps_r;
+    const size_t plane = (size_t)P.H * P.W;
+    const float* ga_p = P.g_alpha ? P.g_alpha + (size_t)b * plane : nullptr;
+    const float* gr_p = P.g_rgb ? P.g_rgb + (size_t)b * 3 * plane : nullptr;
+
+    for (int qchunk = qbeg; qchunk < qend; qchunk += LQ) {
+        const int qn = min(LQ, qend - qchunk);
+        for (int k = lane; k < qn; k += 32) s_acc[warp][k] = make_float2(0.0f, 0.0f);
+        __syncwarp();
+        // union of the chunk's ranges, to skip passes nobody needs
+        int ulo = 0x7fffffff, uhi = -1;
+        for (int k = lane; k < qn; k += 32) {
+            const Query& q = ws.queries[ws.line_items[qchunk + k]];
+            ulo = min(ulo, q.lo); uhi = max(uhi, q.hi_flags & 0xffff);
+        }
+        ulo = __reduce_min_sync(FULL, ulo); uhi = __reduce_max_sync(FULL, uhi);
+
+        for (int pbase = (ulo / (32 * LP)) * (32 * LP); pbase <= uhi; pbase += 32 * LP) {
+            // ---- pixel records of this pass: position j = pbase + i*32 + lane
+            float pa[LP], D[LP], g0v[LP], g1v[LP], g2v[LP];
+#pragma unroll
+            for (int i = 0; i < LP; i++) {
+                const int j = pbase + i * 32 + lane;
+                pa[i] = 0.0f; D[i] = 0.0f; g0v[i] = 0.0f; g1v[i] = 0.0f; g2v[i] = 0.0f;
+                if (j < is1) {
+                    const int xi = axis == 0 ? d0 : j, yi = axis == 0 ? j : d0;
+                    const size_t mi = (size_t)yi * P.Ws + xi;
+                    const int idx = __ldg(fim + mi);
+                    const size_t oi = (size_t)(P.H - 1 - yi / P.ss) * P.W + xi / P.ss;
+                    float A = 0.0f;
+                    if (P.use_alpha && ga_p && idx < 0 && (MODE != LM_SINGLE || !P.split))
+                        A = -(__ldg(ga_p + oi) * sc);                                       // (alpha - 1) * g
+                    if (MODE == LM_ALPHA) { pa[i] = fmaxf(A, 0.0f); }
+                    else {
+                        float c[3];
+                        colour_at(P, b, (size_t)b * P.Hs * P.Ws + mi, idx, bg, c);
+                        if (gr_p) {
+                            g0v[i] = __ldg(gr_p + oi) * sc; g1v[i] = __ldg(gr_p + plane + oi) * sc;
+                            g2v[i] = __ldg(gr_p + 2 * plane + oi) * sc;
+                        }
+                        const float d = __fmaf_rn(c[0], g0v[i], __fmaf_rn(c[1], g1v[i], c[2] * g2v[i]));
+                        if (MODE == LM_SPLIT) { pa[i] = fmaxf(A, 0.0f); D[i] = d; }
+                        else D[i] = A + d;
+                    }
+                }
+            }
+            const float xbase = (float)(pbase + lane);
+            const int pass_hi = pbase + 32 * LP - 1;
+            // ---- queries
+            for (int k = 0; k < qn; k++) {
+                const Query q = ws.queries[ws.line_items[qchunk + k]];      // warp-uniform (broadcast) load
+                const int lo = q.lo, hi = q.hi_flags & 0xffff;
+                if (hi < pbase || lo > pass_hi) continue;
+                const float e0a = (q.hi_flags & QF_POS0) ? ea : -ea, e0r = (q.hi_flags & QF_POS0) ? er : -er;
+                const float e1a = (q.hi_flags & QF_POS1) ? ea : -ea, e1r = (q.hi_flags & QF_POS1) ? er : -er;
+                float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < LP; i++) {
+                    const int j = pbase + i * 32 + lane;
+                    const bool in = (j >= lo) && (j <= hi);
+                    const float t = (xbase + (float)(i * 32)) - q.xc;
+                    if (MODE == LM_ALPHA) {
+                        const float p = in ? pa[i] : 0.0f;
+                        const float da0 = __fmaf_rn(q.k0, t, e0a), da1 = __fmaf_rn(q.k1, t, e1a);
+                        const float r = rcp_approx(da0 * da1);
+                        a0 = __fmaf_rn(p * da1, r, a0);
+                        a1 = __fmaf_rn(p * da0, r, a1);
+                    } else if (MODE == LM_SINGLE) {
+                        float dr = D[i] - __fmaf_rn(q.c0, g0v[i], __fmaf_rn(q.c1, g1v[i], q.c2 * g2v[i]));
+                        const float p = in ? fmaxf(dr, 0.0f) : 0.0f;
+                        const float da0 = __fmaf_rn(q.k0, t, e0a), da1 = __fmaf_rn(q.k1, t, e1a);
+                        const float r = rcp_approx(da0 * da1);
+                        a0 = __fmaf_rn(p * da1, r, a0);
+                        a1 = __fmaf_rn(p * da0, r, a1);
+                    } else {
+                        float dr = D[i] - __fmaf_rn(q.c0, g0v[i], __fmaf_rn(q.c1, g1v[i], q.c2 * g2v[i]));
+                        const float pr = in ? fmaxf(dr, 0.0f) : 0.0f;
+                        const float p = in ? pa[i] : 0.0f;
+                        const float da0 = __fmaf_rn(q.k0, t, e0a), dr0 = __fmaf_rn(q.k0, t, e0r);
+                        const float da1 = __fmaf_rn(q.k1, t, e1a), dr1 = __fmaf_rn(q.k1, t, e1r);
+                        const float p01 = da0 * dr0, p23 = da1 * dr1;
+                        const float r = rcp_approx(p01 * p23);
+                        const float n0 = __fmaf_rn(p, dr0, pr * da0), n1 = __fmaf_rn(p, dr1, pr * da1);
+                        a0 = __fmaf_rn(n0 * p23, r, a0);
+                        a1 = __fmaf_rn(n1 * p01, r, a1);
+                    }
+                }
+                a0 = warp_sum(a0); a1 = warp_sum(a1);
+                if (lane == 0) { float2 v = s_acc[warp][k]; v.x += a0; v.y += a1; s_acc[warp][k] = v; }
+            }
+            __syncwarp();
+        }
+        for (int k = lane; k < qn; k += 32) {
+            const int qi = ws.line_items[qchunk + k];
+            const int hf = ws.queries[qi].hi_flags;
+            const float2 v = s_acc[warp][k];
+            // g -= diff / dist   (rasterize.py:648,653)
+            ws.qres[qi] = make_float2((hf & QF_USE0) ? -v.x : 0.0f, (hf & QF_USE1) ? -v.y : 0.0f);
+        }
+        __syncwarp();
     }
 }
 
@@ -854,7 +1152,22 @@ __global__ void k_grad_assemble(BwdParams P, Workspace ws, float* __restrict__ g
     float g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     float gc[3] = {0, 0, 0};
     if (ws.visible[i]) {
-        const float* part = ws.gpart + (size_t)i * 12;
+        float part[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) part[k] = ws.gpart[(size_t)i * 12 + k];
+        if (P.line_path && ws.scan_buf[ws.lines] <= ws.qmax) {
+            // add the deferred out-sweeps of each (edge, axis) item, in step order (deterministic)
+            const int* item_n = ws.scan_buf + ws.lines + 1;
+            const int it0 = ws.vis_slot[i] * ITEMS, q0 = item_n[0];
+            for (int kind = 0; kind < 6; kind++) {
+                float a0 = 0.0f, a1 = 0.0f;
+                for (int q = item_n[it0 + kind] - q0; q < item_n[it0 + kind + 1] - q0; q++) {
+                    const float2 r = ws.qres[q];
+                    a0 += r.x; a1 += r.y;
+                }
+                part[kind * 2 + 0] += a0; part[kind * 2 + 1] += a1;
+            }
+        }
         if (P.use_alpha || P.use_rgb) {
 #pragma unroll
             for (int v = 0; v < 3; v++) {
@@ -1040,7 +1353,7 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
     if (!g || !g->grad_faces) return SDN_E_ARG;
     if ((r->flags & SDN_RGB) && r->texture_size >= 2 && !r->rgb_ss) return SDN_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
-    Workspace ws = make_ws(r->workspace, r->B, r->F);
+    Workspace ws = make_ws(r->workspace, r->B, r->F, r->H * r->ss, r->W * r->ss);
     BwdParams P;
     P.B = r->B; P.F = r->F; P.H = r->H; P.W = r->W; P.ss = r->ss; P.Hs = r->H * r->ss; P.Ws = r->W * r->ss;
     P.flags = r->flags; P.ts = r->texture_size; P.batch_bug = r->batch_bug;
@@ -1057,7 +1370,12 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
     P.grad_textures = P.use_rgb ? g->grad_textures : nullptr;
 
     cudaError_t e;
-    if ((e = cudaMemsetAsync(ws.vis_count, 0, sizeof(int) * r->B, st)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemsetAsync(ws.vis_count, 0, sizeof(int) * 8, st)) != cudaSuccess) return (int)e;
+    P.line_path = (P.fast_math && (P.use_alpha || P.use_rgb)) ? 1 : 0;
+    if (P.line_path) {
+        if ((e = cudaMemsetAsync(ws.scan_buf, 0, sizeof(int) * (ws.lines + 1), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(ws.line_cursor, 0, sizeof(int) * ws.lines, st)) != cudaSuccess) return (int)e;
+    }
     if (P.grad_textures && P.ts >= 2) {
         const size_t nb = (size_t)r->B * r->F * P.ts * P.ts * P.ts * 3 * sizeof(float);
         if ((e = cudaMemsetAsync(P.grad_textures, 0, nb, st)) != cudaSuccess) return (int)e;
@@ -1065,8 +1383,30 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
     const long BF = (long)r->B * r->F;
     k_compact_visible<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(r->B, r->F, ws);
     if ((rc = check_launch())) return rc;
-    dim3 grid((unsigned)max(1, sm_count() * 4 / max(1, min(r->B, sm_count() * 4))), (unsigned)r->B);
-    k_backward_items<<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+    const int grid = sm_count() * 4;
+    if (P.line_path) {
+        k_backward_items<true, PH_COUNT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+        if ((rc = check_launch())) return rc;
+        const int sblocks = (ws.scan_n + SCAN_ELEMS - 1) / SCAN_ELEMS;
+        k_scan_reduce<<<sblocks, 256, 0, st>>>(ws);
+        if ((rc = check_launch())) return rc;
+        k_scan_sums<<<1, 256, 0, st>>>(ws);
+        if ((rc = check_launch())) return rc;
+        k_scan_apply<<<sblocks, 256, 0, st>>>(ws);
+        if ((rc = check_launch())) return rc;
+        k_backward_items<true, PH_EMIT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+        if ((rc = check_launch())) return rc;
+        const int Hs = P.Hs, Wsz = P.Ws;
+        const int bundles = (Hs + LW - 1) / LW + (Wsz + LW - 1) / LW;
+        const unsigned lgrid = (unsigned)(r->B * bundles);
+        if (P.use_alpha && !P.use_rgb) k_line_sweep<LM_ALPHA><<<lgrid, LW * 32, 0, st>>>(P, ws);
+        else if (P.use_alpha && P.use_rgb && P.split) k_line_sweep<LM_SPLIT><<<lgrid, LW * 32, 0, st>>>(P, ws);
+        else k_line_sweep<LM_SINGLE><<<lgrid, LW * 32, 0, st>>>(P, ws);
+    } else if (P.fast_math) {
+        k_backward_items<true, PH_DIRECT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+    } else {
+        k_backward_items<false, PH_DIRECT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+    }
     if ((rc = check_launch())) return rc;
     k_grad_assemble<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(P, ws, g->grad_faces);
     return check_launch();
@@ -1093,9 +1433,8 @@ const char* sdn_error_string(int code) {
 }
 
 size_t sdn_workspace_bytes(int B, int F, int Hs, int Ws) {
-    (void)Hs; (void)Ws;
-    if (B <= 0 || F <= 0) return 0;
-    return make_ws(nullptr, B, F).total;
+    if (B <= 0 || F <= 0 || Hs <= 0 || Ws <= 0) return 0;
+    return make_ws(nullptr, B, F, Hs, Ws).total;
 }
 
 int sdn_faces_forward(const float* vertices, const int32_t* faces, int B, int nv, int nf, int faces_batched,
@@ -1139,7 +1478,7 @@ int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
     int rc = validate(r);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream_;
-    Workspace ws = make_ws(r->workspace, r->B, r->F);
+    Workspace ws = make_ws(r->workspace, r->B, r->F, r->H * r->ss, r->W * r->ss);
     cudaError_t e = cudaMemsetAsync(r->workspace, 0, ws.zero_bytes, st);
     if (e != cudaSuccess) return (int)e;
     const int Hs = r->H * r->ss, Wss = r->W * r->ss;

@@ -67,15 +67,17 @@ class Renderer(Module):
         return r
 
     def _camera_args(self, vertices):
-        dev, bs = vertices.device, len(vertices)
-        expand = lambda t: t.to(dev)[None, :].expand(bs, -1)
+        # the module's camera tensors live on the host (renderer.py:224-229); they stay there so that the native
+        # renderer can evaluate and cache the (constant) view rotation once per (batch size, device)
+        bs = len(vertices)
+        expand = lambda t: t[None, :].expand(bs, -1)
         return expand(self.eye), self.camera_mode, expand(self.camera_direction), expand(self.camera_up)
 
     def forward(self, vertices, faces, textures=None, render_type=RenderType.RGB):
         eye, mode, direction, up = self._camera_args(vertices)
         return RenderFunction.apply(vertices, faces, textures, self._native(), render_type, eye, mode, direction, up)
 
-    def forward_multi(self, vertices, faces, silhouette=True, depth=True, normal=True, fast_math=False):
+    def forward_multi(self, vertices, faces, silhouette=True, depth=True, normal=True, fast_math=None):
         """Silhouette [B,1,S,S], depth [B,1,S,S] and normal [B,3,S,S] of the same objects in ONE rasterisation."""
         r = self._native()
         r.eye, r.camera_mode, r.camera_direction, r.up = self._camera_args(vertices)

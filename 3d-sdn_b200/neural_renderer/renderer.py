@@ -46,34 +46,66 @@ class Renderer(object):
         self.flip_x = 1.0
 
     # -- camera ------------------------------------------------------------------------------------------------
+    _camera_cache = {}
+
+    @staticmethod
+    def _host(x):
+        """list / tuple / CPU tensor -> CPU float tensor (cacheable); CUDA tensor -> None."""
+        if isinstance(x, torch.Tensor):
+            return None if x.is_cuda else x.detach().float()
+        return torch.as_tensor(np.asarray(x, dtype=np.float32))
+
     def _camera(self, vertices):
-        bs = vertices.shape[0]
+        """Per-image camera for the face kernel.  The rotation is a handful of [bs,3] ops (look.py:28-35); when eye /
+        direction / up live on the host they are evaluated there once and the device copy is cached."""
+        bs, dev = vertices.shape[0], vertices.device
+        H, W = sdn_b200.hw(self.image_size)
+        angle = self.viewing_angle
+        multi_angle = isinstance(angle, torch.Tensor) and angle.numel() > 1
+        look = self.camera_mode in ('look_at', 'look')
+        eye_h = self._host(self.eye) if look else None
+        up_h = self._host([0, 1, 0] if self.up is None else self.up) if look else None
+        dir_h = self._host(self.camera_direction) if self.camera_mode == 'look' else None
+        cacheable = (not multi_angle) and (not look or (eye_h is not None and up_h is not None and
+                                                        (self.camera_mode != 'look' or dir_h is not None)))
+        key = None
+        if cacheable:
+            sig = lambda t: None if t is None else (tuple(t.shape), tuple(t.reshape(-1).tolist()))
+            key = (self.camera_mode, bool(self.perspective), float(angle), H, W, bs, str(dev), float(self.flip_x),
+                   sig(eye_h), sig(up_h), sig(dir_h))
+            hit = Renderer._camera_cache.get(key)
+            if hit is not None:
+                return hit
+        ref = vertices.new_zeros(1) if not cacheable else torch.zeros(1)      # where the glue runs
         rot = eye = None
-        if self.camera_mode in ('look_at', 'look'):
-            eye = _ops.as_tensor(self.eye, vertices)
-            up = _ops.as_tensor([0, 1, 0] if self.up is None else self.up, vertices)
+        if look:
+            eye = _ops.as_tensor(self.eye if eye_h is None else eye_h, ref)
+            up = _ops.as_tensor(([0, 1, 0] if self.up is None else self.up) if up_h is None else up_h, ref)
             eye, up = (t.unsqueeze(0) if t.dim() == 1 else t for t in (eye, up))
             if self.camera_mode == 'look_at':
-                z_dir = _ops.as_tensor([0, 0, 0], vertices).unsqueeze(0) - eye
+                z_dir = _ops.as_tensor([0, 0, 0], ref).unsqueeze(0) - eye
             else:
-                z_dir = _ops.as_tensor(self.camera_direction, vertices)
+                z_dir = _ops.as_tensor(self.camera_direction if dir_h is None else dir_h, ref)
                 z_dir = z_dir.unsqueeze(0) if z_dir.dim() == 1 else z_dir
             n = max(eye.shape[0], up.shape[0], z_dir.shape[0])
-            rot = _ops.camera_rotation(z_dir.expand(n, 3), up.expand(n, 3)).expand(bs, 3, 3)
-            eye = eye.expand(bs, 3)
+            rot = _ops.camera_rotation(z_dir.expand(n, 3), up.expand(n, 3)).expand(bs, 3, 3).contiguous().to(dev)
+            eye = eye.expand(bs, 3).contiguous().to(dev)
         wx = wy = None
         if self.perspective:
-            H, W = sdn_b200.hw(self.image_size)
-            angle = self.viewing_angle
-            if isinstance(angle, torch.Tensor) and angle.numel() > 1:
+            if multi_angle:
                 tan = [perspective_width(a) for a in angle.detach().cpu().tolist()]
             else:
                 tan = [perspective_width(float(angle))] * bs
             wy_np = np.asarray(tan, np.float32)
             wx_np = wy_np if H == W else (wy_np * np.float32(W / H)).astype(np.float32)
-            wy = torch.from_numpy(wy_np).to(vertices.device)
-            wx = torch.from_numpy(wx_np).to(vertices.device)
-        return sdn_b200.Camera(rot, eye, wx, wy, self.flip_x)
+            wy = torch.from_numpy(wy_np).to(dev)
+            wx = torch.from_numpy(wx_np).to(dev)
+        cam = sdn_b200.Camera(rot, eye, wx, wy, self.flip_x)
+        if key is not None:
+            if len(Renderer._camera_cache) > 64:
+                Renderer._camera_cache.clear()
+            Renderer._camera_cache[key] = cam
+        return cam
 
     def _faces(self, vertices, faces, want_normals=False):
         return sdn_b200.FacesFunction.apply(vertices, faces, self._camera(vertices), self.fill_back, want_normals)
@@ -111,7 +143,7 @@ class Renderer(object):
         return _rasterize(f, n, self.image_size, self.anti_aliasing, self.near, self.far,
                                self.rasterizer_eps, self.background_color)
 
-    def render_multi(self, vertices, faces, silhouette=True, depth=True, normal=True, fast_math=False):
+    def render_multi(self, vertices, faces, silhouette=True, depth=True, normal=True, fast_math=None):
         """One pass for what the reference needs three rasterisations for (derender3d/models/__init__.py:203-224).
         Returns dict(silhouette [B,H,W], depth [B,H,W], normal [B,3,H,W]); gradients equal the sum of the three
         reference graphs (alpha with eps 1e-4, rgb with rasterizer_eps)."""

@@ -14,6 +14,11 @@ LIB_PATH = os.path.join(HERE, 'libsdn_b200.so')
 
 SDN_RGB, SDN_ALPHA, SDN_DEPTH = 1, 2, 4
 
+# Backward distance arithmetic when a RasterConfig does not say: False = IEEE divisions in the op order of
+# rasterize.py:646-653 (bit-faithful inclusion AND arithmetic), True = line-sweep kernel with hardware reciprocals
+# (same inclusion tests, ~1e-6 relative).  SDN_FAST_MATH=1 in the environment flips the default.
+DEFAULT_FAST_MATH = bool(int(os.environ.get('SDN_FAST_MATH', '0') or 0))
+
 _lib = None
 
 
@@ -169,7 +174,7 @@ class RasterConfig(object):
 
     def __init__(self, image_size, anti_aliasing=True, near=0.1, far=100, eps=1e-4, background_color=(0, 0, 0),
                  return_rgb=False, return_alpha=False, return_depth=False, batch_bug=False, split_eps=None,
-                 fast_math=False):
+                 fast_math=None):
         self.H, self.W = hw(image_size)
         self.ss = 2 if anti_aliasing else 1
         self.near, self.far, self.eps = float(near), float(far), float(eps)
@@ -177,7 +182,7 @@ class RasterConfig(object):
         self.return_rgb, self.return_alpha, self.return_depth = bool(return_rgb), bool(return_alpha), bool(return_depth)
         self.batch_bug = bool(batch_bug)
         self.split_eps = split_eps      # (eps_alpha, eps_rgb): three-Rasterize semantics of the derender3d bridge
-        self.fast_math = bool(fast_math)
+        self.fast_math = DEFAULT_FAST_MATH if fast_math is None else bool(fast_math)
 
     @property
     def flags(self):

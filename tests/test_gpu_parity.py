@@ -228,3 +228,32 @@ def test_errors(dev):
         nr.rasterize_silhouettes(f.cpu(), 8)
     out = nr.rasterize_silhouettes(f, 8)          # degenerate faces draw nothing
     assert out.shape == (1, 8, 8) and float(out.abs().sum()) == 0
+
+
+@pytest.mark.parametrize('flags', [(0, 1, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1), (0, 1, 1)])
+@pytest.mark.parametrize('ss', [1, 2])
+def test_fast_math_line_sweep_backward(dev, oracle, flags, ss, monkeypatch):
+    """The line-sweep backward (fast path: deferred out-sweeps, one reciprocal per pixel/query pair) against the
+    oracle in every mode: silhouette only, rgb only, one combined pass, with depth."""
+    import sdn_b200
+    monkeypatch.setattr(sdn_b200, 'DEFAULT_FAST_MATH', True)
+    rng = np.random.RandomState(17)
+    B, F, H, W = 2, 300, 41, 90
+    faces = random_faces(rng, B, F, size=0.3)
+    tex = rng.uniform(0, 1, (B, F, 2, 2, 2, 3)).astype(np.float32)
+    rgb, alpha, depth = [bool(x) for x in flags]
+    r = _sdn_raster(faces, tex, H, W, ss, 0.1, 100, 1e-3, (0.2, 0.1, 0.3), flags, dev)
+    fo, to = torch.tensor(faces, requires_grad=True), torch.tensor(tex, requires_grad=True)
+    out = oracle.rasterize_rgbad(fo, to if rgb else None, (H, W), ss == 2, 0.1, 100, 1e-3, (0.2, 0.1, 0.3),
+                                 rgb, alpha, depth)
+    gen = torch.Generator().manual_seed(3)
+    lo = lg = 0
+    for k, on in (('alpha', alpha), ('depth', depth), ('rgb', rgb)):
+        if on:
+            g = torch.randn(out[k].shape, generator=gen)
+            lo = lo + (out[k] * g).sum()
+            lg = lg + (r[k] * g.to(dev)).sum()
+    lo.backward()
+    lg.backward()
+    assert rel_l2(r['faces'].grad, fo.grad) <= TOL
+    assert float(fo.grad.abs().sum()) > 0
