@@ -49,7 +49,10 @@ struct Workspace {
     unsigned char* visible; // [B*F]  face won at least one sample
     float* face_inv;        // [B*F,9]
     short* face_bbox;       // [B*F,4] x0,y0,x1,y1 inclusive, clamped to the raster
-    int* active_ids;        // [B*F]
+    int* active_ids;        // [B*Fp]  per image: ids of the faces that can draw (front-facing, on screen)
+    short* active_bbox;     // [B*Fp,4] their bboxes, same order (streamed with 1-D bulk copies)
+    int* tile_prefix;       // [B+1]   tiles inside each image's face bbox, exclusive prefix
+    int Fp;                 // F rounded up so that per-image list starts stay 16-byte aligned
     int* vis_ids;           // [B*F]  global face ids b*F+fn of the visible faces
     float* gpart;           // [B*F,12]  K6 partials [edge][axis][2]
     float* gint;            // [B*F,6]   interior sums: S_k (3), colour grad (3)
@@ -82,7 +85,10 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.zero_bytes = off;
     w.face_inv = (float*)(p + off); off = align_up(off + BF * 36, 256);
     w.face_bbox = (short*)(p + off); off = align_up(off + BF * 8, 256);
-    w.active_ids = (int*)(p + off); off = align_up(off + BF * 4, 256);
+    w.Fp = (F + 3) / 4 * 4 + 16;
+    w.active_ids = (int*)(p + off); off = align_up(off + (size_t)B * w.Fp * 4, 256);
+    w.active_bbox = (short*)(p + off); off = align_up(off + (size_t)B * w.Fp * 8, 256);
+    w.tile_prefix = (int*)(p + off); off = align_up(off + (size_t)(B + 1) * 4, 256);
     w.vis_ids = (int*)(p + off); off = align_up(off + BF * 4, 256);
     w.gpart = (float*)(p + off); off = align_up(off + BF * 48, 256);
     w.gint = (float*)(p + off); off = align_up(off + BF * 24, 256);
@@ -291,7 +297,9 @@ __global__ void k_face_setup(const float* __restrict__ faces, int B, int F, int 
             int base = 0;
             if ((int)lane == leader) base = atomicAdd(&ws.active_count[lb], __popc(same));
             base = __shfl_sync(same, base, leader);
-            ws.active_ids[(size_t)lb * F + base + __popc(same & ((1u << lane) - 1))] = fn;
+            const size_t slot = (size_t)lb * ws.Fp + base + __popc(same & ((1u << lane) - 1));
+            ws.active_ids[slot] = fn;
+            *reinterpret_cast<short4*>(ws.active_bbox + slot * 4) = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
             int a0 = 65535 - x0, a1 = 65535 - y0, a2 = x1 + 1, a3 = y1 + 1;
             a0 = __reduce_max_sync(same, a0); a1 = __reduce_max_sync(same, a1);
             a2 = __reduce_max_sync(same, a2); a3 = __reduce_max_sync(same, a3);
@@ -383,46 +391,166 @@ __device__ __forceinline__ void shade_sample(const FwdParams& P, const float* __
     rgb[0] = acc[0]; rgb[1] = acc[1]; rgb[2] = acc[2];
 }
 
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int* s_warp, int& total);
+
+// ---- background: everything is first filled with the "no face" values by a pure streaming kernel (16-byte stores);
+// the tile kernel below then only visits tiles that can contain a face.
+__device__ __forceinline__ void fill_words(uint32_t* __restrict__ dst, size_t n, uint32_t v, size_t tid, size_t nthreads) {
+    const size_t n4 = n / 4;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint4 v4 = make_uint4(v, v, v, v);
+    for (size_t i = tid; i < n4; i += nthreads) d4[i] = v4;
+    for (size_t i = n4 * 4 + tid; i < n; i += nthreads) dst[i] = v;
+}
+
+__global__ void __launch_bounds__(256) k_fill_background(FwdParams P) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    const size_t P1 = (size_t)P.H * P.W;
+    fill_words(reinterpret_cast<uint32_t*>(P.face_index), (size_t)P.B * P.Hs * P.Ws, 0xffffffffu, tid, nth);
+    if (P.flags & SDN_ALPHA) fill_words(reinterpret_cast<uint32_t*>(P.alpha), P.B * P1, 0u, tid, nth);
+    if (P.flags & SDN_DEPTH) fill_words(reinterpret_cast<uint32_t*>(P.depth), P.B * P1, __float_as_uint(P.clip.far_f), tid, nth);
+    if (P.flags & SDN_RGB) {
+        const bool uniform = !P.bg_b && P.bg[0] == P.bg[1] && P.bg[1] == P.bg[2];
+        if (uniform) {
+            fill_words(reinterpret_cast<uint32_t*>(P.rgb), P.B * 3 * P1, __float_as_uint(P.bg[0]), tid, nth);
+            if (P.rgb_ss) fill_words(reinterpret_cast<uint32_t*>(P.rgb_ss), (size_t)P.B * P.Hs * P.Ws * 3,
+                                     __float_as_uint(P.bg[0]), tid, nth);
+        } else {
+            for (size_t i = tid; i < P.B * 3 * P1; i += nth) {
+                const int bimg = (int)(i / (3 * P1)), c = (int)((i / P1) % 3);
+                P.rgb[i] = P.bg_b ? P.bg_b[bimg * 3 + c] : P.bg[c];
+            }
+            if (P.rgb_ss) {
+                const size_t per = (size_t)P.Hs * P.Ws * 3;
+                for (size_t i = tid; i < P.B * per; i += nth) {
+                    const int bimg = (int)(i / per), c = (int)(i % 3);
+                    P.rgb_ss[i] = P.bg_b ? P.bg_b[bimg * 3 + c] : P.bg[c];
+                }
+            }
+        }
+    }
+}
+
+// tiles that intersect each image's face bounding box: prefix[b] .. prefix[b+1]
+__device__ __forceinline__ void image_tile_range(const Workspace& ws, int b, int& tx0, int& ty0, int& nx, int& ny) {
+    nx = 0; ny = 0; tx0 = 0; ty0 = 0;
+    if (ws.active_count[b] == 0) return;
+    const int ixmin = 65535 - ws.img_bbox[b * 4 + 0], iymin = 65535 - ws.img_bbox[b * 4 + 1];
+    const int ixmax = ws.img_bbox[b * 4 + 2] - 1, iymax = ws.img_bbox[b * 4 + 3] - 1;
+    tx0 = ixmin / TW; ty0 = iymin / TH;
+    nx = ixmax / TW - tx0 + 1; ny = iymax / TH - ty0 + 1;
+}
+
+__global__ void __launch_bounds__(256) k_tile_prefix(int B, Workspace ws) {
+    __shared__ int s_warp[8];
+    int carry = 0;
+    for (int base = 0; base < B; base += 256) {
+        const int b = base + threadIdx.x;
+        int n = 0;
+        if (b < B) { int tx0, ty0, nx, ny; image_tile_range(ws, b, tx0, ty0, nx, ny); n = nx * ny; }
+        int total;
+        const int ex = block_exclusive_scan_256(n, s_warp, total);
+        if (b < B) ws.tile_prefix[b] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) ws.tile_prefix[B] = carry;
+}
+
+// ---- 1-D bulk copies (TMA) + mbarrier: the per-image active-face lists are streamed into shared memory
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int BCH = 1024;       // active-list entries per pipeline stage
+
+template <int SS>
 __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) {
     __shared__ u64 s_key[TH * TW];
+    __shared__ __align__(128) short4 s_bb[2][BCH];
+    __shared__ __align__(128) int s_ids[2][BCH];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int s_queue[QCAP];
     __shared__ float s_xp[TW], s_yp[TH];
     __shared__ int s_qn, s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float far_f = P.clip.far_f;
+    const int total_tiles = ws.tile_prefix[P.B];
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phase[2] = {0u, 0u};
 
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(&ws.counters[0], 1);
         __syncthreads();
         const int tile = s_tile;
-        if (tile >= P.num_tiles) break;
-        const int b = tile / (P.tiles_x * P.tiles_y);
-        const int trem = tile % (P.tiles_x * P.tiles_y);
-        const int ty = trem / P.tiles_x, tx = trem % P.tiles_x;
+        if (tile >= total_tiles) break;
+        // image of this ticket: largest b with prefix[b] <= tile
+        int lo = 0, hi = P.B - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ws.tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1; }
+        const int b = lo;
+        int tx0, ty0, nx, ny;
+        image_tile_range(ws, b, tx0, ty0, nx, ny);
+        const int trem = tile - ws.tile_prefix[b];
+        const int ty = ty0 + trem / nx, tx = tx0 + trem % nx;
         const int sx0 = tx * TW, sy0 = ty * TH;
         const int sx1 = min(sx0 + TW, P.Ws) - 1, sy1 = min(sy0 + TH, P.Hs) - 1;
-
         const int count = ws.active_count[b];
-        const int ixmin = 65535 - ws.img_bbox[b * 4 + 0], iymin = 65535 - ws.img_bbox[b * 4 + 1];
-        const int ixmax = ws.img_bbox[b * 4 + 2] - 1, iymax = ws.img_bbox[b * 4 + 3] - 1;
-        const bool empty = (count == 0) || ixmin > sx1 || ixmax < sx0 || iymin > sy1 || iymax < sy0;
 
-        if (!empty) {
-            for (int k = tid; k < TH * TW; k += NT) s_key[k] = ~0ull;
-            if (tid < TW) s_xp[tid] = xp_of(sx0 + tid, P.Ws);
-            if (tid < TH) s_yp[tid] = xp_of(sy0 + tid, P.Hs);
-            if (tid == 0) s_qn = 0;
-            __syncthreads();
-            const int* ids = ws.active_ids + (size_t)b * P.F;
-            for (int base = 0; base < count; base += NT) {
+        for (int k = tid; k < TH * TW; k += NT) s_key[k] = ~0ull;
+        if (tid < TW) s_xp[tid] = xp_of(sx0 + tid, P.Ws);
+        if (tid < TH) s_yp[tid] = xp_of(sy0 + tid, P.Hs);
+        if (tid == 0) s_qn = 0;
+        const int* ids_g = ws.active_ids + (size_t)b * ws.Fp;
+        const short4* bb_g = reinterpret_cast<const short4*>(ws.active_bbox) + (size_t)b * ws.Fp;
+        const int nchunks = (count + BCH - 1) / BCH;
+        // stage 0 of the pipeline
+        if (tid == 0 && nchunks > 0) {
+            const int n = min(BCH, count);
+            const uint32_t by_i = ((n + 3) / 4) * 16, by_b = ((n + 1) / 2) * 16;
+            mbar_expect_tx(&s_bar[0], by_i + by_b);
+            bulk_g2s(&s_ids[0][0], ids_g, by_i, &s_bar[0]);
+            bulk_g2s(&s_bb[0][0], bb_g, by_b, &s_bar[0]);
+        }
+        __syncthreads();
+        for (int c = 0; c < nchunks; c++) {
+            const int st = c & 1;
+            if (tid == 0 && c + 1 < nchunks) {      // prefetch the next chunk into the other stage (already drained)
+                const int n = min(BCH, count - (c + 1) * BCH);
+                const uint32_t by_i = ((n + 3) / 4) * 16, by_b = ((n + 1) / 2) * 16;
+                mbar_expect_tx(&s_bar[st ^ 1], by_i + by_b);
+                bulk_g2s(&s_ids[st ^ 1][0], ids_g + (size_t)(c + 1) * BCH, by_i, &s_bar[st ^ 1]);
+                bulk_g2s(&s_bb[st ^ 1][0], bb_g + (size_t)(c + 1) * BCH, by_b, &s_bar[st ^ 1]);
+            }
+            mbar_wait(&s_bar[st], phase[st]);
+            phase[st] ^= 1u;
+            const int nin = min(BCH, count - c * BCH);
+            for (int base = 0; base < nin; base += NT) {
                 const int e = base + tid;
                 bool hit = false;
                 int id = -1;
-                if (e < count) {
-                    id = ids[e];
-                    const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + ((size_t)b * P.F + id) * 4);
+                if (e < nin) {
+                    const short4 bb = s_bb[st][e];
                     hit = !(bb.x > sx1 || bb.z < sx0 || bb.y > sy1 || bb.w < sy0);
+                    id = s_ids[st][e];
                 }
                 const unsigned m = __ballot_sync(FULL, hit);
                 int wb = 0;
@@ -431,7 +559,7 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                 if (hit) s_queue[wb + __popc(m & ((1u << lane) - 1))] = id;
                 __syncthreads();
                 const int qn = s_qn;
-                const bool last = base + NT >= count;
+                const bool last = (c == nchunks - 1) && (base + NT >= nin);
                 if (qn > QCAP - NT || last) {
                     // ---- face-parallel coverage: one warp per queued face, lanes over an 8x4 sample footprint
                     for (int q = warp; q < qn; q += NT / 32) {
@@ -461,47 +589,45 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                 }
             }
         }
+        __syncthreads();
 
-        // ---------------- resolve + write (background tiles take the same path with constant keys)
+        // ---------------- resolve + write
         float bg[3];
         load_bg(P, b, bg);
         const bool want_rgb = (P.flags & SDN_RGB) != 0;
-        // (1) face-index map, int4 rows
+        // (1) face-index map, int4 rows; mark the faces that own a sample
         {
             int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+            const bool vec = (P.Ws & 3) == 0;
             for (int k = tid; k < TH * (TW / 4); k += NT) {
                 const int r = k / (TW / 4), c4 = (k % (TW / 4)) * 4;
                 const int yy = sy0 + r, xx = sx0 + c4;
                 if (yy > sy1 || xx > sx1) continue;
                 int v[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = empty ? -1 : (int)(unsigned)(s_key[r * TW + c4 + j] & 0xffffffffu);
+                for (int j = 0; j < 4; j++) v[j] = (int)(unsigned)(s_key[r * TW + c4 + j] & 0xffffffffu);
                 int32_t* dst = fim + (size_t)yy * P.Ws + xx;
-                if (xx + 3 <= sx1 && ((P.Ws & 3) == 0)) *reinterpret_cast<int4*>(dst) = make_int4(v[0], v[1], v[2], v[3]);
+                if (xx + 3 <= sx1 && vec) *reinterpret_cast<int4*>(dst) = make_int4(v[0], v[1], v[2], v[3]);
                 else for (int j = 0; j < 4 && xx + j <= sx1; j++) dst[j] = v[j];
-                if (!empty) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) if (v[j] >= 0) ws.visible[(size_t)b * P.F + v[j]] = 1;
-                }
+                for (int j = 0; j < 4; j++)
+                    if (v[j] >= 0 && (j == 0 || v[j] != v[j - 1])) ws.visible[(size_t)b * P.F + v[j]] = 1;
             }
         }
-        // (2) colour / alpha / depth, one output pixel (ss x ss samples) per thread-iteration
-        const int ss = P.ss;
-        const int ow = TW / ss, oh = TH / ss;
-        for (int k = tid; k < ow * oh; k += NT) {
-            const int orow = k / ow, ocol = k % ow;
-            const int ox = sx0 / ss + ocol, oyr = sy0 / ss + orow;    // oyr: row in raster orientation
+        // (2) colour / alpha / depth: one output pixel (SS x SS samples) per thread-iteration
+        constexpr int OW = TW / SS, OH = TH / SS;
+        const size_t plane = (size_t)P.H * P.W;
+        for (int k = tid; k < OW * OH; k += NT) {
+            const int orow = k / OW, ocol = k % OW;
+            const int ox = sx0 / SS + ocol, oyr = sy0 / SS + orow;    // oyr: row in raster orientation
             if (ox >= P.W || oyr >= P.H) continue;
             float a_sum = 0.0f, d_sum = 0.0f, c_sum[3] = {0.0f, 0.0f, 0.0f};
-            for (int j = 0; j < ss * ss; j++) {
-                const int lx = ocol * ss + (j % ss), ly = orow * ss + (j / ss);
-                int fn = -1;
-                float zp = far_f;
-                if (!empty) {
-                    const u64 key = s_key[ly * TW + lx];
-                    fn = (int)(unsigned)(key & 0xffffffffu);
-                    if (fn >= 0) zp = __uint_as_float((unsigned)(key >> 32));
-                }
+#pragma unroll
+            for (int j = 0; j < SS * SS; j++) {
+                const int lx = ocol * SS + (j % SS), ly = orow * SS + (j / SS);
+                const u64 key = s_key[ly * TW + lx];
+                const int fn = (int)(unsigned)(key & 0xffffffffu);
+                const float zp = fn >= 0 ? __uint_as_float((unsigned)(key >> 32)) : far_f;
                 float col[3] = {bg[0], bg[1], bg[2]};
                 if (fn >= 0) {
                     a_sum += 1.0f;
@@ -514,15 +640,15 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                     o[0] = col[0]; o[1] = col[1]; o[2] = col[2];
                 }
             }
-            const float scale = (ss == 2) ? 0.25f : 1.0f;
+            const float scale = (SS == 2) ? 0.25f : 1.0f;
             const int oy = P.H - 1 - oyr;                               // rasterize.py:953-957 row flip
             const size_t po = (size_t)oy * P.W + ox;
-            if (P.flags & SDN_ALPHA) P.alpha[(size_t)b * P.H * P.W + po] = a_sum * scale;
-            if (P.flags & SDN_DEPTH) P.depth[(size_t)b * P.H * P.W + po] = d_sum * scale;
+            if (P.flags & SDN_ALPHA) P.alpha[(size_t)b * plane + po] = a_sum * scale;
+            if (P.flags & SDN_DEPTH) P.depth[(size_t)b * plane + po] = d_sum * scale;
             if (want_rgb) {
-                P.rgb[((size_t)b * 3 + 0) * P.H * P.W + po] = c_sum[0] * scale;
-                P.rgb[((size_t)b * 3 + 1) * P.H * P.W + po] = c_sum[1] * scale;
-                P.rgb[((size_t)b * 3 + 2) * P.H * P.W + po] = c_sum[2] * scale;
+                P.rgb[((size_t)b * 3 + 0) * plane + po] = c_sum[0] * scale;
+                P.rgb[((size_t)b * 3 + 1) * plane + po] = c_sum[1] * scale;
+                P.rgb[((size_t)b * 3 + 2) * plane + po] = c_sum[2] * scale;
             }
         }
         __syncthreads();
@@ -687,15 +813,18 @@ constexpr int PH_EMIT = 2;      // write the queries, run in-sweeps and interior
 constexpr int ITEMS = 7;
 constexpr int BWD_WARPS = 4;
 
-template <bool FAST, int PHASE>
-__global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, Workspace ws) {
+// Direct form: every sweep runs inline, one warp per (face, edge, axis) item.  FAST = false is the exact-math parity
+// path; FAST = true is the fallback of the line-sweep path when the queries do not fit the workspace
+// (`only_on_overflow`): it returns at once unless that happened.
+template <bool FAST>
+__global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, Workspace ws, int only_on_overflow) {
     const int lane = threadIdx.x & 31;
     const int nitems = ws.vis_count[0] * ITEMS;
-    const int ticket = PHASE == PH_COUNT ? 2 : 1;
-    int* item_n = ws.scan_buf + ws.lines + 1;       // counts (PH_COUNT) / exclusive bases (after the scan)
-    if (PHASE == PH_COUNT && blockIdx.x == 0 && threadIdx.x == 0) item_n[nitems] = 0;      // scan sentinel
-    // all queries fit the workspace, or none is deferred (then every sweep runs inline, slower but complete)
-    const bool defer_ok = PHASE == PH_EMIT && ws.scan_buf[ws.lines] <= ws.qmax;
+    if (only_on_overflow && ws.scan_buf[ws.lines] <= ws.qmax) return;
+    constexpr int PHASE = PH_DIRECT;
+    constexpr int ticket = 1;
+    int* item_n = ws.scan_buf + ws.lines + 1;
+    const bool defer_ok = false;
 
     for (;;) {
         // dynamic scheduling: work per item varies by orders of magnitude (edge length x sweep length)
@@ -933,6 +1062,255 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// fast path, step 1: enumerate the edge steps of every visible face (rasterize.py:540-599) -- one warp per face,
+// the six (edge, axis) items in turn, lanes over the steps d0.  EMIT = false counts the out-sweep queries per item and
+// per raster line; EMIT = true (after the scan) writes them.
+// ------------------------------------------------------------------------------------------------------------
+struct EdgeSetup {
+    float p[3][2];
+    int direction, d0_from, d0_to, is0, is1;
+    float slope, dp;
+};
+
+__device__ __forceinline__ void edge_setup(const float* f, int edge, int axis, int Hs, int Ws, EdgeSetup& E) {
+    int pi[3];
+    float pp[3][2];
+#pragma unroll
+    for (int n = 0; n < 3; n++) pi[n] = (edge + n) % 3;
+#pragma unroll
+    for (int n = 0; n < 3; n++) { pp[n][0] = to_pixel(f[3 * pi[n]], Ws); pp[n][1] = to_pixel(f[3 * pi[n] + 1], Hs); }
+#pragma unroll
+    for (int n = 0; n < 3; n++) { E.p[n][0] = pp[n][axis]; E.p[n][1] = pp[n][1 - axis]; }
+    E.is0 = axis == 0 ? Ws : Hs; E.is1 = axis == 0 ? Hs : Ws;
+    if (axis == 0) E.direction = (E.p[0][0] < E.p[1][0]) ? -1 : 1;
+    else E.direction = (E.p[0][0] < E.p[1][0]) ? 1 : -1;
+    E.d0_from = __double2int_rz(fmax((double)ceilf(fminf(E.p[0][0], E.p[1][0])), 0.));
+    E.d0_to = __double2int_rz(fmin((double)fmaxf(E.p[0][0], E.p[1][0]), E.is0 - 1.));
+    E.slope = __fdiv_rn(E.p[1][1] - E.p[0][1], E.p[1][0] - E.p[0][0]);
+    E.dp = E.p[1][0] - E.p[0][0];
+}
+
+// crossing of step d0: returns false when the step is skipped by rasterize.py:575-576
+__device__ __forceinline__ bool step_cross(const EdgeSetup& E, int d0, float& d1_cross, int& d1_in, int& d1_out) {
+    const float d0f = (float)d0;
+    float dc = E.slope * (d0f - E.p[0][0]);
+    dc = dc + E.p[0][1];
+    d1_cross = dc;
+    d1_in = (0 < E.direction) ? __float2int_rz(floorf(dc)) : __float2int_rz(ceilf(dc));
+    if (d1_in < 0 || E.is1 <= d1_in) return false;
+    d1_out = d1_in + E.direction;
+    return !(d1_out < 0 || E.is1 <= d1_out);
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
+    const int lane = threadIdx.x & 31;
+    const int nvis = ws.vis_count[0];
+    int* item_n = ws.scan_buf + ws.lines + 1;       // counts, then (after the scan) exclusive bases
+    if (!EMIT && blockIdx.x == 0 && threadIdx.x == 0) item_n[nvis * ITEMS] = 0;        // scan sentinel
+    if (EMIT && ws.scan_buf[ws.lines] > ws.qmax) return;    // queries do not fit: k_backward_items<true> takes over
+    const int q_origin = EMIT ? item_n[0] : 0;
+    for (int vi = blockIdx.x * 8 + (threadIdx.x >> 5); vi < nvis; vi += gridDim.x * 8) {
+        const size_t fo = (size_t)ws.vis_ids[vi];
+        const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
+        const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+        float f[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) f[k] = __ldg(P.faces + fo * 9 + k);
+        float bg[3];
+        if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+        else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+        if (!EMIT && lane == 0) item_n[vi * ITEMS + 6] = 0;
+        for (int kind = 0; kind < 6; kind++) {
+            const int axis = kind & 1;
+            EdgeSetup E;
+            edge_setup(f, kind >> 1, axis, P.Hs, P.Ws, E);
+            const int line0 = b * (P.Hs + P.Ws) + (axis == 0 ? P.Hs : 0);
+            const int qbase = EMIT ? item_n[vi * ITEMS + kind] - q_origin : 0;
+            int nq = 0;
+            for (int sbase = E.d0_from; sbase <= E.d0_to; sbase += 32) {
+                const int d0 = sbase + lane;
+                float d1_cross;
+                int d1_in = 0, d1_out = 0;
+                bool sweep = (d0 <= E.d0_to) && step_cross(E, d0, d1_cross, d1_in, d1_out);
+                size_t mi_in = 0;
+                if (sweep) {
+                    mi_in = axis == 0 ? (size_t)d1_in * P.Ws + d0 : (size_t)d0 * P.Ws + d1_in;
+                    sweep = __ldg(fim + mi_in) == fn;              // rasterize.py:601
+                }
+                const unsigned m = __ballot_sync(FULL, sweep);
+                const int qi = qbase + nq + __popc(m & ((1u << lane) - 1));
+                nq += __popc(m);
+                if (!sweep) continue;
+                const int line = line0 + d0;
+                if (!EMIT) { atomicAdd(&ws.scan_buf[line], 1); continue; }
+                const float d0f = (float)d0;
+                const bool use0 = E.p[1][0] != d0f, use1 = E.p[0][0] != d0f;
+                const float k0 = __fdiv_rn(E.dp, E.p[1][0] - d0f) * (2.0f / (float)E.is1);
+                const float k1 = __fdiv_rn(E.dp, d0f - E.p[0][0]) * (2.0f / (float)E.is1);
+                const int d1_limit = (0 < E.direction) ? E.is1 - 1 : 0;
+                Query q;
+                q.lo = max(min(d1_out, d1_limit), 0);
+                int hf = min(max(d1_out, d1_limit), E.is1 - 1);
+                if (use0) hf |= QF_USE0;
+                if (use1) hf |= QF_USE1;
+                if ((k0 > 0.0f) == (E.direction > 0) && k0 != 0.0f) hf |= QF_POS0;
+                if ((k1 > 0.0f) == (E.direction > 0) && k1 != 0.0f) hf |= QF_POS1;
+                q.hi_flags = hf;
+                q.xc = d1_cross; q.k0 = use0 ? k0 : 0.0f; q.k1 = use1 ? k1 : 0.0f;
+                float c[3] = {0.0f, 0.0f, 0.0f};
+                if (P.use_rgb) colour_at(P, b, (size_t)b * P.Hs * P.Ws + mi_in, fn, bg, c);
+                q.c0 = c[0]; q.c1 = c[1]; q.c2 = c[2];
+                ws.queries[qi] = q;
+                const int pos = atomicAdd(&ws.line_cursor[line], 1);
+                ws.line_items[ws.scan_buf[line] + pos] = qi;
+            }
+            if (!EMIT && lane == 0) item_n[vi * ITEMS + kind] = nq;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fast path, step 2: everything that happens ON the samples a face owns -- the depth / texture gathers
+// (rasterize.py:747-844) and the in-sweeps (rasterize.py:659-727).  The reference walks each edge step across the
+// triangle; here each owned sample asks, for the six (edge, axis) items, whether the step through its own row / column
+// would have visited it (identical float tests), so the cost is proportional to the owned area.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bwd_face(BwdParams P, Workspace ws) {
+    const int lane = threadIdx.x & 31;
+    const int nunits = ws.vis_count[0] * ITEMS;
+    if (ws.scan_buf[ws.lines] > ws.qmax) return;    // the direct kernel does all of it
+    const bool need_depth = P.use_depth && P.g_depth;
+    const bool need_tex = P.use_rgb && P.g_rgb && P.grad_textures;
+    const bool need_k6 = P.use_alpha || P.use_rgb;
+    const float sc = (P.ss == 2) ? 0.25f : 1.0f;
+    // unit = (visible face, kind): kinds 0..5 are the in-sweeps of one (edge, axis), kind 6 the depth/texture gather
+    for (int u = blockIdx.x * 8 + (threadIdx.x >> 5); u < nunits; u += gridDim.x * 8) {
+        const size_t fo = (size_t)ws.vis_ids[u / ITEMS];
+        const int kind = u % ITEMS;
+        const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
+        const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+        const size_t base_px = (size_t)b * P.Hs * P.Ws;
+        float f[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) f[k] = __ldg(P.faces + fo * 9 + k);
+        const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+
+        if (kind == 6) {
+            float S[3] = {0.0f, 0.0f, 0.0f}, G[3] = {0.0f, 0.0f, 0.0f};
+            if (need_depth || need_tex) {
+                float inv[9], zf[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) inv[k] = __ldg(ws.face_inv + fo * 9 + k);
+                const float* zsrc = P.faces + ((size_t)(P.batch_bug ? 0 : b) * P.F + fn) * 9;
+#pragma unroll
+                for (int k = 0; k < 9; k++) zf[k] = __ldg(zsrc + k);
+                const int ts = P.ts == 1 ? 2 : P.ts;
+                for (int yy = bb.y + (lane >> 3); yy <= bb.w; yy += 4) {
+                    for (int xx = bb.x + (lane & 7); xx <= bb.z; xx += 8) {
+                        const size_t mi = (size_t)yy * P.Ws + xx;
+                        if (__ldg(fim + mi) != fn) continue;
+                        const size_t oi = out_index(P, xx, yy);
+                        float w[3], zp;
+                        if (!eval_sample(f, inv, xp_of(xx, P.Ws), xp_of(yy, P.Hs), (float)xx, (float)yy, P.clip, w, zp))
+                            continue;
+                        if (need_depth) {      // rasterize.py:821-824: sum_s gd * w_k * depth^2
+                            const float gd = __ldg(P.g_depth + (size_t)b * P.H * P.W + oi) * sc;
+                            const float d2 = zp * zp;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) S[k] += gd * w[k] * d2;
+                        }
+                        if (need_tex) {        // rasterize.py:772-778
+                            float g[3];
+#pragma unroll
+                            for (int k = 0; k < 3; k++) g[k] = __ldg(P.g_rgb + ((size_t)b * 3 + k) * P.H * P.W + oi) * sc;
+                            float tif[3];
+                            texture_index(w, zp, zf, ts, P.eps_tex, tif);
+                            if (P.ts == 1) {
+                                float wsum = 0.0f;
+#pragma unroll
+                                for (int pn = 0; pn < 8; pn++) { int tii[3]; wsum += corner_weight(tif, pn, tii); }
+#pragma unroll
+                                for (int k = 0; k < 3; k++) G[k] += wsum * g[k];
+                            } else {
+                                float* gt = P.grad_textures + fo * ts * ts * ts * 3;
+#pragma unroll
+                                for (int pn = 0; pn < 8; pn++) {
+                                    int tii[3];
+                                    const float cw = corner_weight(tif, pn, tii);
+                                    const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
+#pragma unroll
+                                    for (int k = 0; k < 3; k++) atomicAdd(gt + isc * 3 + k, cw * g[k]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) { S[k] = warp_sum(S[k]); G[k] = warp_sum(G[k]); }
+            if (lane == 0) {
+                float* o = ws.gint + fo * 6;
+                o[0] = S[0]; o[1] = S[1]; o[2] = S[2]; o[3] = G[0]; o[4] = G[1]; o[5] = G[2];
+            }
+            continue;
+        }
+
+        float g0 = 0.0f, g1 = 0.0f;
+        if (need_k6) {
+            const int axis = kind & 1;
+            EdgeSetup E;
+            edge_setup(f, kind >> 1, axis, P.Hs, P.Ws, E);
+            float bg[3];
+            if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+            else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+            const float is1f = (float)E.is1;
+            // only the part of the bbox the edge's steps can reach
+            int x0 = bb.x, x1 = bb.z, y0 = bb.y, y1 = bb.w;
+            if (axis == 0) { x0 = max(x0, E.d0_from); x1 = min(x1, E.d0_to); }
+            else { y0 = max(y0, E.d0_from); y1 = min(y1, E.d0_to); }
+            for (int yy = y0 + (lane >> 3); yy <= y1; yy += 4) {
+                for (int xx = x0 + (lane & 7); xx <= x1; xx += 8) {
+                    const size_t mi = (size_t)yy * P.Ws + xx;
+                    if (__ldg(fim + mi) != fn) continue;
+                    const int d0 = axis == 0 ? xx : yy, d1 = axis == 0 ? yy : xx;
+                    SweepCtx si;
+                    int d1_in, d1_out;
+                    if (!step_cross(E, d0, si.d1_cross, d1_in, d1_out)) continue;
+                    const float d0f = (float)d0;
+                    float dc2;                                   // rasterize.py:662-667
+                    if ((d0f - E.p[0][0]) * (d0f - E.p[2][0]) < 0) {
+                        dc2 = __fdiv_rn(E.p[2][1] - E.p[0][1], E.p[2][0] - E.p[0][0]);
+                        dc2 = dc2 * (d0f - E.p[0][0]);
+                        dc2 = dc2 + E.p[0][1];
+                    } else {
+                        dc2 = __fdiv_rn(E.p[1][1] - E.p[2][1], E.p[1][0] - E.p[2][0]);
+                        dc2 = dc2 * (d0f - E.p[2][0]);
+                        dc2 = dc2 + E.p[2][1];
+                    }
+                    const int d1_limit = (0 < E.direction) ? __float2int_rz(ceilf(dc2)) : __float2int_rz(floorf(dc2));
+                    const int d1_from = max(min(d1_in, d1_limit), 0);
+                    const int d1_to = min(max(d1_in, d1_limit), E.is1 - 1);
+                    if (d1 < d1_from || d1 > d1_to) continue;
+                    const size_t mi_out = axis == 0 ? (size_t)d1_out * P.Ws + d0 : (size_t)d0 * P.Ws + d1_out;
+                    const int idx_out = __ldg(fim + mi_out);
+                    si.ref_alpha = idx_out >= 0 ? 1.0f : 0.0f;
+                    si.ref_c[0] = si.ref_c[1] = si.ref_c[2] = 0.0f;
+                    if (P.use_rgb) colour_at(P, b, base_px + mi_out, idx_out, bg, si.ref_c);
+                    si.use0 = E.p[1][0] != d0f; si.use1 = E.p[0][0] != d0f;
+                    si.q0 = __fdiv_rn(E.dp, E.p[1][0] - d0f); si.q1 = __fdiv_rn(E.dp, d0f - E.p[0][0]);
+                    si.k0 = si.q0 * (2.0f / is1f); si.k1 = si.q1 * (2.0f / is1f);
+                    visit<true>(P, b, bg, base_px + mi, fn, xx, yy, d1, si, is1f, g0, g1);
+                }
+            }
+        }
+        g0 = warp_sum(g0); g1 = warp_sum(g1);
+        if (lane == 0) { ws.gpart[fo * 12 + kind * 2 + 0] = g0; ws.gpart[fo * 12 + kind * 2 + 1] = g1; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // exclusive scan of ws.scan_buf[0 .. n) (n = lines + 1 + 7 * visible faces + 1), three small kernels
 // ------------------------------------------------------------------------------------------------------------
@@ -1015,15 +1393,26 @@ constexpr int LM_ALPHA = 0;     // silhouette only: the positive part does not d
 constexpr int LM_SINGLE = 1;    // one reference pass (rgb, or alpha+rgb summed before the > 0 test)
 constexpr int LM_SPLIT = 2;     // alpha pass (eps_a) + rgb pass (eps_r), separate > 0 tests
 constexpr int LW = 8;           // warps (= adjacent lines) per CTA
-constexpr int LP = 8;           // pixels per lane per pass
-constexpr int LQ = 128;         // queries whose partial sums live in shared memory at a time
+constexpr int LP = 8;           // pixels per lane per pass (a pass = 256 pixels of the line, held in registers)
+constexpr int LQ = 32;          // queries staged per warp at a time; lane k owns query k's final reduction
 
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 relu2(float2 a) { return make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)); }
+__device__ __forceinline__ float2 rcp2(float2 a) { return make_float2(rcp_approx(a.x), rcp_approx(a.y)); }
+
+// Line sweep: one warp per raster line (8 adjacent lines per CTA so that column bundles share 32-byte sectors).
+// The warp walks its line in passes of 256 pixels held in registers (two pixels per float2) and, inside a pass, loops
+// over the line's queries with packed FP32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100): per pixel pair 3 FFMA2 for
+// the colour term, 4 for the distances, 2 reciprocals, and fused accumulates.  Partial sums stay per lane in shared
+// memory (conflict-free) and are reduced once per query chunk -- no shuffles or atomics in the hot loop, and every
+// query's result is written exactly once, in a fixed order (deterministic).
 template <int MODE>
 __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace ws) {
-    __shared__ float2 s_acc[LW][LQ];
+    extern __shared__ __align__(16) unsigned char s_line_dyn[];
+    float2 (*s_acc)[LQ][33] = reinterpret_cast<float2 (*)[LQ][33]>(s_line_dyn);
+    __shared__ Query s_q[LW][LQ];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_img = P.Hs + P.Ws;
-    // lines are grouped in bundles of LW so that the 8 columns of a bundle share 32-byte sectors
     const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
     const int bundles = bundles_rows + bundles_cols;
     const int b = blockIdx.x / bundles, bi = blockIdx.x % bundles;
@@ -1031,7 +1420,7 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
     if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
     else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
     const int line = b * per_img + (axis == 0 ? P.Hs : 0) + d0;
-    if (ws.scan_buf[ws.lines] > ws.qmax) return;       // nothing was deferred (see k_backward_items)
+    if (ws.scan_buf[ws.lines] > ws.qmax) return;       // nothing was deferred (see k_bwd_steps)
     const int qbeg = ws.scan_buf[line], qend = ws.scan_buf[line + 1];
     if (qbeg == qend) return;
     const int is1 = axis == 0 ? P.Hs : P.Ws;
@@ -1046,100 +1435,135 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
     const size_t plane = (size_t)P.H * P.W;
     const float* ga_p = P.g_alpha ? P.g_alpha + (size_t)b * plane : nullptr;
     const float* gr_p = P.g_rgb ? P.g_rgb + (size_t)b * 3 * plane : nullptr;
+    constexpr int LP2 = LP / 2;
 
     for (int qchunk = qbeg; qchunk < qend; qchunk += LQ) {
         const int qn = min(LQ, qend - qchunk);
-        for (int k = lane; k < qn; k += 32) s_acc[warp][k] = make_float2(0.0f, 0.0f);
-        __syncwarp();
-        // union of the chunk's ranges, to skip passes nobody needs
+        // stage the chunk's queries (lane k <-> query k); union of their ranges tells which passes are needed
         int ulo = 0x7fffffff, uhi = -1;
-        for (int k = lane; k < qn; k += 32) {
-            const Query& q = ws.queries[ws.line_items[qchunk + k]];
-            ulo = min(ulo, q.lo); uhi = max(uhi, q.hi_flags & 0xffff);
+        if (lane < qn) {
+            const Query q = ws.queries[ws.line_items[qchunk + lane]];
+            s_q[warp][lane] = q;
+            ulo = q.lo; uhi = q.hi_flags & 0xffff;
         }
+#pragma unroll 4
+        for (int k = 0; k < LQ; k++) s_acc[warp][k][lane] = make_float2(0.0f, 0.0f);
+        __syncwarp();
         ulo = __reduce_min_sync(FULL, ulo); uhi = __reduce_max_sync(FULL, uhi);
 
         for (int pbase = (ulo / (32 * LP)) * (32 * LP); pbase <= uhi; pbase += 32 * LP) {
-            // ---- pixel records of this pass: position j = pbase + i*32 + lane
-            float pa[LP], D[LP], g0v[LP], g1v[LP], g2v[LP];
+            // ---- pixel records of this pass; position j = pbase + i*32 + lane, pixels (2m, 2m+1) packed in a float2.
+            // All loads are issued before anything is consumed (memory-level parallelism: one latency per pass).
+            float2 pa[LP2], D[LP2], g0v[LP2], g1v[LP2], g2v[LP2];
+            {
+                int idxv[LP];
+                float gav[LP], r0[LP], r1[LP], r2[LP];
 #pragma unroll
-            for (int i = 0; i < LP; i++) {
-                const int j = pbase + i * 32 + lane;
-                pa[i] = 0.0f; D[i] = 0.0f; g0v[i] = 0.0f; g1v[i] = 0.0f; g2v[i] = 0.0f;
-                if (j < is1) {
+                for (int i = 0; i < LP; i++) {
+                    const int j = min(pbase + i * 32 + lane, is1 - 1);
                     const int xi = axis == 0 ? d0 : j, yi = axis == 0 ? j : d0;
-                    const size_t mi = (size_t)yi * P.Ws + xi;
-                    const int idx = __ldg(fim + mi);
                     const size_t oi = (size_t)(P.H - 1 - yi / P.ss) * P.W + xi / P.ss;
-                    float A = 0.0f;
-                    if (P.use_alpha && ga_p && idx < 0 && (MODE != LM_SINGLE || !P.split))
-                        A = -(__ldg(ga_p + oi) * sc);                                       // (alpha - 1) * g
-                    if (MODE == LM_ALPHA) { pa[i] = fmaxf(A, 0.0f); }
-                    else {
-                        float c[3];
-                        colour_at(P, b, (size_t)b * P.Hs * P.Ws + mi, idx, bg, c);
-                        if (gr_p) {
-                            g0v[i] = __ldg(gr_p + oi) * sc; g1v[i] = __ldg(gr_p + plane + oi) * sc;
-                            g2v[i] = __ldg(gr_p + 2 * plane + oi) * sc;
+                    idxv[i] = __ldg(fim + (size_t)yi * P.Ws + xi);
+                    gav[i] = (P.use_alpha && ga_p && (MODE != LM_SINGLE || !P.split)) ? __ldg(ga_p + oi) : 0.0f;
+                    if (MODE != LM_ALPHA && gr_p) {
+                        r0[i] = __ldg(gr_p + oi); r1[i] = __ldg(gr_p + plane + oi); r2[i] = __ldg(gr_p + 2 * plane + oi);
+                    } else { r0[i] = 0.0f; r1[i] = 0.0f; r2[i] = 0.0f; }
+                }
+#pragma unroll
+                for (int i = 0; i < LP; i++) {
+                    const int j = pbase + i * 32 + lane;
+                    float v_pa = 0.0f, v_D = 0.0f, v_g0 = 0.0f, v_g1 = 0.0f, v_g2 = 0.0f;
+                    if (j < is1) {
+                        const int idx = idxv[i];
+                        const float A = idx < 0 ? -(gav[i] * sc) : 0.0f;                   // (alpha - 1) * g
+                        if (MODE == LM_ALPHA) { v_pa = fmaxf(A, 0.0f); }
+                        else {
+                            const int xi = axis == 0 ? d0 : j, yi = axis == 0 ? j : d0;
+                            float c[3];
+                            colour_at(P, b, (size_t)b * P.Hs * P.Ws + (size_t)yi * P.Ws + xi, idx, bg, c);
+                            v_g0 = r0[i] * sc; v_g1 = r1[i] * sc; v_g2 = r2[i] * sc;
+                            const float d = __fmaf_rn(c[0], v_g0, __fmaf_rn(c[1], v_g1, c[2] * v_g2));
+                            if (MODE == LM_SPLIT) { v_pa = fmaxf(A, 0.0f); v_D = d; }
+                            else v_D = A + d;
                         }
-                        const float d = __fmaf_rn(c[0], g0v[i], __fmaf_rn(c[1], g1v[i], c[2] * g2v[i]));
-                        if (MODE == LM_SPLIT) { pa[i] = fmaxf(A, 0.0f); D[i] = d; }
-                        else D[i] = A + d;
                     }
+                    if (i & 1) { pa[i / 2].y = v_pa; D[i / 2].y = v_D; g0v[i / 2].y = v_g0; g1v[i / 2].y = v_g1; g2v[i / 2].y = v_g2; }
+                    else { pa[i / 2].x = v_pa; D[i / 2].x = v_D; g0v[i / 2].x = v_g0; g1v[i / 2].x = v_g1; g2v[i / 2].x = v_g2; }
                 }
             }
             const float xbase = (float)(pbase + lane);
             const int pass_hi = pbase + 32 * LP - 1;
             // ---- queries
             for (int k = 0; k < qn; k++) {
-                const Query q = ws.queries[ws.line_items[qchunk + k]];      // warp-uniform (broadcast) load
+                const Query q = s_q[warp][k];                               // broadcast read
                 const int lo = q.lo, hi = q.hi_flags & 0xffff;
                 if (hi < pbase || lo > pass_hi) continue;
-                const float e0a = (q.hi_flags & QF_POS0) ? ea : -ea, e0r = (q.hi_flags & QF_POS0) ? er : -er;
-                const float e1a = (q.hi_flags & QF_POS1) ? ea : -ea, e1r = (q.hi_flags & QF_POS1) ? er : -er;
-                float a0 = 0.0f, a1 = 0.0f;
+                const bool full = (lo <= pbase) && (hi >= pass_hi);        // every pixel of the pass is in range
+                const float2 e0a = f2((q.hi_flags & QF_POS0) ? ea : -ea), e1a = f2((q.hi_flags & QF_POS1) ? ea : -ea);
+                const float2 k0 = f2(q.k0), k1 = f2(q.k1);
+                float2 t = make_float2(xbase - q.xc, (xbase + 32.0f) - q.xc);
+                float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+                if (MODE == LM_ALPHA) {
 #pragma unroll
-                for (int i = 0; i < LP; i++) {
-                    const int j = pbase + i * 32 + lane;
-                    const bool in = (j >= lo) && (j <= hi);
-                    const float t = (xbase + (float)(i * 32)) - q.xc;
-                    if (MODE == LM_ALPHA) {
-                        const float p = in ? pa[i] : 0.0f;
-                        const float da0 = __fmaf_rn(q.k0, t, e0a), da1 = __fmaf_rn(q.k1, t, e1a);
-                        const float r = rcp_approx(da0 * da1);
-                        a0 = __fmaf_rn(p * da1, r, a0);
-                        a1 = __fmaf_rn(p * da0, r, a1);
-                    } else if (MODE == LM_SINGLE) {
-                        float dr = D[i] - __fmaf_rn(q.c0, g0v[i], __fmaf_rn(q.c1, g1v[i], q.c2 * g2v[i]));
-                        const float p = in ? fmaxf(dr, 0.0f) : 0.0f;
-                        const float da0 = __fmaf_rn(q.k0, t, e0a), da1 = __fmaf_rn(q.k1, t, e1a);
-                        const float r = rcp_approx(da0 * da1);
-                        a0 = __fmaf_rn(p * da1, r, a0);
-                        a1 = __fmaf_rn(p * da0, r, a1);
-                    } else {
-                        float dr = D[i] - __fmaf_rn(q.c0, g0v[i], __fmaf_rn(q.c1, g1v[i], q.c2 * g2v[i]));
-                        const float pr = in ? fmaxf(dr, 0.0f) : 0.0f;
-                        const float p = in ? pa[i] : 0.0f;
-                        const float da0 = __fmaf_rn(q.k0, t, e0a), dr0 = __fmaf_rn(q.k0, t, e0r);
-                        const float da1 = __fmaf_rn(q.k1, t, e1a), dr1 = __fmaf_rn(q.k1, t, e1r);
-                        const float p01 = da0 * dr0, p23 = da1 * dr1;
-                        const float r = rcp_approx(p01 * p23);
-                        const float n0 = __fmaf_rn(p, dr0, pr * da0), n1 = __fmaf_rn(p, dr1, pr * da1);
-                        a0 = __fmaf_rn(n0 * p23, r, a0);
-                        a1 = __fmaf_rn(n1 * p01, r, a1);
+                    for (int m = 0; m < LP2; m++) {
+                        const float2 da0 = __ffma2_rn(k0, t, e0a), da1 = __ffma2_rn(k1, t, e1a);
+                        const float2 r = rcp2(__fmul2_rn(da0, da1));
+                        float2 pm = pa[m];
+                        if (!full) {
+                            const int j0 = pbase + (2 * m) * 32 + lane, j1 = j0 + 32;
+                            if (j0 < lo || j0 > hi) pm.x = 0.0f;
+                            if (j1 < lo || j1 > hi) pm.y = 0.0f;
+                        }
+                        const float2 pr_ = __fmul2_rn(pm, r);
+                        a0 = __ffma2_rn(pr_, da1, a0);
+                        a1 = __ffma2_rn(pr_, da0, a1);
+                        t = __fadd2_rn(t, f2(64.0f));
+                    }
+                } else {
+                    const float2 nc0 = f2(-q.c0), nc1 = f2(-q.c1), nc2 = f2(-q.c2);
+                    const float2 e0r = f2((q.hi_flags & QF_POS0) ? er : -er), e1r = f2((q.hi_flags & QF_POS1) ? er : -er);
+#pragma unroll
+                    for (int m = 0; m < LP2; m++) {
+                        float2 dr = __ffma2_rn(nc0, g0v[m], D[m]);
+                        dr = __ffma2_rn(nc1, g1v[m], dr);
+                        dr = __ffma2_rn(nc2, g2v[m], dr);
+                        float2 pr = relu2(dr);
+                        float2 pm = pa[m];
+                        if (!full) {        // boundary pass: drop the pixels outside [lo, hi]
+                            const int j0 = pbase + (2 * m) * 32 + lane, j1 = j0 + 32;
+                            if (j0 < lo || j0 > hi) { pm.x = 0.0f; pr.x = 0.0f; }
+                            if (j1 < lo || j1 > hi) { pm.y = 0.0f; pr.y = 0.0f; }
+                        }
+                        if (MODE == LM_SINGLE) {
+                            const float2 da0 = __ffma2_rn(k0, t, e0a), da1 = __ffma2_rn(k1, t, e1a);
+                            const float2 r = __fmul2_rn(pr, rcp2(__fmul2_rn(da0, da1)));
+                            a0 = __ffma2_rn(r, da1, a0);
+                            a1 = __ffma2_rn(r, da0, a1);
+                        } else {
+                            const float2 da0 = __ffma2_rn(k0, t, e0a), dr0 = __ffma2_rn(k0, t, e0r);
+                            const float2 da1 = __ffma2_rn(k1, t, e1a), dr1 = __ffma2_rn(k1, t, e1r);
+                            const float2 r0 = rcp2(__fmul2_rn(da0, dr0)), r1 = rcp2(__fmul2_rn(da1, dr1));
+                            const float2 n0 = __ffma2_rn(pm, dr0, __fmul2_rn(pr, da0));
+                            const float2 n1 = __ffma2_rn(pm, dr1, __fmul2_rn(pr, da1));
+                            a0 = __ffma2_rn(n0, r0, a0);
+                            a1 = __ffma2_rn(n1, r1, a1);
+                        }
+                        t = __fadd2_rn(t, f2(64.0f));
                     }
                 }
-                a0 = warp_sum(a0); a1 = warp_sum(a1);
-                if (lane == 0) { float2 v = s_acc[warp][k]; v.x += a0; v.y += a1; s_acc[warp][k] = v; }
+                float2 v = s_acc[warp][k][lane];
+                v.x += a0.x + a0.y; v.y += a1.x + a1.y;
+                s_acc[warp][k][lane] = v;
             }
-            __syncwarp();
         }
-        for (int k = lane; k < qn; k += 32) {
-            const int qi = ws.line_items[qchunk + k];
-            const int hf = ws.queries[qi].hi_flags;
-            const float2 v = s_acc[warp][k];
+        __syncwarp();
+        if (lane < qn) {        // lane k reduces query k over the 32 per-lane partials, in lane order
+            float r0 = 0.0f, r1 = 0.0f;
+#pragma unroll 8
+            for (int l = 0; l < 32; l++) { const float2 v = s_acc[warp][lane][l]; r0 += v.x; r1 += v.y; }
+            const int hf = s_q[warp][lane].hi_flags;
             // g -= diff / dist   (rasterize.py:648,653)
-            ws.qres[qi] = make_float2((hf & QF_USE0) ? -v.x : 0.0f, (hf & QF_USE1) ? -v.y : 0.0f);
+            ws.qres[ws.line_items[qchunk + lane]] = make_float2((hf & QF_USE0) ? -r0 : 0.0f, (hf & QF_USE1) ? -r1 : 0.0f);
         }
         __syncwarp();
     }
@@ -1385,7 +1809,8 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
     if ((rc = check_launch())) return rc;
     const int grid = sm_count() * 4;
     if (P.line_path) {
-        k_backward_items<true, PH_COUNT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+        const int fgrid = sm_count() * 8;
+        k_bwd_steps<false><<<fgrid, 256, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
         const int sblocks = (ws.scan_n + SCAN_ELEMS - 1) / SCAN_ELEMS;
         k_scan_reduce<<<sblocks, 256, 0, st>>>(ws);
@@ -1394,18 +1819,29 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         if ((rc = check_launch())) return rc;
         k_scan_apply<<<sblocks, 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
-        k_backward_items<true, PH_EMIT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+        k_bwd_steps<true><<<fgrid, 256, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
-        const int Hs = P.Hs, Wsz = P.Ws;
-        const int bundles = (Hs + LW - 1) / LW + (Wsz + LW - 1) / LW;
+        k_bwd_face<<<sm_count() * 16, 256, 0, st>>>(P, ws);
+        if ((rc = check_launch())) return rc;
+        k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 1);      // no-op unless the queries overflowed
+        if ((rc = check_launch())) return rc;
+        const int bundles = (P.Hs + LW - 1) / LW + (P.Ws + LW - 1) / LW;
         const unsigned lgrid = (unsigned)(r->B * bundles);
-        if (P.use_alpha && !P.use_rgb) k_line_sweep<LM_ALPHA><<<lgrid, LW * 32, 0, st>>>(P, ws);
-        else if (P.use_alpha && P.use_rgb && P.split) k_line_sweep<LM_SPLIT><<<lgrid, LW * 32, 0, st>>>(P, ws);
-        else k_line_sweep<LM_SINGLE><<<lgrid, LW * 32, 0, st>>>(P, ws);
+        const size_t lsmem = sizeof(float2) * LW * LQ * 33;
+        if (P.use_alpha && !P.use_rgb) {
+            cudaFuncSetAttribute(k_line_sweep<LM_ALPHA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            k_line_sweep<LM_ALPHA><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
+        } else if (P.use_alpha && P.use_rgb && P.split) {
+            cudaFuncSetAttribute(k_line_sweep<LM_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            k_line_sweep<LM_SPLIT><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
+        } else {
+            cudaFuncSetAttribute(k_line_sweep<LM_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            k_line_sweep<LM_SINGLE><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
+        }
     } else if (P.fast_math) {
-        k_backward_items<true, PH_DIRECT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+        k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 0);
     } else {
-        k_backward_items<false, PH_DIRECT><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws);
+        k_backward_items<false><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 0);
     }
     if ((rc = check_launch())) return rc;
     k_grad_assemble<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(P, ws, g->grad_faces);
@@ -1496,8 +1932,13 @@ int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
     P.rgb = r->rgb; P.alpha = r->alpha; P.depth = r->depth; P.face_index = r->face_index; P.rgb_ss = r->rgb_ss;
     P.tiles_x = (Wss + TW - 1) / TW; P.tiles_y = (Hs + TH - 1) / TH;
     P.num_tiles = P.tiles_x * P.tiles_y * r->B;
-    const int grid = min(P.num_tiles, sm_count() * 6);
-    k_raster_tiles<<<grid, NT, 0, st>>>(P, ws);
+    k_fill_background<<<sm_count() * 8, 256, 0, st>>>(P);
+    if ((rc = check_launch())) return rc;
+    k_tile_prefix<<<1, 256, 0, st>>>(r->B, ws);
+    if ((rc = check_launch())) return rc;
+    const int grid = min(P.num_tiles, sm_count() * 4);
+    if (r->ss == 2) k_raster_tiles<2><<<grid, NT, 0, st>>>(P, ws);
+    else k_raster_tiles<1><<<grid, NT, 0, st>>>(P, ws);
     return check_launch();
 }
 
