@@ -150,6 +150,36 @@ __device__ __forceinline__ bool eval_sample(const float* f, const float* inv, fl
     return zp < c.far_f;        // depth_min starts at (float)far, rasterize.py:297; also rejects NaN
 }
 
+
+// Same arithmetic as eval_sample, split so that two samples can be evaluated with interleaved (independent) division
+// chains: `inside_test` is the three half-plane tests, `depth_of` the weights / depth / clip tests.
+__device__ __forceinline__ bool inside_test(const float* f, float xp, float yp) {
+    return !(((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) ||
+             ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) ||
+             ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7])));
+}
+__device__ __forceinline__ bool depth_of(const float* f, const float* inv, float xif, float yif, const Clip& c,
+                                         float& zp) {
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float t = inv[3 * k + 0] * xif;
+        float u = inv[3 * k + 1] * yif;
+        t = t + u;
+        w[k] = fminf(fmaxf(t + inv[3 * k + 2], 0.0f), 1.0f);
+    }
+    float ws = w[0] + w[1];
+    ws = ws + w[2];
+    w[0] = __fdiv_rn(w[0], ws);
+    w[1] = __fdiv_rn(w[1], ws);
+    w[2] = __fdiv_rn(w[2], ws);
+    float s = __fdiv_rn(w[0], f[2]) + __fdiv_rn(w[1], f[5]);
+    s = s + __fdiv_rn(w[2], f[8]);
+    zp = __fdiv_rn(1.0f, s);
+    if ((double)zp <= c.near_ || c.far_ <= (double)zp) return false;
+    return zp < c.far_f;
+}
+
 // rasterize.py:399-423: the 8 trilinear corners of one covered sample.  ti[k] float index along texture axis k.
 __device__ __forceinline__ void texture_index(const float* w, float depth, const float* f, int ts, double eps,
                                               float* tif) {
@@ -571,16 +601,22 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                         const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
                         const int bx0 = max((int)bb.x, sx0), bx1 = min((int)bb.z, sx1);
                         const int by0 = max((int)bb.y, sy0), by1 = min((int)bb.w, sy1);
-                        for (int yy = by0 + (lane >> 3); yy <= by1; yy += 4) {
-                            const float yp = s_yp[yy - sy0];
-                            const float yif = (float)yy;
-                            for (int xx = bx0 + (lane & 7); xx <= bx1; xx += 8) {
-                                float w[3], zp;
-                                if (eval_sample(f, inv, s_xp[xx - sx0], yp, (float)xx, yif, P.clip, w, zp)) {
-                                    const u64 key = ((u64)__float_as_uint(zp) << 32) | (unsigned)fn;
-                                    atomicMin(&s_key[(yy - sy0) * TW + (xx - sx0)], key);
-                                }
-                            }
+                        // two 8x4 sample blocks per iteration: their division chains are independent (ILP)
+                        const int nbx = (bx1 - bx0) / 8 + 1, nby = (by1 - by0) / 4 + 1, nblk = nbx * nby;
+                        for (int n0 = 0; n0 < nblk; n0 += 2) {
+                            int xa = bx0 + (n0 % nbx) * 8 + (lane & 7), ya = by0 + (n0 / nbx) * 4 + (lane >> 3);
+                            const int n1 = n0 + 1;
+                            int xb = bx0 + (n1 % nbx) * 8 + (lane & 7), yb = by0 + (n1 / nbx) * 4 + (lane >> 3);
+                            const bool va = xa <= bx1 && ya <= by1, vb = n1 < nblk && xb <= bx1 && yb <= by1;
+                            xa = min(xa, sx1); ya = min(ya, sy1); xb = min(xb, sx1); yb = min(yb, sy1);
+                            const bool ia = va && inside_test(f, s_xp[xa - sx0], s_yp[ya - sy0]);
+                            const bool ib = vb && inside_test(f, s_xp[xb - sx0], s_yp[yb - sy0]);
+                            if (!__any_sync(FULL, ia || ib)) continue;
+                            float za, zb;
+                            const bool oa = depth_of(f, inv, (float)xa, (float)ya, P.clip, za);
+                            const bool ob = depth_of(f, inv, (float)xb, (float)yb, P.clip, zb);
+                            if (ia && oa) atomicMin(&s_key[(ya - sy0) * TW + (xa - sx0)], ((u64)__float_as_uint(za) << 32) | (unsigned)fn);
+                            if (ib && ob) atomicMin(&s_key[(yb - sy0) * TW + (xb - sx0)], ((u64)__float_as_uint(zb) << 32) | (unsigned)fn);
                         }
                     }
                     __syncthreads();
@@ -1172,60 +1208,115 @@ __global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
     }
 }
 
+
+// Backward-only: weights and depth of a sample the face is known to own (no inclusion tests, reciprocal arithmetic).
+__device__ __forceinline__ void eval_owned_fast(const float* f, const float* inv, float xif, float yif, float* w,
+                                                float& zp) {
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        w[k] = fminf(fmaxf(__fmaf_rn(inv[3 * k], xif, __fmaf_rn(inv[3 * k + 1], yif, inv[3 * k + 2])), 0.0f), 1.0f);
+    const float rs = rcp_approx(w[0] + w[1] + w[2]);
+    w[0] *= rs; w[1] *= rs; w[2] *= rs;
+    zp = rcp_approx(w[0] * rcp_approx(f[2]) + w[1] * rcp_approx(f[5]) + w[2] * rcp_approx(f[8]));
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // fast path, step 2: everything that happens ON the samples a face owns -- the depth / texture gathers
 // (rasterize.py:747-844) and the in-sweeps (rasterize.py:659-727).  The reference walks each edge step across the
 // triangle; here each owned sample asks, for the six (edge, axis) items, whether the step through its own row / column
 // would have visited it (identical float tests), so the cost is proportional to the owned area.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bwd_face(BwdParams P, Workspace ws) {
+__global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
     const int lane = threadIdx.x & 31;
-    const int nunits = ws.vis_count[0] * ITEMS;
+    const int nvis = ws.vis_count[0];
     if (ws.scan_buf[ws.lines] > ws.qmax) return;    // the direct kernel does all of it
     const bool need_depth = P.use_depth && P.g_depth;
     const bool need_tex = P.use_rgb && P.g_rgb && P.grad_textures;
     const bool need_k6 = P.use_alpha || P.use_rgb;
     const float sc = (P.ss == 2) ? 0.25f : 1.0f;
-    // unit = (visible face, kind): kinds 0..5 are the in-sweeps of one (edge, axis), kind 6 the depth/texture gather
-    for (int u = blockIdx.x * 8 + (threadIdx.x >> 5); u < nunits; u += gridDim.x * 8) {
-        const size_t fo = (size_t)ws.vis_ids[u / ITEMS];
-        const int kind = u % ITEMS;
+    const size_t plane = (size_t)P.H * P.W;
+    const float ea = (float)P.eps_a, er = (float)P.eps_r;
+    const bool one_pass = !(P.split || !P.use_alpha);       // alpha and rgb summed before the > 0 test
+
+    for (;;) {
+        int vi = 0;
+        if (lane == 0) vi = atomicAdd(&ws.counters[2], 1);
+        vi = __shfl_sync(FULL, vi, 0);
+        if (vi >= nvis) break;
+        const size_t fo = (size_t)ws.vis_ids[vi];
         const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
         const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
         const size_t base_px = (size_t)b * P.Hs * P.Ws;
-        float f[9];
+        float f[9], inv[9], zf[9];
 #pragma unroll
-        for (int k = 0; k < 9; k++) f[k] = __ldg(P.faces + fo * 9 + k);
+        for (int k = 0; k < 9; k++) { f[k] = __ldg(P.faces + fo * 9 + k); inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
+        const float* zsrc = P.faces + ((size_t)(P.batch_bug ? 0 : b) * P.F + fn) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++) zf[k] = __ldg(zsrc + k);
         const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+        float bg[3];
+        if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+        else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+        const float* ga_p = (P.use_alpha && P.g_alpha) ? P.g_alpha + (size_t)b * plane : nullptr;
+        const float* gr_p = (P.use_rgb && P.g_rgb) ? P.g_rgb + (size_t)b * 3 * plane : nullptr;
+        const float* gd_p = need_depth ? P.g_depth + (size_t)b * plane : nullptr;
+        const int ts = P.ts == 1 ? 2 : P.ts;
 
-        if (kind == 6) {
-            float S[3] = {0.0f, 0.0f, 0.0f}, G[3] = {0.0f, 0.0f, 0.0f};
-            if (need_depth || need_tex) {
-                float inv[9], zf[9];
+        // ---- per-face constants of the six (edge, axis) items (rasterize.py:540-566), hoisted
+        float pc[3][2];                  // pixel coordinates [vertex][x|y]
 #pragma unroll
-                for (int k = 0; k < 9; k++) inv[k] = __ldg(ws.face_inv + fo * 9 + k);
-                const float* zsrc = P.faces + ((size_t)(P.batch_bug ? 0 : b) * P.F + fn) * 9;
+        for (int n = 0; n < 3; n++) { pc[n][0] = to_pixel(f[3 * n], P.Ws); pc[n][1] = to_pixel(f[3 * n + 1], P.Hs); }
+        float slope[2][3];               // [axis][edge e = (e, e+1)]: exact IEEE quotient, orientation-independent
 #pragma unroll
-                for (int k = 0; k < 9; k++) zf[k] = __ldg(zsrc + k);
-                const int ts = P.ts == 1 ? 2 : P.ts;
-                for (int yy = bb.y + (lane >> 3); yy <= bb.w; yy += 4) {
-                    for (int xx = bb.x + (lane & 7); xx <= bb.z; xx += 8) {
-                        const size_t mi = (size_t)yy * P.Ws + xx;
-                        if (__ldg(fim + mi) != fn) continue;
-                        const size_t oi = out_index(P, xx, yy);
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int e = 0; e < 3; e++)
+                slope[a][e] = __fdiv_rn(pc[(e + 1) % 3][1 - a] - pc[e][1 - a], pc[(e + 1) % 3][a] - pc[e][a]);
+        int d0_from[6], d0_to[6];
+#pragma unroll
+        for (int kind = 0; kind < 6; kind++) {
+            const int e = kind >> 1, a = kind & 1;
+            const float p00 = pc[e][a], p10 = pc[(e + 1) % 3][a];
+            const int is0 = a == 0 ? P.Ws : P.Hs;
+            d0_from[kind] = __double2int_rz(fmax((double)ceilf(fminf(p00, p10)), 0.));
+            d0_to[kind] = __double2int_rz(fmin((double)fmaxf(p00, p10), is0 - 1.));
+        }
+
+        float S[3] = {0.0f, 0.0f, 0.0f}, G[3] = {0.0f, 0.0f, 0.0f};
+        float acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[k] = 0.0f;
+
+        for (int yy0 = bb.y; yy0 <= bb.w; yy0 += 4) {
+            const int yy = yy0 + (lane >> 3);
+            for (int xx0 = bb.x; xx0 <= bb.z; xx0 += 32) {
+                int idv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {           // four independent loads in flight
+                    const int xx = xx0 + 8 * u + (lane & 7);
+                    idv[u] = (yy <= bb.w && xx <= bb.z) ? __ldg(fim + (size_t)yy * P.Ws + xx) : -2;
+                }
+#pragma unroll 1
+                for (int u = 0; u < 4; u++) {
+                    if (idv[u] != fn) continue;
+                    const int xx = xx0 + 8 * u + (lane & 7);
+                    const size_t mi = (size_t)yy * P.Ws + xx;
+                    const size_t oi = out_index(P, xx, yy);
+                    // gradients at this sample (one set of loads for everything below)
+                    const float ga = ga_p ? __ldg(ga_p + oi) * sc : 0.0f;
+                    float g[3] = {0.0f, 0.0f, 0.0f};
+                    if (gr_p) { g[0] = __ldg(gr_p + oi) * sc; g[1] = __ldg(gr_p + plane + oi) * sc; g[2] = __ldg(gr_p + 2 * plane + oi) * sc; }
+
+                    if (need_depth || need_tex) {
                         float w[3], zp;
-                        if (!eval_sample(f, inv, xp_of(xx, P.Ws), xp_of(yy, P.Hs), (float)xx, (float)yy, P.clip, w, zp))
-                            continue;
+                        eval_owned_fast(f, inv, (float)xx, (float)yy, w, zp);
                         if (need_depth) {      // rasterize.py:821-824: sum_s gd * w_k * depth^2
-                            const float gd = __ldg(P.g_depth + (size_t)b * P.H * P.W + oi) * sc;
+                            const float gd = __ldg(gd_p + oi) * sc;
                             const float d2 = zp * zp;
 #pragma unroll
                             for (int k = 0; k < 3; k++) S[k] += gd * w[k] * d2;
                         }
                         if (need_tex) {        // rasterize.py:772-778
-                            float g[3];
-#pragma unroll
-                            for (int k = 0; k < 3; k++) g[k] = __ldg(P.g_rgb + ((size_t)b * 3 + k) * P.H * P.W + oi) * sc;
                             float tif[3];
                             texture_index(w, zp, zf, ts, P.eps_tex, tif);
                             if (P.ts == 1) {
@@ -1247,67 +1338,92 @@ __global__ void __launch_bounds__(256) k_bwd_face(BwdParams P, Workspace ws) {
                             }
                         }
                     }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) { S[k] = warp_sum(S[k]); G[k] = warp_sum(G[k]); }
-            if (lane == 0) {
-                float* o = ws.gint + fo * 6;
-                o[0] = S[0]; o[1] = S[1]; o[2] = S[2]; o[3] = G[0]; o[4] = G[1]; o[5] = G[2];
-            }
-            continue;
-        }
+                    if (!need_k6) continue;
 
-        float g0 = 0.0f, g1 = 0.0f;
-        if (need_k6) {
-            const int axis = kind & 1;
-            EdgeSetup E;
-            edge_setup(f, kind >> 1, axis, P.Hs, P.Ws, E);
-            float bg[3];
-            if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
-            else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
-            const float is1f = (float)E.is1;
-            // only the part of the bbox the edge's steps can reach
-            int x0 = bb.x, x1 = bb.z, y0 = bb.y, y1 = bb.w;
-            if (axis == 0) { x0 = max(x0, E.d0_from); x1 = min(x1, E.d0_to); }
-            else { y0 = max(y0, E.d0_from); y1 = min(y1, E.d0_to); }
-            for (int yy = y0 + (lane >> 3); yy <= y1; yy += 4) {
-                for (int xx = x0 + (lane & 7); xx <= x1; xx += 8) {
-                    const size_t mi = (size_t)yy * P.Ws + xx;
-                    if (__ldg(fim + mi) != fn) continue;
-                    const int d0 = axis == 0 ? xx : yy, d1 = axis == 0 ? yy : xx;
-                    SweepCtx si;
-                    int d1_in, d1_out;
-                    if (!step_cross(E, d0, si.d1_cross, d1_in, d1_out)) continue;
-                    const float d0f = (float)d0;
-                    float dc2;                                   // rasterize.py:662-667
-                    if ((d0f - E.p[0][0]) * (d0f - E.p[2][0]) < 0) {
-                        dc2 = __fdiv_rn(E.p[2][1] - E.p[0][1], E.p[2][0] - E.p[0][0]);
-                        dc2 = dc2 * (d0f - E.p[0][0]);
-                        dc2 = dc2 + E.p[0][1];
-                    } else {
-                        dc2 = __fdiv_rn(E.p[1][1] - E.p[2][1], E.p[1][0] - E.p[2][0]);
-                        dc2 = dc2 * (d0f - E.p[2][0]);
-                        dc2 = dc2 + E.p[2][1];
+                    // ---- in-sweeps (rasterize.py:659-727): would the step through this sample's row / column have
+                    //      visited it?  Same float tests as the reference, evaluated per sample.
+                    float csel[3] = {0.0f, 0.0f, 0.0f};
+                    if (P.use_rgb) colour_at(P, b, base_px + mi, fn, bg, csel);
+                    float d1c[6];
+                    int d1o[6];
+                    unsigned inc = 0;
+#pragma unroll
+                    for (int kind = 0; kind < 6; kind++) {
+                        const int e = kind >> 1, a = kind & 1;
+                        const int i0 = e, i1 = (e + 1) % 3, i2 = (e + 2) % 3;
+                        const float p00 = pc[i0][a], p01 = pc[i0][1 - a], p10 = pc[i1][a], p11 = pc[i1][1 - a];
+                        const float p20 = pc[i2][a], p21 = pc[i2][1 - a];
+                        (void)p11;
+                        const int is1 = a == 0 ? P.Hs : P.Ws;
+                        const int d0 = a == 0 ? xx : yy, d1 = a == 0 ? yy : xx;
+                        const float d0f = (float)d0;
+                        int direction;
+                        if (a == 0) direction = (p00 < p10) ? -1 : 1; else direction = (p00 < p10) ? 1 : -1;
+                        float dc = slope[a][e] * (d0f - p00);
+                        dc = dc + p01;
+                        const int d1_in = (0 < direction) ? __float2int_rz(floorf(dc)) : __float2int_rz(ceilf(dc));
+                        const int d1_out = d1_in + direction;
+                        float dc2;                                   // rasterize.py:662-667
+                        if ((d0f - p00) * (d0f - p20) < 0) { dc2 = slope[a][i2] * (d0f - p00); dc2 = dc2 + p01; }
+                        else { dc2 = slope[a][i1] * (d0f - p20); dc2 = dc2 + p21; }
+                        const int d1_limit = (0 < direction) ? __float2int_rz(ceilf(dc2)) : __float2int_rz(floorf(dc2));
+                        const int d1_from = max(min(d1_in, d1_limit), 0), d1_to = min(max(d1_in, d1_limit), is1 - 1);
+                        const bool ok = d0 >= d0_from[kind] && d0 <= d0_to[kind] && d1_in >= 0 && d1_in < is1 &&
+                                        d1_out >= 0 && d1_out < is1 && d1 >= d1_from && d1 <= d1_to;
+                        d1c[kind] = dc; d1o[kind] = d1_out;
+                        if (ok) inc |= 1u << kind;
                     }
-                    const int d1_limit = (0 < E.direction) ? __float2int_rz(ceilf(dc2)) : __float2int_rz(floorf(dc2));
-                    const int d1_from = max(min(d1_in, d1_limit), 0);
-                    const int d1_to = min(max(d1_in, d1_limit), E.is1 - 1);
-                    if (d1 < d1_from || d1 > d1_to) continue;
-                    const size_t mi_out = axis == 0 ? (size_t)d1_out * P.Ws + d0 : (size_t)d0 * P.Ws + d1_out;
-                    const int idx_out = __ldg(fim + mi_out);
-                    si.ref_alpha = idx_out >= 0 ? 1.0f : 0.0f;
-                    si.ref_c[0] = si.ref_c[1] = si.ref_c[2] = 0.0f;
-                    if (P.use_rgb) colour_at(P, b, base_px + mi_out, idx_out, bg, si.ref_c);
-                    si.use0 = E.p[1][0] != d0f; si.use1 = E.p[0][0] != d0f;
-                    si.q0 = __fdiv_rn(E.dp, E.p[1][0] - d0f); si.q1 = __fdiv_rn(E.dp, d0f - E.p[0][0]);
-                    si.k0 = si.q0 * (2.0f / is1f); si.k1 = si.q1 * (2.0f / is1f);
-                    visit<true>(P, b, bg, base_px + mi, fn, xx, yy, d1, si, is1f, g0, g1);
+                    if (!inc) continue;
+                    int ido[6];
+#pragma unroll
+                    for (int kind = 0; kind < 6; kind++) {      // the out-pixel loads go out together
+                        const int a = kind & 1;
+                        const size_t mo = a == 0 ? (size_t)d1o[kind] * P.Ws + xx : (size_t)yy * P.Ws + d1o[kind];
+                        ido[kind] = (inc >> kind) & 1 ? __ldg(fim + mo) : -1;
+                    }
+#pragma unroll
+                    for (int kind = 0; kind < 6; kind++) {
+                        if (!((inc >> kind) & 1)) continue;
+                        const int e = kind >> 1, a = kind & 1;
+                        const float p00 = pc[e][a], p10 = pc[(e + 1) % 3][a];
+                        const int is1 = a == 0 ? P.Hs : P.Ws;
+                        const int d0 = a == 0 ? xx : yy, d1 = a == 0 ? yy : xx;
+                        const float d0f = (float)d0;
+                        const size_t mo = a == 0 ? (size_t)d1o[kind] * P.Ws + xx : (size_t)yy * P.Ws + d1o[kind];
+                        float da = ((1.0f - (ido[kind] >= 0 ? 1.0f : 0.0f)) * ga), dr = 0.0f;     // alpha here is 1
+                        if (P.use_rgb) {
+                            float co[3];
+                            colour_at(P, b, base_px + mo, ido[kind], bg, co);
+                            const float d = (csel[0] - co[0]) * g[0] + (csel[1] - co[1]) * g[1] + (csel[2] - co[2]) * g[2];
+                            if (one_pass) da += d; else dr = d;
+                        }
+                        const float pa = fmaxf(da, 0.0f), pr = fmaxf(dr, 0.0f);
+                        if (pa <= 0.0f && pr <= 0.0f) continue;
+                        const float t = (float)d1 - d1c[kind];
+                        const float dp = p10 - p00, k2 = 2.0f / (float)is1;
+                        const float x0 = dp * rcp_approx(p10 - d0f) * k2 * t, x1 = dp * rcp_approx(d0f - p00) * k2 * t;
+                        if (p10 != d0f) {
+                            const float a0 = (0.0f < x0) ? x0 + ea : x0 - ea, r0 = (0.0f < x0) ? x0 + er : x0 - er;
+                            acc[kind * 2] -= __fmaf_rn(pa, rcp_approx(a0), pr * rcp_approx(r0));
+                        }
+                        if (p00 != d0f) {
+                            const float a1 = (0.0f < x1) ? x1 + ea : x1 - ea, r1 = (0.0f < x1) ? x1 + er : x1 - er;
+                            acc[kind * 2 + 1] -= __fmaf_rn(pa, rcp_approx(a1), pr * rcp_approx(r1));
+                        }
+                    }
                 }
             }
         }
-        g0 = warp_sum(g0); g1 = warp_sum(g1);
-        if (lane == 0) { ws.gpart[fo * 12 + kind * 2 + 0] = g0; ws.gpart[fo * 12 + kind * 2 + 1] = g1; }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { S[k] = warp_sum(S[k]); G[k] = warp_sum(G[k]); }
+#pragma unroll
+        for (int k = 0; k < 12; k++) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+            float* o = ws.gint + fo * 6;
+            o[0] = S[0]; o[1] = S[1]; o[2] = S[2]; o[3] = G[0]; o[4] = G[1]; o[5] = G[2];
+#pragma unroll
+            for (int k = 0; k < 12; k++) ws.gpart[fo * 12 + k] = acc[k];
+        }
     }
 }
 
@@ -1569,6 +1685,24 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
     }
 }
 
+
+// adds the deferred out-sweep results of every (edge, axis) item onto its in-sweep partial, in step order
+__global__ void __launch_bounds__(256) k_item_sums(Workspace ws) {
+    if (ws.scan_buf[ws.lines] > ws.qmax) return;
+    const int n = ws.vis_count[0] * ITEMS;
+    const int* item_n = ws.scan_buf + ws.lines + 1;
+    const int q0 = item_n[0];
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+        const int kind = it % ITEMS;
+        if (kind == 6) continue;
+        float a0 = 0.0f, a1 = 0.0f;
+        const int qe = item_n[it + 1] - q0;
+        for (int q = item_n[it] - q0; q < qe; q++) { const float2 r = ws.qres[q]; a0 += r.x; a1 += r.y; }
+        float* part = ws.gpart + (size_t)ws.vis_ids[it / ITEMS] * 12 + kind * 2;
+        part[0] += a0; part[1] += a1;
+    }
+}
+
 // deterministic assembly of grad_faces [B,F,9] (+ per-face colour gradient when ts == 1)
 __global__ void k_grad_assemble(BwdParams P, Workspace ws, float* __restrict__ grad_faces) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1579,19 +1713,6 @@ __global__ void k_grad_assemble(BwdParams P, Workspace ws, float* __restrict__ g
         float part[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) part[k] = ws.gpart[(size_t)i * 12 + k];
-        if (P.line_path && ws.scan_buf[ws.lines] <= ws.qmax) {
-            // add the deferred out-sweeps of each (edge, axis) item, in step order (deterministic)
-            const int* item_n = ws.scan_buf + ws.lines + 1;
-            const int it0 = ws.vis_slot[i] * ITEMS, q0 = item_n[0];
-            for (int kind = 0; kind < 6; kind++) {
-                float a0 = 0.0f, a1 = 0.0f;
-                for (int q = item_n[it0 + kind] - q0; q < item_n[it0 + kind + 1] - q0; q++) {
-                    const float2 r = ws.qres[q];
-                    a0 += r.x; a1 += r.y;
-                }
-                part[kind * 2 + 0] += a0; part[kind * 2 + 1] += a1;
-            }
-        }
         if (P.use_alpha || P.use_rgb) {
 #pragma unroll
             for (int v = 0; v < 3; v++) {
@@ -1821,7 +1942,7 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         if ((rc = check_launch())) return rc;
         k_bwd_steps<true><<<fgrid, 256, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
-        k_bwd_face<<<sm_count() * 16, 256, 0, st>>>(P, ws);
+        k_bwd_face<<<sm_count() * 8, 128, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
         k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 1);      // no-op unless the queries overflowed
         if ((rc = check_launch())) return rc;
@@ -1844,6 +1965,10 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         k_backward_items<false><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 0);
     }
     if ((rc = check_launch())) return rc;
+    if (P.line_path) {
+        k_item_sums<<<sm_count() * 8, 256, 0, st>>>(ws);
+        if ((rc = check_launch())) return rc;
+    }
     k_grad_assemble<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(P, ws, g->grad_faces);
     return check_launch();
 }
