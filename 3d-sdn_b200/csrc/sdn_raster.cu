@@ -64,7 +64,9 @@ struct Workspace {
     int* line_items;        // [qmax]    query indices grouped by line
     struct Query* queries;  // [qmax]
     float2* qres;           // [qmax]    (g0, g1) of each query
-    int lines, qmax, scan_n;
+    int2* unit_tab;         // [umax]    (visible-face slot, block index) of every 4x32-sample unit of k_bwd_face
+    float* upart;           // [umax,18] per-unit partial sums
+    int lines, qmax, scan_n, umax;
     size_t zero_bytes;      // leading bytes cleared at the start of every forward
     size_t total;
 };
@@ -95,7 +97,9 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.lines = B * (Hs + Ws);
     const size_t qm = BF * 24;
     w.qmax = (int)(qm < 65536 ? 65536 : (qm > 6000000 ? 6000000 : qm));
-    w.scan_n = w.lines + 1 + (int)BF * 7 + 1;
+    w.scan_n = w.lines + 1 + (int)BF * 7 + 1 + (int)BF + 1;
+    const size_t um = BF * 2 + 65536;
+    w.umax = (int)(um > 2000000 ? 2000000 : um);
     w.vis_slot = (int*)(p + off); off = align_up(off + BF * 4, 256);
     w.scan_buf = (int*)(p + off); off = align_up(off + (size_t)w.scan_n * 4, 256);
     w.block_sums = (int*)(p + off); off = align_up(off + ((size_t)w.scan_n / 2048 + 2) * 4, 256);
@@ -103,6 +107,8 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.line_items = (int*)(p + off); off = align_up(off + (size_t)w.qmax * 4, 256);
     w.queries = (struct Query*)(p + off); off = align_up(off + (size_t)w.qmax * 32, 256);
     w.qres = (float2*)(p + off); off = align_up(off + (size_t)w.qmax * 8, 256);
+    w.unit_tab = (int2*)(p + off); off = align_up(off + (size_t)w.umax * 8, 256);
+    w.upart = (float*)(p + off); off = align_up(off + (size_t)w.umax * 72, 256);
     w.total = off;
     return w;
 }
@@ -849,6 +855,18 @@ constexpr int PH_EMIT = 2;      // write the queries, run in-sweeps and interior
 constexpr int ITEMS = 7;
 constexpr int BWD_WARPS = 4;
 
+// layout of ws.scan_buf: [lines + 1 | 7 per visible face + 1 | 1 per visible face + 1]; after the exclusive scan the
+// first region holds the per-line query bases, the second the per-item query bases, the third the per-face unit bases
+constexpr int ITEMS_ = 7;
+__device__ __forceinline__ int* item_region(const Workspace& ws) { return ws.scan_buf + ws.lines + 1; }
+__device__ __forceinline__ int* unit_region(const Workspace& ws) { return ws.scan_buf + ws.lines + 1 + ws.vis_count[0] * ITEMS_ + 1; }
+// the deferred work does not fit the workspace: the direct kernel (k_backward_items<true>) does everything instead
+__device__ __forceinline__ bool bwd_overflow(const Workspace& ws) {
+    const int* u = unit_region(ws);
+    return ws.scan_buf[ws.lines] > ws.qmax || (u[ws.vis_count[0]] - u[0]) > ws.umax;
+}
+constexpr int UNIT_W = 32, UNIT_H = 4;      // samples per unit of k_bwd_face
+
 // Direct form: every sweep runs inline, one warp per (face, edge, axis) item.  FAST = false is the exact-math parity
 // path; FAST = true is the fallback of the line-sweep path when the queries do not fit the workspace
 // (`only_on_overflow`): it returns at once unless that happened.
@@ -856,7 +874,7 @@ template <bool FAST>
 __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, Workspace ws, int only_on_overflow) {
     const int lane = threadIdx.x & 31;
     const int nitems = ws.vis_count[0] * ITEMS;
-    if (only_on_overflow && ws.scan_buf[ws.lines] <= ws.qmax) return;
+    if (only_on_overflow && !bwd_overflow(ws)) return;
     constexpr int PHASE = PH_DIRECT;
     constexpr int ticket = 1;
     int* item_n = ws.scan_buf + ws.lines + 1;
@@ -1099,6 +1117,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) k_backward_items(BwdParams P, 
 }
 
 
+
 // ------------------------------------------------------------------------------------------------------------
 // fast path, step 1: enumerate the edge steps of every visible face (rasterize.py:540-599) -- one warp per face,
 // the six (edge, axis) items in turn, lanes over the steps d0.  EMIT = false counts the out-sweep queries per item and
@@ -1145,8 +1164,9 @@ __global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
     const int lane = threadIdx.x & 31;
     const int nvis = ws.vis_count[0];
     int* item_n = ws.scan_buf + ws.lines + 1;       // counts, then (after the scan) exclusive bases
-    if (!EMIT && blockIdx.x == 0 && threadIdx.x == 0) item_n[nvis * ITEMS] = 0;        // scan sentinel
-    if (EMIT && ws.scan_buf[ws.lines] > ws.qmax) return;    // queries do not fit: k_backward_items<true> takes over
+    int* unit_n = unit_region(ws);
+    if (!EMIT && blockIdx.x == 0 && threadIdx.x == 0) { item_n[nvis * ITEMS] = 0; unit_n[nvis] = 0; }   // scan sentinels
+    if (EMIT && bwd_overflow(ws)) return;      // does not fit: k_backward_items<true> takes over
     const int q_origin = EMIT ? item_n[0] : 0;
     for (int vi = blockIdx.x * 8 + (threadIdx.x >> 5); vi < nvis; vi += gridDim.x * 8) {
         const size_t fo = (size_t)ws.vis_ids[vi];
@@ -1158,7 +1178,15 @@ __global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
         float bg[3];
         if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
         else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
-        if (!EMIT && lane == 0) item_n[vi * ITEMS + 6] = 0;
+        {   // units of k_bwd_face: the face's bbox cut into 4-row x 32-column blocks
+            const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+            const int nbx = (bb.z - bb.x) / UNIT_W + 1, nby = (bb.w - bb.y) / UNIT_H + 1;
+            if (!EMIT) { if (lane == 0) { item_n[vi * ITEMS + 6] = 0; unit_n[vi] = nbx * nby; } }
+            else {
+                const int ub = unit_n[vi] - unit_n[0];
+                for (int u = lane; u < nbx * nby; u += 32) ws.unit_tab[ub + u] = make_int2(vi, u);
+            }
+        }
         for (int kind = 0; kind < 6; kind++) {
             const int axis = kind & 1;
             EdgeSetup E;
@@ -1228,8 +1256,9 @@ __device__ __forceinline__ void eval_owned_fast(const float* f, const float* inv
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
     const int lane = threadIdx.x & 31;
-    const int nvis = ws.vis_count[0];
-    if (ws.scan_buf[ws.lines] > ws.qmax) return;    // the direct kernel does all of it
+    if (bwd_overflow(ws)) return;                    // the direct kernel does all of it
+    const int* unit_n = unit_region(ws);
+    const int nunits = unit_n[ws.vis_count[0]] - unit_n[0];
     const bool need_depth = P.use_depth && P.g_depth;
     const bool need_tex = P.use_rgb && P.g_rgb && P.grad_textures;
     const bool need_k6 = P.use_alpha || P.use_rgb;
@@ -1239,11 +1268,13 @@ __global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
     const bool one_pass = !(P.split || !P.use_alpha);       // alpha and rgb summed before the > 0 test
 
     for (;;) {
-        int vi = 0;
-        if (lane == 0) vi = atomicAdd(&ws.counters[2], 1);
-        vi = __shfl_sync(FULL, vi, 0);
-        if (vi >= nvis) break;
-        const size_t fo = (size_t)ws.vis_ids[vi];
+        // unit = one 4-row x 32-column block of a visible face's bbox: uniform, small pieces of work
+        int un = 0;
+        if (lane == 0) un = atomicAdd(&ws.counters[2], 1);
+        un = __shfl_sync(FULL, un, 0);
+        if (un >= nunits) break;
+        const int2 ut = ws.unit_tab[un];
+        const size_t fo = (size_t)ws.vis_ids[ut.x];
         const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
         const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
         const size_t base_px = (size_t)b * P.Hs * P.Ws;
@@ -1287,9 +1318,11 @@ __global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = 0.0f;
 
-        for (int yy0 = bb.y; yy0 <= bb.w; yy0 += 4) {
+        {
+            const int nbx = (bb.z - bb.x) / UNIT_W + 1;
+            const int yy0 = bb.y + (ut.y / nbx) * UNIT_H, xx0 = bb.x + (ut.y % nbx) * UNIT_W;
             const int yy = yy0 + (lane >> 3);
-            for (int xx0 = bb.x; xx0 <= bb.z; xx0 += 32) {
+            {
                 int idv[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {           // four independent loads in flight
@@ -1419,12 +1452,28 @@ __global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = warp_sum(acc[k]);
         if (lane == 0) {
-            float* o = ws.gint + fo * 6;
-            o[0] = S[0]; o[1] = S[1]; o[2] = S[2]; o[3] = G[0]; o[4] = G[1]; o[5] = G[2];
+            float* o = ws.upart + (size_t)un * 18;
 #pragma unroll
-            for (int k = 0; k < 12; k++) ws.gpart[fo * 12 + k] = acc[k];
+            for (int k = 0; k < 12; k++) o[k] = acc[k];
+            o[12] = S[0]; o[13] = S[1]; o[14] = S[2]; o[15] = G[0]; o[16] = G[1]; o[17] = G[2];
         }
     }
+}
+
+// sums the unit partials of every visible face, in unit order (deterministic)
+__global__ void __launch_bounds__(256) k_face_sums(Workspace ws) {
+    if (bwd_overflow(ws)) return;
+    const int nvis = ws.vis_count[0];
+    const int* unit_n = unit_region(ws);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int vi = t / 18, k = t % 18;
+    if (vi >= nvis) return;
+    float a = 0.0f;
+    const int ue = unit_n[vi + 1] - unit_n[0];
+    for (int u = unit_n[vi] - unit_n[0]; u < ue; u++) a += ws.upart[(size_t)u * 18 + k];
+    const size_t fo = (size_t)ws.vis_ids[vi];
+    if (k < 12) ws.gpart[fo * 12 + k] = a;
+    else ws.gint[fo * 6 + (k - 12)] = a;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1432,7 +1481,7 @@ __global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SCAN_ELEMS = 2048;        // per block of 256 threads
 
-__device__ __forceinline__ int scan_len(const Workspace& ws) { return ws.lines + 1 + ws.vis_count[0] * ITEMS + 1; }
+__device__ __forceinline__ int scan_len(const Workspace& ws) { return ws.lines + 1 + ws.vis_count[0] * ITEMS + 1 + ws.vis_count[0] + 1; }
 
 __device__ __forceinline__ int block_exclusive_scan_256(int v, int* s_warp, int& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1536,7 +1585,7 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
     if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
     else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
     const int line = b * per_img + (axis == 0 ? P.Hs : 0) + d0;
-    if (ws.scan_buf[ws.lines] > ws.qmax) return;       // nothing was deferred (see k_bwd_steps)
+    if (bwd_overflow(ws)) return;                       // nothing was deferred (see k_bwd_steps)
     const int qbeg = ws.scan_buf[line], qend = ws.scan_buf[line + 1];
     if (qbeg == qend) return;
     const int is1 = axis == 0 ? P.Hs : P.Ws;
@@ -1688,7 +1737,7 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
 
 // adds the deferred out-sweep results of every (edge, axis) item onto its in-sweep partial, in step order
 __global__ void __launch_bounds__(256) k_item_sums(Workspace ws) {
-    if (ws.scan_buf[ws.lines] > ws.qmax) return;
+    if (bwd_overflow(ws)) return;
     const int n = ws.vis_count[0] * ITEMS;
     const int* item_n = ws.scan_buf + ws.lines + 1;
     const int q0 = item_n[0];
@@ -1943,6 +1992,8 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         k_bwd_steps<true><<<fgrid, 256, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
         k_bwd_face<<<sm_count() * 8, 128, 0, st>>>(P, ws);
+        if ((rc = check_launch())) return rc;
+        k_face_sums<<<(unsigned)((BF * 18 + 255) / 256), 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
         k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 1);      // no-op unless the queries overflowed
         if ((rc = check_launch())) return rc;
