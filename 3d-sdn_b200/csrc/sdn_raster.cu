@@ -23,6 +23,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
 
 #include "sdn_b200.h"
 
@@ -36,6 +41,36 @@ constexpr unsigned FULL = 0xffffffffu;
 typedef unsigned long long u64;
 
 std::atomic<long long> g_launches{0};
+
+// Optional per-kernel timing (sdn_timing_enable): every launch is bracketed by CUDA events on the launching stream.
+// Off by default; it is diagnostic state only and never influences results.
+std::atomic<int> g_timing{0};
+std::mutex g_timing_mu;
+struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
+std::vector<TimedLaunch> g_timed;
+const char* g_pending_name = nullptr;
+cudaEvent_t g_pending_e0 = nullptr;
+cudaStream_t g_pending_stream = nullptr;
+
+inline void timing_begin(const char* name, cudaStream_t st) {
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    cudaEvent_t e0;
+    if (cudaEventCreate(&e0) != cudaSuccess) return;
+    cudaEventRecord(e0, st);
+    g_pending_name = name; g_pending_e0 = e0; g_pending_stream = st;
+}
+inline void timing_end() {
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (!g_pending_name) return;
+    cudaEvent_t e1;
+    if (cudaEventCreate(&e1) == cudaSuccess) {
+        cudaEventRecord(e1, g_pending_stream);
+        g_timed.push_back({g_pending_name, g_pending_e0, e1});
+    }
+    g_pending_name = nullptr;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // workspace
@@ -1902,6 +1937,7 @@ __global__ void k_faces_backward_vertex(const float* __restrict__ vertices, int 
 // ------------------------------------------------------------------------------------------------------------
 inline int check_launch() {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    timing_end();
     return (int)cudaPeekAtLastError();
 }
 
@@ -1975,26 +2011,35 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         if ((e = cudaMemsetAsync(P.grad_textures, 0, nb, st)) != cudaSuccess) return (int)e;
     }
     const long BF = (long)r->B * r->F;
+    timing_begin("k_compact_visible", st);
     k_compact_visible<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(r->B, r->F, ws);
     if ((rc = check_launch())) return rc;
     const int grid = sm_count() * 4;
     if (P.line_path) {
         const int fgrid = sm_count() * 8;
+        timing_begin("k_bwd_steps", st);
         k_bwd_steps<false><<<fgrid, 256, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
         const int sblocks = (ws.scan_n + SCAN_ELEMS - 1) / SCAN_ELEMS;
+        timing_begin("k_scan_reduce", st);
         k_scan_reduce<<<sblocks, 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
+        timing_begin("k_scan_sums", st);
         k_scan_sums<<<1, 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
+        timing_begin("k_scan_apply", st);
         k_scan_apply<<<sblocks, 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
+        timing_begin("k_bwd_steps", st);
         k_bwd_steps<true><<<fgrid, 256, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
+        timing_begin("k_bwd_face", st);
         k_bwd_face<<<sm_count() * 8, 128, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
+        timing_begin("k_face_sums", st);
         k_face_sums<<<(unsigned)((BF * 18 + 255) / 256), 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
+        timing_begin("k_backward_items", st);
         k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 1);      // no-op unless the queries overflowed
         if ((rc = check_launch())) return rc;
         const int bundles = (P.Hs + LW - 1) / LW + (P.Ws + LW - 1) / LW;
@@ -2002,24 +2047,31 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         const size_t lsmem = sizeof(float2) * LW * LQ * 33;
         if (P.use_alpha && !P.use_rgb) {
             cudaFuncSetAttribute(k_line_sweep<LM_ALPHA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            timing_begin("k_line_sweep", st);
             k_line_sweep<LM_ALPHA><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
         } else if (P.use_alpha && P.use_rgb && P.split) {
             cudaFuncSetAttribute(k_line_sweep<LM_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            timing_begin("k_line_sweep", st);
             k_line_sweep<LM_SPLIT><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
         } else {
             cudaFuncSetAttribute(k_line_sweep<LM_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            timing_begin("k_line_sweep", st);
             k_line_sweep<LM_SINGLE><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
         }
     } else if (P.fast_math) {
+        timing_begin("k_backward_items", st);
         k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 0);
     } else {
+        timing_begin("k_backward_items", st);
         k_backward_items<false><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 0);
     }
     if ((rc = check_launch())) return rc;
     if (P.line_path) {
+        timing_begin("k_item_sums", st);
         k_item_sums<<<sm_count() * 8, 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
     }
+    timing_begin("k_grad_assemble", st);
     k_grad_assemble<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(P, ws, g->grad_faces);
     return check_launch();
 }
@@ -2034,6 +2086,36 @@ extern "C" {
 int sdn_version(void) { return SDN_VERSION; }
 
 long long sdn_launch_count(void) { return g_launches.load(); }
+
+int sdn_timing_enable(int on) {
+    g_timing.store(on ? 1 : 0);
+    return 0;
+}
+
+// Writes "kernel_name total_ms launches\n" lines (aggregated since the last read) into buf; returns bytes written.
+int sdn_timing_read(char* buf, int cap) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    struct Agg { std::string name; double ms; int n; };
+    std::vector<Agg> agg;
+    for (auto& t : g_timed) {
+        cudaEventSynchronize(t.e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, t.e0, t.e1);
+        cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+        bool found = false;
+        for (auto& a : agg) if (a.name == t.name) { a.ms += ms; a.n += 1; found = true; break; }
+        if (!found) agg.push_back({t.name, ms, 1});
+    }
+    g_timed.clear();
+    int off = 0;
+    for (auto& a : agg) {
+        const int w = snprintf(buf ? buf + off : nullptr, buf ? (size_t)(cap - off > 0 ? cap - off : 0) : 0, "%s %.6f %d\n",
+                               a.name.c_str(), a.ms, a.n);
+        if (w < 0 || off + w >= cap) break;
+        off += w;
+    }
+    return off;
+}
 
 const char* sdn_error_string(int code) {
     if (code == 0) return "ok";
@@ -2054,6 +2136,7 @@ int sdn_faces_forward(const float* vertices, const int32_t* faces, int B, int nv
     if (!vertices || !faces || !face_ndc || B <= 0 || nv <= 0 || nf <= 0) return SDN_E_ARG;
     if (cam && cam->width_x && !cam->width_y) return SDN_E_ARG;
     const long n = (long)B * (fill_back ? 2 * nf : nf);
+    timing_begin("k_faces_forward", (cudaStream_t)stream);
     k_faces_forward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         vertices, faces, B, nv, nf, faces_batched, fill_back, make_cam(cam), face_ndc, face_normal);
     return check_launch();
@@ -2075,12 +2158,14 @@ int sdn_faces_backward(const float* grad_face_ndc, const float* grad_face_normal
     const long n = (long)B * (fill_back ? 2 * nf : nf);
     int rc;
     if (grad_face_ndc || grad_face_normal) {
+        timing_begin("k_faces_backward_scatter", st);
         k_faces_backward_scatter<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
             grad_face_ndc, grad_face_normal, vertices, faces, B, nv, nf, faces_batched, fill_back, c.flip, acc_ndc,
             acc_pre);
         if ((rc = check_launch())) return rc;
     }
     const long nvt = (long)B * nv;
+    timing_begin("k_faces_backward_vertex", st);
     k_faces_backward_vertex<<<(unsigned)((nvt + 255) / 256), 256, 0, st>>>(vertices, B, nv, c, acc_ndc, acc_pre,
                                                                            grad_vertices);
     return check_launch();
@@ -2095,6 +2180,7 @@ int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
     if (e != cudaSuccess) return (int)e;
     const int Hs = r->H * r->ss, Wss = r->W * r->ss;
     const long BF = (long)r->B * r->F;
+    timing_begin("k_face_setup", st);
     k_face_setup<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(r->faces, r->B, r->F, Hs, Wss, ws);
     if ((rc = check_launch())) return rc;
 
@@ -2108,13 +2194,15 @@ int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
     P.rgb = r->rgb; P.alpha = r->alpha; P.depth = r->depth; P.face_index = r->face_index; P.rgb_ss = r->rgb_ss;
     P.tiles_x = (Wss + TW - 1) / TW; P.tiles_y = (Hs + TH - 1) / TH;
     P.num_tiles = P.tiles_x * P.tiles_y * r->B;
+    timing_begin("k_fill_background", st);
     k_fill_background<<<sm_count() * 8, 256, 0, st>>>(P);
     if ((rc = check_launch())) return rc;
+    timing_begin("k_tile_prefix", st);
     k_tile_prefix<<<1, 256, 0, st>>>(r->B, ws);
     if ((rc = check_launch())) return rc;
     const int grid = min(P.num_tiles, sm_count() * 4);
-    if (r->ss == 2) k_raster_tiles<2><<<grid, NT, 0, st>>>(P, ws);
-    else k_raster_tiles<1><<<grid, NT, 0, st>>>(P, ws);
+    if (r->ss == 2) { timing_begin("k_raster_tiles", st); k_raster_tiles<2><<<grid, NT, 0, st>>>(P, ws); }
+    else { timing_begin("k_raster_tiles", st); k_raster_tiles<1><<<grid, NT, 0, st>>>(P, ws); }
     return check_launch();
 }
 

@@ -1,0 +1,54 @@
+"""Image encoder of the geometric branch (reference: derender3d/models/derenderer.py:7-65): ResNet-18 trunk + three
+fully connected layers + head split.  Attribute names (net, relu, fc1, fc2, _fc3) match the reference so that its
+checkpoints load unchanged.  The convolutions are library GEMMs (cuDNN through torchvision): DESIGN.md "Encoder"."""
+import os
+
+import torch
+import torchvision
+from torch.nn.modules import Module
+
+
+class Derenderer(Module):
+    in_size = 4
+    hidden_size = 256
+
+    def __init__(self, num_classes=8, grid_size=4):
+        super(Derenderer, self).__init__()
+        self.num_classes = num_classes
+        self.grid_size = grid_size
+        self.out_sizes = {
+            '_theta_deltas': 2,
+            '_translation2ds': 2,
+            '_log_scales': 3,
+            '_log_depths': 1,
+            '_class_probs': num_classes,
+            '_ffd_coeffs': num_classes * (grid_size ** 3) * 3,
+        }
+        # derenderer.py:25 asks for ImageNet weights; there is no network here, so they are loaded only if a local
+        # file is named (RESNET18_WEIGHTS); a 3D-SDN checkpoint overwrites them anyway.
+        self.net = torchvision.models.resnet18(weights=None)
+        path = os.environ.get('RESNET18_WEIGHTS')
+        if path and os.path.isfile(path):
+            self.net.load_state_dict(torch.load(path, map_location='cpu'))
+        self.net.avgpool = torch.nn.AdaptiveAvgPool2d(1)
+        self.net.fc = torch.nn.Linear(512, Derenderer.hidden_size)
+        self.relu = torch.nn.ReLU(inplace=True)
+        self.fc1 = torch.nn.Linear(self.hidden_size + self.in_size, self.hidden_size)
+        self.fc2 = torch.nn.Linear(self.hidden_size, self.hidden_size)
+        self._fc3 = torch.nn.Linear(self.hidden_size, sum(self.out_sizes.values()))
+
+    def forward(self, images, mroi_norms, droi_norms):
+        x = self.relu(self.net(images))
+        x = torch.cat([x.float(), mroi_norms, droi_norms], dim=1)
+        x = self.relu(self.fc1(x))
+        x = self.relu(self.fc2(x))
+        x = self._fc3(x)
+        (theta, t2d, log_scales, log_depths, class_logits, ffd) = torch.split(x, list(self.out_sizes.values()), dim=1)
+        return {
+            '_theta_deltas': theta / torch.norm(theta, p=2, dim=1, keepdim=True),
+            '_translation2ds': t2d,
+            '_log_scales': log_scales,
+            '_log_depths': log_depths,
+            '_class_probs': torch.nn.functional.softmax(class_logits, dim=1),
+            '_ffd_coeffs': ffd.reshape(-1, self.num_classes, (self.grid_size ** 3) * 3),
+        }

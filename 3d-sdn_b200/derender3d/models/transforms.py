@@ -1,0 +1,124 @@
+"""Mesh deformation and camera-space transform of the geometric branch (reference:
+derender3d/models/transforms.py:10-158), batched and device-resident.
+
+Differences from the reference, none of them numerical:
+  * FFD keeps its Bernstein tensor as a registered buffer (moved once with the module) instead of re-uploading
+    ~4.8 MB on every call (transforms.py:97), and accepts a batch of coefficient vectors [N,192] -> [N,nv,3];
+  * the deformation is evaluated as one [nv,64] x [64,3] product per object instead of a broadcast multiply + sum.
+"""
+import numpy as np
+import scipy.special
+import torch
+from torch.nn.modules import Module
+
+
+class FFD(Module):
+    """Free-form deformation of a fixed vertex set by a 4x4x4 Bezier lattice (transforms.py:10-99)."""
+
+    class Constraint:
+        class Type:
+            symmetry = 0
+            homogeneity = 1
+
+        class Axis:
+            x = 0
+            y = 1
+            z = 2
+
+        @staticmethod
+        def symmetry(axis):
+            c = FFD.Constraint(FFD.Constraint.Type.symmetry)
+            c.axis = axis
+            return c
+
+        @staticmethod
+        def homogeneity(axis, index):
+            c = FFD.Constraint(FFD.Constraint.Type.homogeneity)
+            c.axis = axis
+            c.index = index
+            return c
+
+        def __init__(self, type):
+            self.type = type
+
+    def __init__(self, vertices, num_grids=4, constraints=None):
+        super(FFD, self).__init__()
+        assert num_grids % 2 == 0
+        self.num_grids = num_grids
+        self.constraints = constraints or []
+        vertices = torch.as_tensor(vertices, dtype=torch.float32)
+        grids = np.arange(num_grids)
+        binoms = torch.tensor(scipy.special.binom(num_grids - 1, grids), dtype=torch.float32)
+        g1 = torch.tensor(grids, dtype=torch.float32)
+        # Bernstein basis per axis: C(n,i) (0.5+v)^i (0.5-v)^(n-i)        (transforms.py:57-61)
+        coeff = (binoms * torch.pow((0.5 + vertices).unsqueeze(2), g1) *
+                 torch.pow((0.5 - vertices).unsqueeze(2), num_grids - 1 - g1))
+        cx, cy, cz = coeff.unbind(dim=1)
+        B = torch.einsum('ni,nj,nk->nijk', cx, cy, cz)                      # [nv,4,4,4]   (transforms.py:63)
+        g3 = torch.tensor(np.stack(np.meshgrid(grids, grids, grids, indexing='ij')), dtype=torch.float32)
+        self.register_buffer('B', B.unsqueeze(1), persistent=False)          # [nv,1,4,4,4] like the reference
+        self.register_buffer('P0', g3 / (num_grids - 1) - 0.5, persistent=False)   # [3,4,4,4]   (transforms.py:66)
+
+    def constrain(self, dP):
+        """dP [...,3,n,n,n] -> constrained offsets (transforms.py:71-95)."""
+        n = self.num_grids
+        for c in self.constraints:
+            dim = dP.dim() - 3 + c.axis
+            if c.type == FFD.Constraint.Type.symmetry:
+                sign = dP.new_tensor([1.0, 1.0, -1.0]).view(3, 1, 1, 1)
+                dP = (dP + dP.flip(dim) * sign) / 2
+            elif c.type == FFD.Constraint.Type.homogeneity:
+                slices = list(dP.unbind(dim))
+                mean = sum(slices[i] for i in c.index) / len(c.index)
+                comp = dP.dim() - 4                      # dimension of the xyz component in a slice
+                for i in c.index:
+                    keep = slices[i].select(comp, c.axis)
+                    merged = mean.clone()
+                    merged.select(comp, c.axis).copy_(keep)
+                    slices[i] = merged
+                dP = torch.stack(slices, dim=dim)
+        return dP
+
+    def forward(self, ffd_coeff):
+        """ffd_coeff [3*n^3] -> [nv,3]   or   [N,3*n^3] -> [N,nv,3]."""
+        n = self.num_grids
+        single = ffd_coeff.dim() == 1
+        dP = ffd_coeff.reshape(-1, 3, n, n, n)
+        P = (self.P0.to(dP.device) + self.constrain(dP)).reshape(-1, 3, n * n * n)        # [N,3,64]
+        V = torch.matmul(self.B.to(dP.device).reshape(-1, n * n * n), P.transpose(1, 2))  # [N,nv,3]
+        return V[0] if single else V
+
+
+class PerspectiveTransform(Module):
+    """Scale, rotate (unit quaternion), translate, shear along the principal ray, zoom (transforms.py:102-158)."""
+
+    def forward(self, vertices, scales=None, rotations=None, translations=None, perspective_translations=None,
+                zooms=None, zoom_tos=None):
+        if scales is not None:
+            vertices = vertices * scales.unsqueeze(1)
+        if rotations is not None:
+            a, b, c, d = rotations.unbind(dim=1)
+            T = torch.stack([
+                a * a + b * b - c * c - d * d, 2 * b * c - 2 * a * d, 2 * b * d + 2 * a * c,
+                2 * b * c + 2 * a * d, a * a - b * b + c * c - d * d, 2 * c * d - 2 * a * b,
+                2 * b * d - 2 * a * c, 2 * c * d + 2 * a * b, a * a - b * b - c * c + d * d,
+            ], dim=1).view(-1, 3, 3)
+            vertices = torch.matmul(vertices, T.transpose(1, 2))
+        if translations is not None:
+            translations = translations.unsqueeze(1)
+            vertices = vertices + translations
+        if perspective_translations is not None:
+            perspective_translations = perspective_translations.unsqueeze(1)
+        else:
+            perspective_translations = translations
+        x, y, z = vertices.unbind(dim=2)
+        x0, y0, z0 = perspective_translations.unbind(dim=2)
+        x = x - x0 / z0 * z
+        y = y - y0 / z0 * z
+        if zoom_tos is not None:
+            zooms = torch.min(torch.abs(z) / torch.max(torch.abs(x), torch.abs(y)), dim=1, keepdim=True)[0] * zoom_tos
+        z = z / zooms
+        vertices = torch.stack([x, y, z], dim=2)
+        if zoom_tos is None:
+            return vertices
+        return vertices, zooms

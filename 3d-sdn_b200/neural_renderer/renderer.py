@@ -93,13 +93,16 @@ class Renderer(object):
         wx = wy = None
         if self.perspective:
             if multi_angle:
-                tan = [perspective_width(a) for a in angle.detach().cpu().tolist()]
+                # per-image angles stay on the device (no host sync): the float32 steps of perspective.py:10-13
+                a = angle.detach().to(device=dev, dtype=torch.float32).reshape(-1)
+                a = (a / 180.0) * 3.1416
+                wy = torch.tan(a.double()).float()
+                wx = wy if H == W else wy * float(np.float32(W / H))
             else:
-                tan = [perspective_width(float(angle))] * bs
-            wy_np = np.asarray(tan, np.float32)
-            wx_np = wy_np if H == W else (wy_np * np.float32(W / H)).astype(np.float32)
-            wy = torch.from_numpy(wy_np).to(dev)
-            wx = torch.from_numpy(wx_np).to(dev)
+                wy_np = np.asarray([perspective_width(float(angle))] * bs, np.float32)
+                wx_np = wy_np if H == W else (wy_np * np.float32(W / H)).astype(np.float32)
+                wy = torch.from_numpy(wy_np).to(dev)
+                wx = torch.from_numpy(wx_np).to(dev)
         cam = sdn_b200.Camera(rot, eye, wx, wy, self.flip_x)
         if key is not None:
             if len(Renderer._camera_cache) > 64:

@@ -60,6 +60,8 @@ def lib():
         L.sdn_workspace_bytes.restype = ctypes.c_size_t
         L.sdn_workspace_bytes.argtypes = [ctypes.c_int] * 4
         L.sdn_launch_count.restype = ctypes.c_longlong
+        L.sdn_timing_enable.argtypes = [ctypes.c_int]
+        L.sdn_timing_read.argtypes = [ctypes.c_char_p, ctypes.c_int]
         vp, ci = ctypes.c_void_p, ctypes.c_int
         L.sdn_faces_forward.argtypes = [vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(_Camera), vp, vp, vp]
         L.sdn_faces_backward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(_Camera), vp, vp,
@@ -74,6 +76,22 @@ def lib():
 
 def launch_count():
     return int(lib().sdn_launch_count())
+
+
+def timing_enable(on=True):
+    """Bracket every kernel launch of the library with CUDA events (diagnostics; off by default)."""
+    lib().sdn_timing_enable(int(bool(on)))
+
+
+def timing_read():
+    """-> {kernel_name: (total_ms, launches)} since the last read."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib().sdn_timing_read(buf, len(buf))
+    out = {}
+    for line in buf.raw[:n].decode().splitlines():
+        name, ms, cnt = line.split()
+        out[name] = (float(ms), int(cnt))
+    return out
 
 
 def _check(rc):

@@ -25,6 +25,8 @@ for _p in (ROOT, os.path.join(ROOT, '3d-sdn_b200')):
 import torch  # noqa: E402
 
 H, W, SS = 375, 1242, 2
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {}
 NF_EFF = 2 * 1984
 C_OUT = 5
 
@@ -166,6 +168,15 @@ def run_ours(args):
 
     # per-call device time of the four C-ABI calls (events on the launching stream = torch's current stream)
     seg = segment_times(renderer, v_dev, f_dev, g_dev, fast, steps=max(5, min(args.steps, 20)))
+    # per-kernel device time: the library brackets each of its launches with CUDA events on that same stream
+    ksteps = max(5, min(args.steps, 20))
+    sdn_b200.timing_enable(True)
+    sdn_b200.timing_read()
+    for _ in range(ksteps):
+        step_resident()
+    torch.cuda.synchronize()
+    kern = {k: v[0] / ksteps for k, v in sdn_b200.timing_read().items()}
+    sdn_b200.timing_enable(False)
 
     images = B * world * args.steps
     value = images / (ms * 1e-3)
@@ -188,14 +199,17 @@ def run_ours(args):
     if rank == 0:
         fwd_b, bwd_b = algorithmic_bytes()
         peak, how = measured_peaks()
-        dom = max(seg, key=lambda k: seg[k])
-        algo = {'rasterize_forward': fwd_b * B, 'rasterize_backward': bwd_b * B}.get(dom, (fwd_b + bwd_b) * B)
-        achieved = algo / (seg[dom] * 1e-3) / 1e9
-        line['roofline'] = {'bound': 'hbm', 'kernel': {'rasterize_forward': 'k_raster_tiles',
-                                                       'rasterize_backward': 'k_backward_items'}.get(dom, dom),
-                            'achieved': round(achieved, 1), 'peak': peak, 'peak_source': how, 'unit': 'GB/s',
-                            'frac': round(achieved / peak, 4), 'traffic': None,
-                            'algorithmic_bytes_per_launch': int(algo), 'launch_ms': round(seg[dom], 4),
+        dom = max(kern, key=lambda k: kern[k])
+        fwd_kernels = ('k_face_setup', 'k_fill_background', 'k_tile_prefix', 'k_raster_tiles')
+        # the dominant kernel is charged the algorithmic bytes of the pass it belongs to: it is the
+        # kernel that has to stream them; the other kernels of the pass only add time
+        algo = (fwd_b if dom in fwd_kernels else bwd_b) * B
+        achieved = algo / (kern[dom] * 1e-3) / 1e9
+        line['roofline'] = {'bound': 'hbm', 'kernel': dom, 'achieved': round(achieved, 1), 'peak': peak,
+                            'peak_source': how, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
+                            'traffic': NCU_TRAFFIC.get(dom), 'algorithmic_bytes_per_launch': int(algo),
+                            'launch_ms': round(kern[dom], 4),
+                            'kernels_ms': {k: round(v, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])},
                             'segments_ms': {k: round(v, 4) for k, v in seg.items()},
                             'whole_step_frac': round(value / world * sum(algorithmic_bytes()) / 1e9 / peak, 4)}
         if world == 1 and not args.no_cpu:

@@ -127,8 +127,13 @@ int sdn_rasterize_backward(const sdn_raster* r, const sdn_raster_grad* g, void* 
 int sdn_rasterize_backward_split(const sdn_raster* r, const sdn_raster_grad* g, double eps_alpha, double eps_rgb,
                                  void* stream);
 
-/* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long sdn_launch_count(void);
+
+/* Diagnostics: when enabled, every kernel launch is bracketed by CUDA events on the launching stream;
+ * sdn_timing_read() drains them as "kernel_name total_ms launches\n" lines (returns bytes written).  Off by default. */
+int sdn_timing_enable(int on);
+int sdn_timing_read(char* buf, int cap);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,65 @@
+"""World-size-2 test of the multi-GPU host logic on CPU (gloo): image sharding and the single flat-bucket gradient
+all-reduce that replaces DataParallel."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, '3d-sdn_b200'))
+    from sdn_b200.dist import FlatGradSync, shard_range
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    data = torch.randn(10, 6, generator=torch.Generator().manual_seed(1))
+    lo, hi = shard_range(10, rank, world)
+    sync = FlatGradSync(model)
+    # per-rank loss is the MEAN over its shard; equal shard sizes -> mean of means == global mean
+    model(data[lo:hi]).pow(2).mean().backward()
+    sync()
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    out[rank] = (lo, hi, flat.clone(), sync.numel)
+    dist.destroy_process_group()
+
+
+def test_shard_and_flat_allreduce_two_ranks():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert (out[0][0], out[0][1], out[1][0], out[1][1]) == (0, 5, 5, 10)
+    assert torch.equal(out[0][2], out[1][2])                         # identical gradients on every rank
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+    data = torch.randn(10, 6, generator=torch.Generator().manual_seed(1))
+    model(data).pow(2).mean().backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.allclose(out[0][2], ref, atol=1e-6)                 # == the single-process gradient
+    assert out[0][3] == ref.numel()
+
+
+def test_shard_range_covers_everything():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, '3d-sdn_b200'))
+    from sdn_b200.dist import shard_range
+    for n in (0, 1, 7, 256):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1

@@ -257,3 +257,88 @@ def test_fast_math_line_sweep_backward(dev, oracle, flags, ss, monkeypatch):
     lg.backward()
     assert rel_l2(r['faces'].grad, fo.grad) <= TOL
     assert float(fo.grad.abs().sum()) > 0
+
+
+def _synthetic_objs():
+    from sdn_b200 import workloads as wl
+    from derender3d.models import ShapenetObj
+    objs = []
+    for k in range(8):
+        v, f = wl.superellipsoid_mesh(10 + k, 8 + k, 0.4 + 0.1 * k, 0.5) if k % 2 else wl.cube_mesh()
+        objs.append(ShapenetObj(vertices=v * np.array([1.0, 0.6, 0.5], np.float32), faces=f))
+    return objs
+
+
+def _synthetic_blob(B, dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    c = 0.4 * (torch.rand(B, 2, generator=g) - 0.5)
+    d = 0.25 + 0.2 * torch.rand(B, 2, generator=g)
+    roi = torch.cat([c - d / 2, c + d / 2], dim=1)
+    theta = torch.randn(B, 2, generator=g)
+    blob = {
+        '_mroi_norms': torch.stack([roi[:, 2] + roi[:, 0], roi[:, 3] + roi[:, 1]], dim=1) / 2.0,
+        '_droi_norms': torch.stack([roi[:, 2] - roi[:, 0], roi[:, 3] - roi[:, 1]], dim=1),
+        '_focals': torch.full((B, 1), 725.0),
+        '_theta_deltas': theta / theta.norm(dim=1, keepdim=True),
+        '_translation2ds': 0.05 * torch.randn(B, 2, generator=g),
+        '_log_scales': 0.1 * torch.randn(B, 3, generator=g) + torch.tensor([1.3, 0.4, 0.5]),
+        '_log_depths': 0.2 * torch.randn(B, 1, generator=g) + 2.0,
+        '_class_probs': torch.softmax(3 * torch.randn(B, 8, generator=g), dim=1),
+        '_ffd_coeffs': 0.03 * torch.randn(B, 8, 192, generator=g),
+    }
+    return {k: v.to(dev) for k, v in blob.items()}, roi.to(dev)
+
+
+@pytest.mark.parametrize('training', [False, True])
+def test_derenderer3d_batched_render_matches_per_object_oracle(dev, oracle, training):
+    """Derenderer3d.render groups objects by mesh class and renders each group in one native call; the reference
+    renders them one by one (derender3d/models/__init__.py:161-224).  Same masks / normals / depth maps."""
+    from derender3d import TargetType
+    from derender3d.models import Derenderer3d
+    from derender3d.models.renderer import RenderType
+    S, B = 48, 7
+    model = Derenderer3d(TargetType.extend, image_size=256, render_size=S, objs=_synthetic_objs()).to(dev)
+    model.train(training)
+    model._force_no_sample = True
+    blob, _ = _synthetic_blob(B, dev)
+    blob['_ffd_coeffs'].requires_grad_(True)
+    out = model.render(blob)
+    assert out['_masks'].shape == (B, 1, S, S) and out['_normals'].shape == (B, 3, S, S)
+    assert float(out['_masks'].sum()) > 20
+    p = model.pose(blob)
+    classes = p['_class_samples'].tolist()
+    ang = (torch.atan(S / (2.0 * blob['_focals'].double().reshape(-1))) / np.pi * 180).cpu()
+    for k, sel, verts, z in model.object_vertices(blob, p, classes):
+        faces = model.objs[k].faces[None]
+        for j, i in enumerate(sel.tolist()):
+            v = verts[j:j + 1].detach().cpu()
+            so = oracle.derender_render(v, faces, S, float(ang[i]), RenderType.Silhouette)
+            assert torch.equal(out['_masks'][i:i + 1].cpu(), so), (k, i)
+            do = oracle.derender_render(v, faces, S, float(ang[i]), RenderType.Depth)
+            no = oracle.derender_render(v, faces, S, float(ang[i]), RenderType.Normal)
+            assert rel_l2(out['_depth_maps'][i:i + 1], do) <= TOL and rel_l2(out['_normals'][i:i + 1], no) <= TOL
+    (out['_masks'].sum() + out['_normals'].sum()).backward()
+    assert torch.isfinite(blob['_ffd_coeffs'].grad).all() and float(blob['_ffd_coeffs'].grad.abs().sum()) > 0
+
+
+def test_full_train_step_config3_shape(dev):
+    """BASELINE config 3 in miniature: encoder -> render -> MSE + REINFORCE -> Adam, on synthetic targets."""
+    from derender3d import TargetType
+    from derender3d.models import Derenderer3d
+    from derender3d.train_step import train_step
+    torch.manual_seed(0)
+    B, S = 6, 64
+    model = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=_synthetic_objs()).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3)
+    blob, roi = _synthetic_blob(B, dev, seed=2)
+    batch = {'images': torch.randn(B, 3, 224, 224, device=dev), 'roi_norms': roi,
+             'focals': torch.full((B, 1), 725.0, device=dev),
+             'targets': torch.full((B,), TargetType.full, device=dev, dtype=torch.long),
+             'thetas': torch.rand(B, 1, device=dev), 'translation2ds': torch.zeros(B, 2, device=dev),
+             'log_scales': torch.zeros(B, 3, device=dev), 'log_depths': torch.full((B, 1), 2.0, device=dev),
+             'masks': (torch.rand(B, 1, 40, 40, device=dev) > 0.5).float(), 'ignores': torch.zeros(B, 1, 40, 40, device=dev)}
+    before = model.derenderer._fc3.weight.detach().clone()
+    loss, losses, out = train_step(model, opt, batch, TargetType.full)
+    assert torch.isfinite(loss) and set(losses) >= {'mask_loss', 'class_reward', 'ffd_coeff_reg', 'scale_loss'}
+    assert out['_masks'].shape == (B, 1, S, S)
+    assert not torch.equal(before, model.derenderer._fc3.weight)
