@@ -26,7 +26,7 @@ import torch  # noqa: E402
 
 H, W, SS = 375, 1242, 2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {'k_line_sweep': 195101696}      # profiles/r1_prof_line_v4.txt
 NF_EFF = 2 * 1984
 C_OUT = 5
 
