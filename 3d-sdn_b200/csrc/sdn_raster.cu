@@ -28,6 +28,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "sdn_b200.h"
 
@@ -52,7 +53,13 @@ const char* g_pending_name = nullptr;
 cudaEvent_t g_pending_e0 = nullptr;
 cudaStream_t g_pending_stream = nullptr;
 
+// SDN_DEBUG_SYNC=1 in the environment: print every launch and synchronise after it (hang / fault localisation)
+const bool g_debug_sync = getenv("SDN_DEBUG_SYNC") != nullptr;
+const char* g_dbg_name = nullptr;
+cudaStream_t g_dbg_stream = nullptr;
+
 inline void timing_begin(const char* name, cudaStream_t st) {
+    if (g_debug_sync) { g_dbg_name = name; g_dbg_stream = st; fprintf(stderr, "[sdn] launch %s\n", name); fflush(stderr); }
     if (!g_timing.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_timing_mu);
     cudaEvent_t e0;
@@ -131,10 +138,10 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.gint = (float*)(p + off); off = align_up(off + BF * 24, 256);
     w.lines = B * (Hs + Ws);
     const size_t qm = BF * 24;
-    w.qmax = (int)(qm < 65536 ? 65536 : (qm > 6000000 ? 6000000 : qm));
+    w.qmax = (int)(qm < 65536 ? 65536 : (qm > 48000000 ? 48000000 : qm));
     w.scan_n = w.lines + 1 + (int)BF * 7 + 1 + (int)BF + 1;
     const size_t um = BF * 2 + 65536;
-    w.umax = (int)(um > 2000000 ? 2000000 : um);
+    w.umax = (int)(um > 8000000 ? 8000000 : um);
     w.vis_slot = (int*)(p + off); off = align_up(off + BF * 4, 256);
     w.scan_buf = (int*)(p + off); off = align_up(off + (size_t)w.scan_n * 4, 256);
     w.block_sums = (int*)(p + off); off = align_up(off + ((size_t)w.scan_n / 2048 + 2) * 4, 256);
@@ -593,6 +600,7 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
         const int* ids_g = ws.active_ids + (size_t)b * ws.Fp;
         const short4* bb_g = reinterpret_cast<const short4*>(ws.active_bbox) + (size_t)b * ws.Fp;
         const int nchunks = (count + BCH - 1) / BCH;
+        int qtotal = 0;                                 // faces queued so far (uniform across the CTA)
         // stage 0 of the pipeline
         if (tid == 0 && nchunks > 0) {
             const int n = min(BCH, count);
@@ -628,8 +636,10 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                 if (lane == 0 && m) wb = atomicAdd(&s_qn, __popc(m));
                 wb = __shfl_sync(FULL, wb, 0);
                 if (hit) s_queue[wb + __popc(m & ((1u << lane) - 1))] = id;
-                __syncthreads();
-                const int qn = s_qn;
+                // The flush decision must be identical in every thread (it guards barriers): use the barrier's own
+                // CTA-wide count, never a racy read of s_qn (faster warps may already be appending the next batch).
+                qtotal += __syncthreads_count(hit);
+                const int qn = qtotal;
                 const bool last = (c == nchunks - 1) && (base + NT >= nin);
                 if (qn > QCAP - NT || last) {
                     // ---- face-parallel coverage: one warp per queued face, lanes over an 8x4 sample footprint
@@ -662,6 +672,7 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                     }
                     __syncthreads();
                     if (tid == 0) s_qn = 0;
+                    qtotal = 0;
                     __syncthreads();
                 }
             }
@@ -1938,6 +1949,12 @@ __global__ void k_faces_backward_vertex(const float* __restrict__ vertices, int 
 inline int check_launch() {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     timing_end();
+    if (g_debug_sync && g_dbg_name) {
+        const cudaError_t e = cudaStreamSynchronize(g_dbg_stream);
+        fprintf(stderr, "[sdn] done   %s -> %s\n", g_dbg_name, cudaGetErrorString(e));
+        fflush(stderr);
+        g_dbg_name = nullptr;
+    }
     return (int)cudaPeekAtLastError();
 }
 
@@ -2090,6 +2107,23 @@ long long sdn_launch_count(void) { return g_launches.load(); }
 int sdn_timing_enable(int on) {
     g_timing.store(on ? 1 : 0);
     return 0;
+}
+
+// Diagnostics for hangs: names of timed launches that have started but not finished (non-blocking event queries).
+int sdn_debug_pending(char* buf, int cap) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    int off = 0, idx = 0;
+    for (auto& t : g_timed) {
+        const bool started = cudaEventQuery(t.e0) == cudaSuccess, done = cudaEventQuery(t.e1) == cudaSuccess;
+        if (!done) {
+            const int w = snprintf(buf + off, (size_t)(cap - off > 0 ? cap - off : 0), "#%d %s %s\n", idx, t.name,
+                                   started ? "RUNNING" : "queued");
+            if (w < 0 || off + w >= cap) break;
+            off += w;
+        }
+        idx++;
+    }
+    return off;
 }
 
 // Writes "kernel_name total_ms launches\n" lines (aggregated since the last read) into buf; returns bytes written.

@@ -134,6 +134,7 @@ long long sdn_launch_count(void);
  * sdn_timing_read() drains them as "kernel_name total_ms launches\n" lines (returns bytes written).  Off by default. */
 int sdn_timing_enable(int on);
 int sdn_timing_read(char* buf, int cap);
+int sdn_debug_pending(char* buf, int cap);   /* timed launches not finished yet: "#i name RUNNING|queued\n" */
 
 #ifdef __cplusplus
 }

@@ -342,3 +342,19 @@ def test_full_train_step_config3_shape(dev):
     assert torch.isfinite(loss) and set(losses) >= {'mask_loss', 'class_reward', 'ffd_coeff_reg', 'scale_loss'}
     assert out['_masks'].shape == (B, 1, S, S)
     assert not torch.equal(before, model.derenderer._fc3.weight)
+
+
+@pytest.mark.timeout(300)
+def test_many_faces_per_tile_queue_flush_is_stable(dev, oracle):
+    """Thousands of faces overlapping one 64x32 tile force repeated queue flushes inside k_raster_tiles; the flush
+    decision guards barriers and must be CTA-uniform (regression test for a divergent-barrier hang)."""
+    import sdn_b200
+    rng = np.random.RandomState(5)
+    B, F, H, W = 2, 6000, 48, 96
+    faces = random_faces(rng, B, F, spread=0.5, size=0.35)
+    st = oracle.raster_forward(faces, None, H, W, 0.1, 100, 1e-4, None, False, True, True)
+    cfg = sdn_b200.RasterConfig((H, W), False, return_alpha=True, return_depth=True)
+    f = torch.tensor(faces, device=dev)
+    for _ in range(8):
+        sdn_b200.RasterizeFunction.apply(f, None, cfg)
+        assert np.array_equal(cfg.last_face_index.cpu().numpy(), st.face_index_map)
