@@ -373,11 +373,12 @@ void orc_backward_pixel(const float *faces, const int32_t *face_index_map, const
 void orc_backward_textures(const int32_t *face_index_map, const float *sampling_weight_map,
                            const int32_t *sampling_index_map, const float *grad_rgb_map,
                            int B, int F, int H, int W, int ts, float *grad_textures) {
-    const long npix = (long)B * H * W;
-    for (long i = 0; i < npix; i++) {
+    /* images are independent (each owns its slice of grad_textures): parallel over bn, serial inside */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int bn = 0; bn < B; bn++)
+    for (long i = (long)bn * H * W; i < (long)(bn + 1) * H * W; i++) {
         const int face_index = face_index_map[i];
         if (face_index < 0) continue;
-        const int bn = (int)(i / ((long)H * W));
         float *gt = grad_textures + ((size_t)bn * F + face_index) * ts * ts * ts * 3;
         for (int pn = 0; pn < 8; pn++) {
             const float w = sampling_weight_map[i * 8 + pn];
@@ -392,11 +393,12 @@ void orc_backward_textures(const int32_t *face_index_map, const float *sampling_
 void orc_backward_depth(const float *faces, const float *depth_map, const int32_t *face_index_map,
                         const float *face_inv_map, const float *weight_map, const float *grad_depth_map,
                         int B, int F, int H, int W, float *grad_faces) {
-    const long npix = (long)B * H * W;
-    for (long i = 0; i < npix; i++) {
+    /* images are independent (each owns its slice of grad_faces): parallel over bn, serial inside */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int bn = 0; bn < B; bn++)
+    for (long i = (long)bn * H * W; i < (long)(bn + 1) * H * W; i++) {
         const int fn = face_index_map[i];
         if (fn < 0) continue;
-        const int bn = (int)(i / ((long)H * W));
         const float *face = faces + ((size_t)bn * F + fn) * 9;
         const float depth = depth_map[i];
         const float depth2 = depth * depth;
@@ -413,6 +415,100 @@ void orc_backward_depth(const float *faces, const float *depth_map, const int32_
         for (int k = 0; k < 3; k++) for (int l = 0; l < 2; l++) {
             const int is = (l == 0) ? W : H;
             gf[3 * k + l] += -gd * tmp[l] * weight[k] * depth2 * (float)is / 2.0f;
+        }
+    }
+}
+
+/* K1u  rasterize.py:102-236: the per-face scanline kernel 3D-SDN actually runs (scripts/env.sh:11 sets
+ * NEURAL_RENDERER_UNSAFE=1).  On the GPU it is racy (spin lock per pixel); executed face by face in index order it
+ * is deterministic and keeps the first face among equal depths (strict '<'), like the safe path -- but it decides
+ * "inside" with ceil/floor scanline bounds instead of the three half-plane tests, so a thin set of edge samples
+ * differs.  Used as the comparator / CPU timing arm, never as the parity definition.  Parallel over images. */
+void orc_visibility_scanline(const float *faces, int B, int F, int H, int W, double near, double far,
+                             int return_depth, int32_t *face_index_map, float *weight_map, float *depth_map,
+                             float *face_inv_map) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int bn = 0; bn < B; bn++) {
+        for (int fn = 0; fn < F; fn++) {
+            const float *face = faces + ((size_t)bn * F + fn) * 9;
+            if (is_backside(face)) continue;
+            int pi[3];
+            if (face[0] < face[3]) {
+                pi[0] = (face[6] < face[0]) ? 2 : 0;
+                pi[2] = (face[3] < face[6]) ? 2 : 1;
+            } else {
+                pi[0] = (face[6] < face[3]) ? 2 : 1;
+                pi[2] = (face[0] < face[6]) ? 2 : 0;
+            }
+            pi[1] = 0;
+            for (int k = 0; k < 3; k++) if (pi[0] != k && pi[2] != k) pi[1] = k;
+            float p[3][3];
+            for (int n = 0; n < 3; n++) {
+                p[n][0] = to_pixel(face[3 * pi[n] + 0], W);
+                p[n][1] = to_pixel(face[3 * pi[n] + 1], H);
+                p[n][2] = face[3 * pi[n] + 2];
+            }
+            if (p[0][0] == p[2][0]) continue;
+            float fi[9] = {
+                p[1][1] - p[2][1], p[2][0] - p[1][0], p[1][0] * p[2][1] - p[2][0] * p[1][1],
+                p[2][1] - p[0][1], p[0][0] - p[2][0], p[2][0] * p[0][1] - p[0][0] * p[2][1],
+                p[0][1] - p[1][1], p[1][0] - p[0][0], p[0][0] * p[1][1] - p[1][0] * p[0][1]};
+            const float den = (p[2][0] * (p[0][1] - p[1][1]) + p[0][0] * (p[1][1] - p[2][1])) +
+                              p[1][0] * (p[2][1] - p[0][1]);
+            for (int k = 0; k < 9; k++) fi[k] /= den;
+            const int xi_min = f2i(dmax((double)ceilf(p[0][0]), 0.));
+            const int xi_max = f2i(dmin((double)p[2][0], W - 1.));
+            for (int xi = xi_min; xi <= xi_max; xi++) {
+                const float xif = (float)xi;
+                float yi1, yi2;
+                if (xif <= p[1][0]) {
+                    if (p[1][0] - p[0][0] != 0) {
+                        yi1 = (p[1][1] - p[0][1]) / (p[1][0] - p[0][0]);
+                        yi1 = yi1 * (xif - p[0][0]);
+                        yi1 = yi1 + p[0][1];
+                    } else yi1 = p[1][1];
+                } else {
+                    if (p[2][0] - p[1][0] != 0) {
+                        yi1 = (p[2][1] - p[1][1]) / (p[2][0] - p[1][0]);
+                        yi1 = yi1 * (xif - p[1][0]);
+                        yi1 = yi1 + p[1][1];
+                    } else yi1 = p[1][1];
+                }
+                yi2 = (p[2][1] - p[0][1]) / (p[2][0] - p[0][0]);
+                yi2 = yi2 * (xif - p[0][0]);
+                yi2 = yi2 + p[0][1];
+                const int yi_min = f2i(dmax(0., (double)ceilf(fminc(yi1, yi2))));
+                const int yi_max = f2i(dmin((double)fmaxc(yi1, yi2), H - 1.));
+                for (int yi = yi_min; yi <= yi_max; yi++) {
+                    const long index = (long)bn * H * W + (long)yi * W + xi;
+                    const float yif = (float)yi;
+                    float w[3], w_sum = 0;
+                    for (int k = 0; k < 3; k++) {
+                        float t = fi[3 * k + 0] * xif;
+                        float u = fi[3 * k + 1] * yif;
+                        t = t + u;
+                        w[k] = t + fi[3 * k + 2];
+                    }
+                    for (int k = 0; k < 3; k++) {
+                        w[k] = (float)dmin(dmax((double)w[k], 0.), 1.);
+                        w_sum += w[k];
+                    }
+                    for (int k = 0; k < 3; k++) w[k] /= w_sum;
+                    float s = w[0] / p[0][2];
+                    s = s + w[1] / p[1][2];
+                    s = s + w[2] / p[2][2];
+                    const float zp = (float)(1. / (double)s);
+                    if ((double)zp <= near || far <= (double)zp) continue;
+                    if (zp < depth_map[index]) {
+                        depth_map[index] = zp;
+                        face_index_map[index] = fn;
+                        for (int k = 0; k < 3; k++) weight_map[3 * index + pi[k]] = w[k];
+                        if (return_depth)
+                            for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++)
+                                face_inv_map[9 * index + 3 * pi[l] + k] = fi[3 * l + k];
+                    }
+                }
+            }
         }
     }
 }

@@ -101,9 +101,12 @@ class RasterState(object):
     pass
 
 
+SCANLINE = False        # bench.py's reference arm: use the per-face scanline kernel 3D-SDN actually runs (K1u)
+
+
 def raster_forward(faces, textures, H, W, near=DEFAULT_NEAR, far=DEFAULT_FAR, eps=DEFAULT_EPS,
                    background_color=(0, 0, 0), return_rgb=False, return_alpha=False, return_depth=False,
-                   batch_bug=False, use_ref=False):
+                   batch_bug=False, use_ref=False, scanline=None):
     """faces [B,F,3,3] f32, textures [B,F,ts,ts,ts,3] f32 or None; raster is H rows x W cols.
     use_ref=True runs the reference's own kernel bodies (square rasters only)."""
     if not any((return_rgb, return_alpha, return_depth)):
@@ -143,6 +146,17 @@ def raster_forward(faces, textures, H, W, near=DEFAULT_NEAR, far=DEFAULT_FAR, ep
             r.ref_k2_texture_sampling(ctypes.c_int(B * H * W), _fp(faces), _fp(textures), _ip(st.face_index_map),
                                       _fp(st.weight_map), _fp(st.depth_map), _fp(st.rgb_map),
                                       _ip(st.sampling_index_map), _fp(st.sampling_weight_map), *cfg)
+    elif (SCANLINE if scanline is None else scanline):
+        L = lib()      # rasterize.py:102-236, the NEURAL_RENDERER_UNSAFE=1 kernel (comparator / timing only)
+        L.orc_visibility_scanline(_fp(faces), ctypes.c_int(B), ctypes.c_int(F), ctypes.c_int(H), ctypes.c_int(W),
+                                  ctypes.c_double(st.near), ctypes.c_double(st.far), ctypes.c_int(int(return_depth)),
+                                  _ip(st.face_index_map), _fp(st.weight_map), _fp(st.depth_map), _fp(st.face_inv_map))
+        if return_rgb:
+            L.orc_texture_sampling(_fp(faces), _fp(textures), _ip(st.face_index_map), _fp(st.weight_map),
+                                   _fp(st.depth_map), ctypes.c_int(B), ctypes.c_int(F), ctypes.c_int(H),
+                                   ctypes.c_int(W), ctypes.c_int(ts), ctypes.c_double(st.eps),
+                                   ctypes.c_int(int(batch_bug)), _fp(st.rgb_map), _ip(st.sampling_index_map),
+                                   _fp(st.sampling_weight_map))
     else:
         L = lib()
         L.orc_face_inv(_fp(faces), ctypes.c_int(B * F), ctypes.c_int(H), ctypes.c_int(W), _fp(faces_inv))

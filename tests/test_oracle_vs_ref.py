@@ -78,3 +78,16 @@ def test_unsafe_kernel_differs_only_on_edges(oracle):
     st = oracle.raster_forward(faces, None, S, S, return_alpha=True)
     fi, _, _ = oracle.raster_forward_unsafe_ref(faces, S)
     assert (fi != st.face_index_map).mean() < 0.05
+
+
+def test_scanline_port_matches_reference_unsafe_kernel(oracle):
+    """orc_visibility_scanline == the reference's K1u body (rasterize.py:102-236) run face by face, bit for bit."""
+    if oracle.ref_lib() is None:
+        pytest.skip('oracle/_ref not built')
+    rng = np.random.RandomState(11)
+    for S, F in ((48, 60), (64, 200)):
+        faces = random_faces(rng, 2, F, size=0.4)
+        fi, w, d = oracle.raster_forward_unsafe_ref(faces, S, return_depth=True)
+        st = oracle.raster_forward(faces, None, S, S, return_alpha=True, return_depth=True, scanline=True)
+        assert np.array_equal(st.face_index_map, fi) and (fi >= 0).mean() > 0.2
+        assert np.array_equal(st.depth_map, d) and np.array_equal(st.weight_map, w)
