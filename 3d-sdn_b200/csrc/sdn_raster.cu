@@ -593,15 +593,11 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
         const int sx1 = min(sx0 + TW, P.Ws) - 1, sy1 = min(sy0 + TH, P.Hs) - 1;
         const int count = ws.active_count[b];
 
-        for (int k = tid; k < TH * TW; k += NT) s_key[k] = ~0ull;
-        if (tid < TW) s_xp[tid] = xp_of(sx0 + tid, P.Ws);
-        if (tid < TH) s_yp[tid] = xp_of(sy0 + tid, P.Hs);
-        if (tid == 0) s_qn = 0;
         const int* ids_g = ws.active_ids + (size_t)b * ws.Fp;
         const short4* bb_g = reinterpret_cast<const short4*>(ws.active_bbox) + (size_t)b * ws.Fp;
         const int nchunks = (count + BCH - 1) / BCH;
         int qtotal = 0;                                 // faces queued so far (uniform across the CTA)
-        // stage 0 of the pipeline
+        // stage 0 of the pipeline goes out first; the shared-memory initialisation below hides its latency
         if (tid == 0 && nchunks > 0) {
             const int n = min(BCH, count);
             const uint32_t by_i = ((n + 3) / 4) * 16, by_b = ((n + 1) / 2) * 16;
@@ -609,6 +605,10 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
             bulk_g2s(&s_ids[0][0], ids_g, by_i, &s_bar[0]);
             bulk_g2s(&s_bb[0][0], bb_g, by_b, &s_bar[0]);
         }
+        for (int k = tid; k < TH * TW; k += NT) s_key[k] = ~0ull;
+        if (tid < TW) s_xp[tid] = xp_of(sx0 + tid, P.Ws);
+        if (tid < TH) s_yp[tid] = xp_of(sy0 + tid, P.Hs);
+        if (tid == 0) s_qn = 0;
         __syncthreads();
         for (int c = 0; c < nchunks; c++) {
             const int st = c & 1;
@@ -1300,7 +1300,7 @@ __device__ __forceinline__ void eval_owned_fast(const float* f, const float* inv
 // triangle; here each owned sample asks, for the six (edge, axis) items, whether the step through its own row / column
 // would have visited it (identical float tests), so the cost is proportional to the owned area.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
+__device__ __forceinline__ void bwd_face_role(const BwdParams& P, const Workspace& ws) {
     const int lane = threadIdx.x & 31;
     if (bwd_overflow(ws)) return;                    // the direct kernel does all of it
     const int* unit_n = unit_region(ws);
@@ -1506,6 +1506,8 @@ __global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) {
     }
 }
 
+__global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) { bwd_face_role(P, ws); }
+
 // sums the unit partials of every visible face, in unit order (deterministic)
 __global__ void __launch_bounds__(256) k_face_sums(Workspace ws) {
     if (bwd_overflow(ws)) return;
@@ -1604,8 +1606,8 @@ constexpr int LM_ALPHA = 0;     // silhouette only: the positive part does not d
 constexpr int LM_SINGLE = 1;    // one reference pass (rgb, or alpha+rgb summed before the > 0 test)
 constexpr int LM_SPLIT = 2;     // alpha pass (eps_a) + rgb pass (eps_r), separate > 0 tests
 constexpr int LW = 8;           // warps (= adjacent lines) per CTA
-constexpr int LP = 8;           // pixels per lane per pass (a pass = 256 pixels of the line, held in registers)
-constexpr int LQ = 32;          // queries staged per warp at a time; lane k owns query k's final reduction
+// LP = pixels per lane per pass (a pass = 32*LP pixels of the line, held in registers);
+// LQ = queries staged per warp at a time; MINB = CTAs per SM asked of ptxas
 
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 relu2(float2 a) { return make_float2(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f)); }
@@ -1617,16 +1619,23 @@ __device__ __forceinline__ float2 rcp2(float2 a) { return make_float2(rcp_approx
 // the colour term, 4 for the distances, 2 reciprocals, and fused accumulates.  Partial sums stay per lane in shared
 // memory (conflict-free) and are reduced once per query chunk -- no shuffles or atomics in the hot loop, and every
 // query's result is written exactly once, in a fixed order (deterministic).
-template <int MODE>
-__global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace ws) {
+// a query decoded once per chunk: signed pads and negated colour ready for the packed arithmetic
+struct __align__(16) QueryX {
+    int lo, hi, flags;
+    float xc, k0, k1, nc0, nc1, nc2, e0a, e0r, e1a, e1r;
+    float pad_[3];
+};
+
+template <int MODE, int LP, int LQ>
+__device__ __forceinline__ void line_role(const BwdParams& P, const Workspace& ws, const int block_index) {
     extern __shared__ __align__(16) unsigned char s_line_dyn[];
     float2 (*s_acc)[LQ][33] = reinterpret_cast<float2 (*)[LQ][33]>(s_line_dyn);
-    __shared__ Query s_q[LW][LQ];
+    __shared__ QueryX s_q[LW][LQ];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_img = P.Hs + P.Ws;
     const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
     const int bundles = bundles_rows + bundles_cols;
-    const int b = blockIdx.x / bundles, bi = blockIdx.x % bundles;
+    const int b = block_index / bundles, bi = block_index % bundles;
     int axis, d0;
     if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
     else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
@@ -1652,10 +1661,15 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
         const int qn = min(LQ, qend - qchunk);
         // stage the chunk's queries (lane k <-> query k); union of their ranges tells which passes are needed
         int ulo = 0x7fffffff, uhi = -1;
-        if (lane < qn) {
-            const Query q = ws.queries[ws.line_items[qchunk + lane]];
-            s_q[warp][lane] = q;
-            ulo = q.lo; uhi = q.hi_flags & 0xffff;
+        for (int k = lane; k < qn; k += 32) {
+            const Query q = ws.queries[ws.line_items[qchunk + k]];
+            QueryX x;
+            x.lo = q.lo; x.hi = q.hi_flags & 0xffff; x.flags = q.hi_flags;
+            x.xc = q.xc; x.k0 = q.k0; x.k1 = q.k1; x.nc0 = -q.c0; x.nc1 = -q.c1; x.nc2 = -q.c2;
+            x.e0a = (q.hi_flags & QF_POS0) ? ea : -ea; x.e0r = (q.hi_flags & QF_POS0) ? er : -er;
+            x.e1a = (q.hi_flags & QF_POS1) ? ea : -ea; x.e1r = (q.hi_flags & QF_POS1) ? er : -er;
+            s_q[warp][k] = x;
+            ulo = min(ulo, x.lo); uhi = max(uhi, x.hi);
         }
 #pragma unroll 4
         for (int k = 0; k < LQ; k++) s_acc[warp][k][lane] = make_float2(0.0f, 0.0f);
@@ -1706,11 +1720,11 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
             const int pass_hi = pbase + 32 * LP - 1;
             // ---- queries
             for (int k = 0; k < qn; k++) {
-                const Query q = s_q[warp][k];                               // broadcast read
-                const int lo = q.lo, hi = q.hi_flags & 0xffff;
+                const int lo = s_q[warp][k].lo, hi = s_q[warp][k].hi;       // broadcast reads
                 if (hi < pbase || lo > pass_hi) continue;
+                const QueryX q = s_q[warp][k];
                 const bool full = (lo <= pbase) && (hi >= pass_hi);        // every pixel of the pass is in range
-                const float2 e0a = f2((q.hi_flags & QF_POS0) ? ea : -ea), e1a = f2((q.hi_flags & QF_POS1) ? ea : -ea);
+                const float2 e0a = f2(q.e0a), e1a = f2(q.e1a);
                 const float2 k0 = f2(q.k0), k1 = f2(q.k1);
                 float2 t = make_float2(xbase - q.xc, (xbase + 32.0f) - q.xc);
                 float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
@@ -1731,8 +1745,8 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
                         t = __fadd2_rn(t, f2(64.0f));
                     }
                 } else {
-                    const float2 nc0 = f2(-q.c0), nc1 = f2(-q.c1), nc2 = f2(-q.c2);
-                    const float2 e0r = f2((q.hi_flags & QF_POS0) ? er : -er), e1r = f2((q.hi_flags & QF_POS1) ? er : -er);
+                    const float2 nc0 = f2(q.nc0), nc1 = f2(q.nc1), nc2 = f2(q.nc2);
+                    const float2 e0r = f2(q.e0r), e1r = f2(q.e1r);
 #pragma unroll
                     for (int m = 0; m < LP2; m++) {
                         float2 dr = __ffma2_rn(nc0, g0v[m], D[m]);
@@ -1768,18 +1782,32 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep(BwdParams P, Workspace w
             }
         }
         __syncwarp();
-        if (lane < qn) {        // lane k reduces query k over the 32 per-lane partials, in lane order
+        for (int k = lane; k < qn; k += 32) {   // one lane reduces query k over the 32 per-lane partials, in lane order
             float r0 = 0.0f, r1 = 0.0f;
 #pragma unroll 8
-            for (int l = 0; l < 32; l++) { const float2 v = s_acc[warp][lane][l]; r0 += v.x; r1 += v.y; }
-            const int hf = s_q[warp][lane].hi_flags;
+            for (int l = 0; l < 32; l++) { const float2 v = s_acc[warp][k][l]; r0 += v.x; r1 += v.y; }
+            const int hf = s_q[warp][k].flags;
             // g -= diff / dist   (rasterize.py:648,653)
-            ws.qres[ws.line_items[qchunk + lane]] = make_float2((hf & QF_USE0) ? -r0 : 0.0f, (hf & QF_USE1) ? -r1 : 0.0f);
+            ws.qres[ws.line_items[qchunk + k]] = make_float2((hf & QF_USE0) ? -r0 : 0.0f, (hf & QF_USE1) ? -r1 : 0.0f);
         }
         __syncwarp();
     }
 }
 
+
+template <int MODE, int LP, int LQ, int MINB>
+__global__ void __launch_bounds__(LW * 32, MINB) k_line_sweep(BwdParams P, Workspace ws) {
+    line_role<MODE, LP, LQ>(P, ws, blockIdx.x);
+}
+
+// The two heavy backward stages are independent of each other (the line sweep needs the queries, the face stage the
+// unit table; both exist after k_bwd_steps<EMIT>), one is issue-bound and the other latency-bound: run them as ONE
+// launch whose leading CTAs take the face role and the rest the line role, so they overlap on the SMs.
+template <int MODE>
+__global__ void __launch_bounds__(LW * 32, 2) k_bwd_main(BwdParams P, Workspace ws, int face_ctas) {
+    if ((int)blockIdx.x < face_ctas) { bwd_face_role(P, ws); return; }
+    line_role<MODE, 8, 32>(P, ws, (int)blockIdx.x - face_ctas);
+}
 
 // adds the deferred out-sweep results of every (edge, axis) item onto its in-sweep partial, in step order
 __global__ void __launch_bounds__(256) k_item_sums(Workspace ws) {
@@ -2050,31 +2078,53 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         timing_begin("k_bwd_steps", st);
         k_bwd_steps<true><<<fgrid, 256, 0, st>>>(P, ws);
         if ((rc = check_launch())) return rc;
-        timing_begin("k_bwd_face", st);
-        k_bwd_face<<<sm_count() * 8, 128, 0, st>>>(P, ws);
-        if ((rc = check_launch())) return rc;
-        timing_begin("k_face_sums", st);
-        k_face_sums<<<(unsigned)((BF * 18 + 255) / 256), 256, 0, st>>>(ws);
-        if ((rc = check_launch())) return rc;
+        static const bool fuse = getenv("SDN_FUSE_BWD") != nullptr;     // measured: no gain (both stages are register-bound)
+        if (!fuse) {
+            timing_begin("k_bwd_face", st);
+            k_bwd_face<<<sm_count() * 8, 128, 0, st>>>(P, ws);
+            if ((rc = check_launch())) return rc;
+        }
         timing_begin("k_backward_items", st);
         k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 1);      // no-op unless the queries overflowed
         if ((rc = check_launch())) return rc;
         const int bundles = (P.Hs + LW - 1) / LW + (P.Ws + LW - 1) / LW;
         const unsigned lgrid = (unsigned)(r->B * bundles);
-        const size_t lsmem = sizeof(float2) * LW * LQ * 33;
-        if (P.use_alpha && !P.use_rgb) {
-            cudaFuncSetAttribute(k_line_sweep<LM_ALPHA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-            timing_begin("k_line_sweep", st);
-            k_line_sweep<LM_ALPHA><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
-        } else if (P.use_alpha && P.use_rgb && P.split) {
-            cudaFuncSetAttribute(k_line_sweep<LM_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-            timing_begin("k_line_sweep", st);
-            k_line_sweep<LM_SPLIT><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
+        // kernel variant (registers per pass / staged queries / CTAs per SM); SDN_LINE_VARIANT overrides for tuning
+        static const int variant = getenv("SDN_LINE_VARIANT") ? atoi(getenv("SDN_LINE_VARIANT")) : 0;
+        const int lmode = (P.use_alpha && !P.use_rgb) ? LM_ALPHA : ((P.use_alpha && P.use_rgb && P.split) ? LM_SPLIT : LM_SINGLE);
+#define SDN_LAUNCH_LINE(MODE, LP_, LQ_, MINB_)                                                                          \
+    do {                                                                                                                \
+        const size_t lsmem = sizeof(float2) * LW * LQ_ * 33;                                                             \
+        cudaFuncSetAttribute(k_line_sweep<MODE, LP_, LQ_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem); \
+        timing_begin("k_line_sweep", st);                                                                                \
+        k_line_sweep<MODE, LP_, LQ_, MINB_><<<lgrid, LW * 32, lsmem, st>>>(P, ws);                                       \
+    } while (0)
+#define SDN_LINE_VARIANTS(MODE)                                                                                          \
+    do {                                                                                                                \
+        if (variant == 1) SDN_LAUNCH_LINE(MODE, 16, 32, 1);                                                              \
+        else if (variant == 2) SDN_LAUNCH_LINE(MODE, 12, 32, 1);                                                         \
+        else SDN_LAUNCH_LINE(MODE, 8, 32, 2);                                                                            \
+    } while (0)
+        if (fuse) {
+            const int face_ctas = sm_count() * 4;
+            const size_t lsmem = sizeof(float2) * LW * 32 * 33;
+#define SDN_LAUNCH_MAIN(MODE)                                                                                           \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(k_bwd_main<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);                \
+        timing_begin("k_bwd_main", st);                                                                                 \
+        k_bwd_main<MODE><<<lgrid + face_ctas, LW * 32, lsmem, st>>>(P, ws, face_ctas);                                  \
+    } while (0)
+            if (lmode == LM_ALPHA) SDN_LAUNCH_MAIN(LM_ALPHA);
+            else if (lmode == LM_SPLIT) SDN_LAUNCH_MAIN(LM_SPLIT);
+            else SDN_LAUNCH_MAIN(LM_SINGLE);
         } else {
-            cudaFuncSetAttribute(k_line_sweep<LM_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-            timing_begin("k_line_sweep", st);
-            k_line_sweep<LM_SINGLE><<<lgrid, LW * 32, lsmem, st>>>(P, ws);
+            if (lmode == LM_ALPHA) SDN_LINE_VARIANTS(LM_ALPHA);
+            else if (lmode == LM_SPLIT) SDN_LINE_VARIANTS(LM_SPLIT);
+            else SDN_LINE_VARIANTS(LM_SINGLE);
         }
+        if ((rc = check_launch())) return rc;
+        timing_begin("k_face_sums", st);
+        k_face_sums<<<(unsigned)((BF * 18 + 255) / 256), 256, 0, st>>>(ws);
     } else if (P.fast_math) {
         timing_begin("k_backward_items", st);
         k_backward_items<true><<<grid, BWD_WARPS * 32, 0, st>>>(P, ws, 0);
@@ -2234,7 +2284,7 @@ int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
     timing_begin("k_tile_prefix", st);
     k_tile_prefix<<<1, 256, 0, st>>>(r->B, ws);
     if ((rc = check_launch())) return rc;
-    const int grid = min(P.num_tiles, sm_count() * 4);
+    const int grid = min(P.num_tiles, sm_count() * 5);
     if (r->ss == 2) { timing_begin("k_raster_tiles", st); k_raster_tiles<2><<<grid, NT, 0, st>>>(P, ws); }
     else { timing_begin("k_raster_tiles", st); k_raster_tiles<1><<<grid, NT, 0, st>>>(P, ws); }
     return check_launch();

@@ -358,3 +358,30 @@ def test_many_faces_per_tile_queue_flush_is_stable(dev, oracle):
     for _ in range(8):
         sdn_b200.RasterizeFunction.apply(f, None, cfg)
         assert np.array_equal(cfg.last_face_index.cpu().numpy(), st.face_index_map)
+
+
+def test_analysis_by_synthesis_reduces_silhouette_error(dev):
+    """main.py:405-459 in miniature: Adam on pose / FFD latents through render fwd+bwd drives the silhouettes towards
+    targets rendered from perturbed latents."""
+    import sdn_b200
+    from derender3d import TargetType
+    from derender3d.models import Derenderer3d
+    from derender3d.optimise import refine
+    S, B = 64, 4
+    model = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=_synthetic_objs()).to(dev)
+    model.train()
+    model._force_no_sample = True
+    blob, _ = _synthetic_blob(B, dev, seed=3)
+    with torch.no_grad():
+        target = model.render(blob)['_masks'].clone()
+    start = dict(blob)
+    start['_translation2ds'] = blob['_translation2ds'] + 0.08
+    start['_log_scales'] = blob['_log_scales'] + 0.15
+    old = sdn_b200.DEFAULT_FAST_MATH
+    sdn_b200.DEFAULT_FAST_MATH = True
+    try:
+        refined, hist = refine(model, start, target, num_opts=25)
+    finally:
+        sdn_b200.DEFAULT_FAST_MATH = old
+    assert float(hist[-1]) < 0.6 * float(hist[0]), hist.tolist()
+    assert refined['_masks'].shape == target.shape
