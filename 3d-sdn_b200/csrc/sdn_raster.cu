@@ -94,6 +94,11 @@ struct Workspace {
     int* active_ids;        // [B*Fp]  per image: ids of the faces that can draw (front-facing, on screen)
     short* active_bbox;     // [B*Fp,4] their bboxes, same order (streamed with 1-D bulk copies)
     int* tile_prefix;       // [B+1]   tiles inside each image's face bbox, exclusive prefix
+    int* tile_off;          // [tiles+1] faces binned to every tile: counts, then (scan) offsets into bin_ids
+    int* tile_cursor;       // [tiles]
+    int* bin_ids;           // [bin_cap] face ids grouped by tile
+    int* bin_sums;          // scan scratch
+    int num_tiles, bin_cap;
     int Fp;                 // F rounded up so that per-image list starts stay 16-byte aligned
     int* vis_ids;           // [B*F]  global face ids b*F+fn of the visible faces
     float* gpart;           // [B*F,12]  K6 partials [edge][axis][2]
@@ -126,6 +131,9 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.counters = (int*)(p + off); off += sizeof(int) * 4;       // contiguous with vis_count (one memset)
     w.visible = (unsigned char*)(p + off); off += BF;
     off = align_up(off, 256);
+    w.num_tiles = B * ((Ws + TW - 1) / TW) * ((Hs + TH - 1) / TH);
+    w.tile_off = (int*)(p + off); off = align_up(off + (size_t)(w.num_tiles + 1) * 4, 256);
+    w.tile_cursor = (int*)(p + off); off = align_up(off + (size_t)w.num_tiles * 4, 256);
     w.zero_bytes = off;
     w.face_inv = (float*)(p + off); off = align_up(off + BF * 36, 256);
     w.face_bbox = (short*)(p + off); off = align_up(off + BF * 8, 256);
@@ -133,6 +141,10 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.active_ids = (int*)(p + off); off = align_up(off + (size_t)B * w.Fp * 4, 256);
     w.active_bbox = (short*)(p + off); off = align_up(off + (size_t)B * w.Fp * 8, 256);
     w.tile_prefix = (int*)(p + off); off = align_up(off + (size_t)(B + 1) * 4, 256);
+    const size_t bc = BF * 3 + 262144;
+    w.bin_cap = (int)(bc > 64000000 ? 64000000 : bc);
+    w.bin_ids = (int*)(p + off); off = align_up(off + (size_t)w.bin_cap * 4, 256);
+    w.bin_sums = (int*)(p + off); off = align_up(off + ((size_t)w.num_tiles / 2048 + 2) * 4, 256);
     w.vis_ids = (int*)(p + off); off = align_up(off + BF * 4, 256);
     w.gpart = (float*)(p + off); off = align_up(off + BF * 48, 256);
     w.gint = (float*)(p + off); off = align_up(off + BF * 24, 256);
@@ -345,15 +357,21 @@ __global__ void k_face_setup(const float* __restrict__ faces, int B, int F, int 
                 const float mya = fmaxf(fmaxf(fabsf(f[1]), fabsf(f[4])), fabsf(f[7]));
                 if (mxa > 64.0f || mya > 64.0f) {       // rounding error may exceed a sample: no bbox culling
                     x0 = 0; y0 = 0; x1 = Ws - 1; y1 = Hs - 1;
-                } else {                                // conservative by one sample on each side
+                } else {
+                    // Samples sit at integer pixel coordinates.  One that passes the float half-plane tests lies inside
+                    // the triangle up to the tests' rounding error (~1e-7 relative in NDC, i.e. < 1e-3 pixel here), so
+                    // the integer range of [pmin - m, pmax + m] with m = 0.01 px + 8 ulp is conservative -- and 3-9x
+                    // tighter than a whole-sample margin for the 1-2 pixel faces of ShapeNet-sized meshes.
                     const float pxmin = fminf(fminf(p[0][0], p[1][0]), p[2][0]);
                     const float pxmax = fmaxf(fmaxf(p[0][0], p[1][0]), p[2][0]);
                     const float pymin = fminf(fminf(p[0][1], p[1][1]), p[2][1]);
                     const float pymax = fmaxf(fmaxf(p[0][1], p[1][1]), p[2][1]);
-                    x0 = max(__float2int_rd(pxmin) - 1, 0);
-                    y0 = max(__float2int_rd(pymin) - 1, 0);
-                    x1 = min(__float2int_ru(pxmax) + 1, Ws - 1);
-                    y1 = min(__float2int_ru(pymax) + 1, Hs - 1);
+                    const float mx = 0.01f + 1e-6f * fmaxf(fabsf(pxmin), fabsf(pxmax));
+                    const float my = 0.01f + 1e-6f * fmaxf(fabsf(pymin), fabsf(pymax));
+                    x0 = max(__float2int_ru(pxmin - mx), 0);
+                    y0 = max(__float2int_ru(pymin - my), 0);
+                    x1 = min(__float2int_rd(pxmax + mx), Ws - 1);
+                    y1 = min(__float2int_rd(pymax + my), Hs - 1);
                 }
                 active = (x0 <= x1) && (y0 <= y1);
             }
@@ -509,6 +527,23 @@ __global__ void __launch_bounds__(256) k_fill_background(FwdParams P) {
     }
 }
 
+// faces -> tiles: count (FILL = false), exclusive scan, fill (FILL = true).  One thread per active face.
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_bin_faces(int B, int tiles_x, int tiles_y, Workspace ws) {
+    const int b = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ws.active_count[b]) return;
+    if (FILL && ws.tile_off[ws.num_tiles] > ws.bin_cap) return;        // does not fit: tiles scan the lists instead
+    const size_t slot = (size_t)b * ws.Fp + e;
+    const short4 bb = *reinterpret_cast<const short4*>(ws.active_bbox + slot * 4);
+    const int id = FILL ? ws.active_ids[slot] : 0;
+    for (int ty = bb.y / TH; ty <= bb.w / TH; ty++)
+        for (int tx = bb.x / TW; tx <= bb.z / TW; tx++) {
+            const int t = (b * tiles_y + ty) * tiles_x + tx;
+            if (!FILL) atomicAdd(&ws.tile_off[t], 1);
+            else ws.bin_ids[ws.tile_off[t] + atomicAdd(&ws.tile_cursor[t], 1)] = id;
+        }
+}
+
 // tiles that intersect each image's face bounding box: prefix[b] .. prefix[b+1]
 __device__ __forceinline__ void image_tile_range(const Workspace& ws, int b, int& tx0, int& ty0, int& nx, int& ny) {
     nx = 0; ny = 0; tx0 = 0; ty0 = 0;
@@ -565,8 +600,9 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
     __shared__ __align__(128) int s_ids[2][BCH];
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int s_queue[QCAP];
+    __shared__ int s_big[QCAP];
     __shared__ float s_xp[TW], s_yp[TH];
-    __shared__ int s_qn, s_tile;
+    __shared__ int s_qn, s_tile, s_nbig;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float far_f = P.clip.far_f;
@@ -593,6 +629,81 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
         const int sx1 = min(sx0 + TW, P.Ws) - 1, sy1 = min(sy0 + TH, P.Hs) - 1;
         const int count = ws.active_count[b];
 
+        // ---- face-parallel coverage of the queued faces: one warp per face, lanes over 8x4-sample blocks, two blocks
+        //      per iteration so that their division chains are independent (ILP)
+        auto rasterise_queue = [&](const int qn) {
+            // (1) small faces (<= 16 samples of this tile): one LANE per face -- ShapeNet-sized meshes are almost
+            //     entirely such faces and a whole warp per face would idle 3/4 of its lanes on per-face overhead
+            if (tid == 0) s_nbig = 0;
+            __syncthreads();
+            for (int q = tid; q < qn; q += NT) {
+                const int fn = s_queue[q];
+                const size_t fo = ((size_t)b * P.F + fn);
+                const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+                const int bx0 = max((int)bb.x, sx0), bx1 = min((int)bb.z, sx1);
+                const int by0 = max((int)bb.y, sy0), by1 = min((int)bb.w, sy1);
+                if ((bx1 - bx0 + 1) * (by1 - by0 + 1) > 16) { s_big[atomicAdd(&s_nbig, 1)] = fn; continue; }
+                float f[9], inv[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) { f[k] = __ldg(P.faces + fo * 9 + k); inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
+                for (int yy = by0; yy <= by1; yy++)
+                    for (int xx = bx0; xx <= bx1; xx++) {
+                        if (!inside_test(f, s_xp[xx - sx0], s_yp[yy - sy0])) continue;
+                        float z;
+                        if (depth_of(f, inv, (float)xx, (float)yy, P.clip, z))
+                            atomicMin(&s_key[(yy - sy0) * TW + (xx - sx0)], ((u64)__float_as_uint(z) << 32) | (unsigned)fn);
+                    }
+            }
+            __syncthreads();
+            // (2) larger faces: one WARP per face, lanes over 8x4-sample blocks, two blocks per iteration so that
+            //     their division chains are independent (ILP)
+            const int nbig = s_nbig;
+            for (int q = warp; q < nbig; q += NT / 32) {
+                const int fn = s_big[q];
+                const size_t fo = ((size_t)b * P.F + fn);
+                float f[9], inv[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) { f[k] = __ldg(P.faces + fo * 9 + k); inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
+                const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+                const int bx0 = max((int)bb.x, sx0), bx1 = min((int)bb.z, sx1);
+                const int by0 = max((int)bb.y, sy0), by1 = min((int)bb.w, sy1);
+                const int nbx = (bx1 - bx0) / 8 + 1, nby = (by1 - by0) / 4 + 1, nblk = nbx * nby;
+                for (int n0 = 0; n0 < nblk; n0 += 2) {
+                    int xa = bx0 + (n0 % nbx) * 8 + (lane & 7), ya = by0 + (n0 / nbx) * 4 + (lane >> 3);
+                    const int n1 = n0 + 1;
+                    int xb = bx0 + (n1 % nbx) * 8 + (lane & 7), yb = by0 + (n1 / nbx) * 4 + (lane >> 3);
+                    const bool va = xa <= bx1 && ya <= by1, vb = n1 < nblk && xb <= bx1 && yb <= by1;
+                    xa = min(xa, sx1); ya = min(ya, sy1); xb = min(xb, sx1); yb = min(yb, sy1);
+                    const bool ia = va && inside_test(f, s_xp[xa - sx0], s_yp[ya - sy0]);
+                    const bool ib = vb && inside_test(f, s_xp[xb - sx0], s_yp[yb - sy0]);
+                    if (!__any_sync(FULL, ia || ib)) continue;
+                    float za, zb;
+                    const bool oa = depth_of(f, inv, (float)xa, (float)ya, P.clip, za);
+                    const bool ob = depth_of(f, inv, (float)xb, (float)yb, P.clip, zb);
+                    if (ia && oa) atomicMin(&s_key[(ya - sy0) * TW + (xa - sx0)], ((u64)__float_as_uint(za) << 32) | (unsigned)fn);
+                    if (ib && ob) atomicMin(&s_key[(yb - sy0) * TW + (xb - sx0)], ((u64)__float_as_uint(zb) << 32) | (unsigned)fn);
+                }
+            }
+        };
+
+        const bool binned = ws.tile_off[ws.num_tiles] <= ws.bin_cap;
+        if (binned) {
+            // the faces of this tile were binned by k_bin_faces: every entry is a hit
+            const int tg = (b * P.tiles_y + ty) * P.tiles_x + tx;
+            const int off = ws.tile_off[tg], cnt = ws.tile_off[tg + 1] - off;
+            for (int k = tid; k < TH * TW; k += NT) s_key[k] = ~0ull;
+            if (tid < TW) s_xp[tid] = xp_of(sx0 + tid, P.Ws);
+            if (tid < TH) s_yp[tid] = xp_of(sy0 + tid, P.Hs);
+            for (int base = 0; base < cnt; base += QCAP) {
+                const int n = min(QCAP, cnt - base);
+                __syncthreads();
+                for (int k = tid; k < n; k += NT) s_queue[k] = ws.bin_ids[off + base + k];
+                __syncthreads();
+                rasterise_queue(n);
+            }
+        } else {
+        // ---- overflow of the bins: stream the image's whole active list (ids + bboxes) through shared memory with
+        //      1-D TMA bulk copies and test every bbox against the tile
         const int* ids_g = ws.active_ids + (size_t)b * ws.Fp;
         const short4* bb_g = reinterpret_cast<const short4*>(ws.active_bbox) + (size_t)b * ws.Fp;
         const int nchunks = (count + BCH - 1) / BCH;
@@ -642,40 +753,14 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                 const int qn = qtotal;
                 const bool last = (c == nchunks - 1) && (base + NT >= nin);
                 if (qn > QCAP - NT || last) {
-                    // ---- face-parallel coverage: one warp per queued face, lanes over an 8x4 sample footprint
-                    for (int q = warp; q < qn; q += NT / 32) {
-                        const int fn = s_queue[q];
-                        const size_t fo = ((size_t)b * P.F + fn);
-                        float f[9], inv[9];
-#pragma unroll
-                        for (int k = 0; k < 9; k++) { f[k] = __ldg(P.faces + fo * 9 + k); inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
-                        const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
-                        const int bx0 = max((int)bb.x, sx0), bx1 = min((int)bb.z, sx1);
-                        const int by0 = max((int)bb.y, sy0), by1 = min((int)bb.w, sy1);
-                        // two 8x4 sample blocks per iteration: their division chains are independent (ILP)
-                        const int nbx = (bx1 - bx0) / 8 + 1, nby = (by1 - by0) / 4 + 1, nblk = nbx * nby;
-                        for (int n0 = 0; n0 < nblk; n0 += 2) {
-                            int xa = bx0 + (n0 % nbx) * 8 + (lane & 7), ya = by0 + (n0 / nbx) * 4 + (lane >> 3);
-                            const int n1 = n0 + 1;
-                            int xb = bx0 + (n1 % nbx) * 8 + (lane & 7), yb = by0 + (n1 / nbx) * 4 + (lane >> 3);
-                            const bool va = xa <= bx1 && ya <= by1, vb = n1 < nblk && xb <= bx1 && yb <= by1;
-                            xa = min(xa, sx1); ya = min(ya, sy1); xb = min(xb, sx1); yb = min(yb, sy1);
-                            const bool ia = va && inside_test(f, s_xp[xa - sx0], s_yp[ya - sy0]);
-                            const bool ib = vb && inside_test(f, s_xp[xb - sx0], s_yp[yb - sy0]);
-                            if (!__any_sync(FULL, ia || ib)) continue;
-                            float za, zb;
-                            const bool oa = depth_of(f, inv, (float)xa, (float)ya, P.clip, za);
-                            const bool ob = depth_of(f, inv, (float)xb, (float)yb, P.clip, zb);
-                            if (ia && oa) atomicMin(&s_key[(ya - sy0) * TW + (xa - sx0)], ((u64)__float_as_uint(za) << 32) | (unsigned)fn);
-                            if (ib && ob) atomicMin(&s_key[(yb - sy0) * TW + (xb - sx0)], ((u64)__float_as_uint(zb) << 32) | (unsigned)fn);
-                        }
-                    }
+                    rasterise_queue(qn);
                     __syncthreads();
                     if (tid == 0) s_qn = 0;
                     qtotal = 0;
                     __syncthreads();
                 }
             }
+        }
         }
         __syncthreads();
 
@@ -1551,48 +1636,50 @@ __device__ __forceinline__ int block_exclusive_scan_256(int v, int* s_warp, int&
     return before + x - v;
 }
 
-__global__ void __launch_bounds__(256) k_scan_reduce(Workspace ws) {
+// The scan runs either over ws.scan_buf (length known on the device only: n_fixed < 0) or over any int buffer of a
+// length the host knows (the per-tile face counts of the forward).
+__global__ void __launch_bounds__(256) k_scan_reduce(Workspace ws, int* buf, int* sums, int n_fixed) {
     __shared__ int s_warp[8];
-    const int n = scan_len(ws);
+    const int n = n_fixed >= 0 ? n_fixed : scan_len(ws);
     const int base = blockIdx.x * SCAN_ELEMS;
     if (base >= n) return;
     int v = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { const int i = base + threadIdx.x * 8 + k; if (i < n) v += ws.scan_buf[i]; }
+    for (int k = 0; k < 8; k++) { const int i = base + threadIdx.x * 8 + k; if (i < n) v += buf[i]; }
     int total;
     block_exclusive_scan_256(v, s_warp, total);
-    if (threadIdx.x == 0) ws.block_sums[blockIdx.x] = total;
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(256) k_scan_sums(Workspace ws) {
+__global__ void __launch_bounds__(256) k_scan_sums(Workspace ws, int* sums, int n_fixed) {
     __shared__ int s_warp[8];
-    const int n = scan_len(ws);
+    const int n = n_fixed >= 0 ? n_fixed : scan_len(ws);
     const int nb = (n + SCAN_ELEMS - 1) / SCAN_ELEMS;
     int carry = 0;
     for (int base = 0; base < nb; base += 256) {
         const int i = base + threadIdx.x;
-        const int v = i < nb ? ws.block_sums[i] : 0;
+        const int v = i < nb ? sums[i] : 0;
         int total;
         const int ex = block_exclusive_scan_256(v, s_warp, total);
-        if (i < nb) ws.block_sums[i] = carry + ex;
+        if (i < nb) sums[i] = carry + ex;
         carry += total;
     }
 }
 
-__global__ void __launch_bounds__(256) k_scan_apply(Workspace ws) {
+__global__ void __launch_bounds__(256) k_scan_apply(Workspace ws, int* buf, const int* sums, int n_fixed) {
     __shared__ int s_warp[8];
-    const int n = scan_len(ws);
+    const int n = n_fixed >= 0 ? n_fixed : scan_len(ws);
     const int base = blockIdx.x * SCAN_ELEMS;
     if (base >= n) return;
     int v[8], sum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) { const int i = base + threadIdx.x * 8 + k; v[k] = i < n ? ws.scan_buf[i] : 0; sum += v[k]; }
+    for (int k = 0; k < 8; k++) { const int i = base + threadIdx.x * 8 + k; v[k] = i < n ? buf[i] : 0; sum += v[k]; }
     int total;
-    int run = ws.block_sums[blockIdx.x] + block_exclusive_scan_256(sum, s_warp, total);
+    int run = sums[blockIdx.x] + block_exclusive_scan_256(sum, s_warp, total);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int i = base + threadIdx.x * 8 + k;
-        if (i < n) ws.scan_buf[i] = run;
+        if (i < n) buf[i] = run;
         run += v[k];
     }
 }
@@ -2067,13 +2154,13 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         if ((rc = check_launch())) return rc;
         const int sblocks = (ws.scan_n + SCAN_ELEMS - 1) / SCAN_ELEMS;
         timing_begin("k_scan_reduce", st);
-        k_scan_reduce<<<sblocks, 256, 0, st>>>(ws);
+        k_scan_reduce<<<sblocks, 256, 0, st>>>(ws, ws.scan_buf, ws.block_sums, -1);
         if ((rc = check_launch())) return rc;
         timing_begin("k_scan_sums", st);
-        k_scan_sums<<<1, 256, 0, st>>>(ws);
+        k_scan_sums<<<1, 256, 0, st>>>(ws, ws.block_sums, -1);
         if ((rc = check_launch())) return rc;
         timing_begin("k_scan_apply", st);
-        k_scan_apply<<<sblocks, 256, 0, st>>>(ws);
+        k_scan_apply<<<sblocks, 256, 0, st>>>(ws, ws.scan_buf, ws.block_sums, -1);
         if ((rc = check_launch())) return rc;
         timing_begin("k_bwd_steps", st);
         k_bwd_steps<true><<<fgrid, 256, 0, st>>>(P, ws);
@@ -2278,6 +2365,25 @@ int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
     P.rgb = r->rgb; P.alpha = r->alpha; P.depth = r->depth; P.face_index = r->face_index; P.rgb_ss = r->rgb_ss;
     P.tiles_x = (Wss + TW - 1) / TW; P.tiles_y = (Hs + TH - 1) / TH;
     P.num_tiles = P.tiles_x * P.tiles_y * r->B;
+    {   // faces -> tiles (count, scan, fill); skipped work when it does not fit is handled inside the kernels
+        const dim3 bgrid((unsigned)((ws.Fp + 255) / 256), (unsigned)r->B);
+        const int tn = ws.num_tiles + 1, tblocks = (tn + SCAN_ELEMS - 1) / SCAN_ELEMS;
+        timing_begin("k_bin_faces", st);
+        k_bin_faces<false><<<bgrid, 256, 0, st>>>(r->B, P.tiles_x, P.tiles_y, ws);
+        if ((rc = check_launch())) return rc;
+        timing_begin("k_scan_reduce", st);
+        k_scan_reduce<<<tblocks, 256, 0, st>>>(ws, ws.tile_off, ws.bin_sums, tn);
+        if ((rc = check_launch())) return rc;
+        timing_begin("k_scan_sums", st);
+        k_scan_sums<<<1, 256, 0, st>>>(ws, ws.bin_sums, tn);
+        if ((rc = check_launch())) return rc;
+        timing_begin("k_scan_apply", st);
+        k_scan_apply<<<tblocks, 256, 0, st>>>(ws, ws.tile_off, ws.bin_sums, tn);
+        if ((rc = check_launch())) return rc;
+        timing_begin("k_bin_faces", st);
+        k_bin_faces<true><<<bgrid, 256, 0, st>>>(r->B, P.tiles_x, P.tiles_y, ws);
+        if ((rc = check_launch())) return rc;
+    }
     timing_begin("k_fill_background", st);
     k_fill_background<<<sm_count() * 8, 256, 0, st>>>(P);
     if ((rc = check_launch())) return rc;

@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""BASELINE config 3: one full geometric-branch training step -- encoder (ResNet-18 + FC, bf16 channels-last through
+cuDNN) -> pose algebra -> class sampling -> batched FFD / camera transform -> render 384x384 (768x768 internal) ->
+masked MSE + REINFORCE -> Adam -- on synthetic VKITTI-shaped inputs with ShapeNet-sized template meshes."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, '3d-sdn_b200')):
+    sys.path.insert(0, p)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import sdn_b200  # noqa: E402
+from sdn_b200 import workloads as wl  # noqa: E402
+from derender3d import TargetType  # noqa: E402
+from derender3d.models import Derenderer3d, ShapenetObj  # noqa: E402
+from derender3d.train_step import geometric_losses  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=16)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--render-size', type=int, default=384)
+    ap.add_argument('--faces', type=int, default=72576, help='triangles per template mesh (ShapeNet: 29k-72k)')
+    ap.add_argument('--fp32', action='store_true')
+    ap.add_argument('--encoder-only', action='store_true')
+    args = ap.parse_args()
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    n_lon = 192
+    n_lat = max(4, args.faces // (2 * n_lon) + 1)
+    objs = []
+    for k in range(8):
+        v, f = wl.superellipsoid_mesh(n_lon, n_lat, 0.5 + 0.04 * k, 0.6)
+        objs.append(ShapenetObj(vertices=v * np.array([1.0, 0.35, 0.45], np.float32), faces=f))
+    B, S = args.batch, args.render_size
+    model = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=objs).to(dev).train()
+    model.derenderer.net = model.derenderer.net.to(memory_format=torch.channels_last)
+    # start from a pose head that puts objects in view (a real run starts from the pre-trained pose stage)
+    with torch.no_grad():
+        model.derenderer._fc3.weight.mul_(0.01)
+        model.derenderer._fc3.bias.zero_()
+        model.derenderer._fc3.bias[0] = 1.0                      # theta
+        model.derenderer._fc3.bias[4:7] = torch.tensor([1.3, 0.4, 0.5])   # log scales
+        model.derenderer._fc3.bias[7] = 2.2                      # log depth
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3)
+    g = torch.Generator().manual_seed(0)
+    c = 0.3 * (torch.rand(B, 2, generator=g) - 0.5)
+    d = 0.25 + 0.15 * torch.rand(B, 2, generator=g)
+    roi = torch.cat([c - d / 2, c + d / 2], dim=1).to(dev)
+    batch = {'images': torch.randn(B, 3, 224, 224, generator=g).to(dev).contiguous(memory_format=torch.channels_last),
+             'roi_norms': roi, 'focals': torch.full((B, 1), 725.0, device=dev),
+             'targets': torch.full((B,), TargetType.full, device=dev, dtype=torch.long),
+             'thetas': torch.rand(B, 1, generator=g).to(dev), 'translation2ds': torch.zeros(B, 2, device=dev),
+             'log_scales': torch.tensor([1.3, 0.4, 0.5], device=dev).expand(B, 3).contiguous(),
+             'log_depths': torch.full((B, 1), 2.2, device=dev),
+             'masks': (torch.rand(B, 1, 256, 256, generator=g) > 0.5).float().to(dev),
+             'ignores': torch.zeros(B, 1, 256, 256, device=dev)}
+    sdn_b200.DEFAULT_FAST_MATH = True
+    amp = not args.fp32
+
+    def step():
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=amp):
+            if args.encoder_only:
+                m = torch.stack([roi[:, 2] + roi[:, 0], roi[:, 3] + roi[:, 1]], dim=1) / 2.0
+                dr = torch.stack([roi[:, 2] - roi[:, 0], roi[:, 3] - roi[:, 1]], dim=1)
+                out = model.derenderer(batch['images'], m, dr)
+                loss = sum(v.float().pow(2).mean() for v in out.values())
+                cov = 0.0
+            else:
+                blob = model(batch['images'], batch['roi_norms'], batch['focals'])
+                loss = sum(geometric_losses(blob, batch, TargetType.full).values())
+                cov = blob['_masks']
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss, cov
+
+    loss, cov = step()
+    coverage = float((cov > 0).float().mean()) if not args.encoder_only else 0.0
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, _ = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    sdn_b200.timing_enable(True)
+    sdn_b200.timing_read()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    kern = {k: round(t[0] / 3, 3) for k, t in sorted(sdn_b200.timing_read().items(), key=lambda kv: -kv[1][0])[:6]}
+    sdn_b200.timing_enable(False)
+    nparam = sum(p.numel() for p in model.parameters())
+    print(json.dumps({'workload': 'config3: B=%d, encoder 224x224 %s, %d-triangle templates, render %dx%d, mode full, Adam'
+                      % (B, 'fp32' if args.fp32 else 'bf16 autocast channels-last', len(objs[0].faces), S, S),
+                      'encoder_only': args.encoder_only, 'ms_per_step': round(ms, 3),
+                      'objects_per_s': round(B / ms * 1e3, 1), 'loss': float(loss), 'mask_coverage': round(coverage, 3),
+                      'parameters': nparam, 'render_kernels_ms': kern}))
+
+
+if __name__ == '__main__':
+    main()
