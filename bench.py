@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in out.strip().split(',')])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
@@ -324,8 +324,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--exact', action='store_true', help='IEEE-division distance math in the backward (default: fast)')
