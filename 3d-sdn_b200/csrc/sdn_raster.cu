@@ -1290,6 +1290,39 @@ __device__ __forceinline__ bool step_cross(const EdgeSetup& E, int d0, float& d1
     return !(d1_out < 0 || E.is1 <= d1_out);
 }
 
+// A face is "small" when its bbox fits 8x8 samples: ShapeNet-sized meshes consist almost entirely of such faces, and
+// warp-per-face stages would idle most lanes on them, so they get lane-per-item / lane-per-face paths.
+__device__ __forceinline__ bool small_face(const short4 bb) { return (bb.z - bb.x) < 8 && (bb.w - bb.y) < 8; }
+// A lane-per-face path for k_bwd_face was tried for tiny faces and measured slower on both workloads (the per-face
+// state costs 164 registers and serialises the samples); every face therefore goes through the 4x32-sample units.
+__device__ __forceinline__ bool tiny_face(const short4) { return false; }
+
+// writes the out-sweep query of one edge step (rasterize.py:601-656, deferred to k_line_sweep) and files it under its line
+__device__ __forceinline__ void emit_query(const BwdParams& P, const Workspace& ws, const EdgeSetup& E, int b, int fn,
+                                           const float* bg, int axis, int d0, float d1_cross, int d1_out, size_t mi_in,
+                                           int qi, int line) {
+    const float d0f = (float)d0;
+    const bool use0 = E.p[1][0] != d0f, use1 = E.p[0][0] != d0f;
+    const float k0 = __fdiv_rn(E.dp, E.p[1][0] - d0f) * (2.0f / (float)E.is1);
+    const float k1 = __fdiv_rn(E.dp, d0f - E.p[0][0]) * (2.0f / (float)E.is1);
+    const int d1_limit = (0 < E.direction) ? E.is1 - 1 : 0;
+    Query q;
+    q.lo = max(min(d1_out, d1_limit), 0);
+    int hf = min(max(d1_out, d1_limit), E.is1 - 1);
+    if (use0) hf |= QF_USE0;
+    if (use1) hf |= QF_USE1;
+    if ((k0 > 0.0f) == (E.direction > 0) && k0 != 0.0f) hf |= QF_POS0;
+    if ((k1 > 0.0f) == (E.direction > 0) && k1 != 0.0f) hf |= QF_POS1;
+    q.hi_flags = hf;
+    q.xc = d1_cross; q.k0 = use0 ? k0 : 0.0f; q.k1 = use1 ? k1 : 0.0f;
+    float c[3] = {0.0f, 0.0f, 0.0f};
+    if (P.use_rgb) colour_at(P, b, (size_t)b * P.Hs * P.Ws + mi_in, fn, bg, c);
+    q.c0 = c[0]; q.c1 = c[1]; q.c2 = c[2];
+    ws.queries[qi] = q;
+    const int pos = atomicAdd(&ws.line_cursor[line], 1);
+    ws.line_items[ws.scan_buf[line] + pos] = qi;
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
     const int lane = threadIdx.x & 31;
@@ -1299,8 +1332,13 @@ __global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
     if (!EMIT && blockIdx.x == 0 && threadIdx.x == 0) { item_n[nvis * ITEMS] = 0; unit_n[nvis] = 0; }   // scan sentinels
     if (EMIT && bwd_overflow(ws)) return;      // does not fit: k_backward_items<true> takes over
     const int q_origin = EMIT ? item_n[0] : 0;
-    for (int vi = blockIdx.x * 8 + (threadIdx.x >> 5); vi < nvis; vi += gridDim.x * 8) {
+    const int gwarp = blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = gridDim.x * 8;
+
+    // ---- (A) larger faces: one warp per face, the six (edge, axis) items in turn, lanes over the steps
+    for (int vi = gwarp; vi < nvis; vi += nwarps) {
         const size_t fo = (size_t)ws.vis_ids[vi];
+        const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+        if (small_face(bb)) continue;
         const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
         const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
         float f[9];
@@ -1310,7 +1348,6 @@ __global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
         if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
         else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
         {   // units of k_bwd_face: the face's bbox cut into 4-row x 32-column blocks
-            const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
             const int nbx = (bb.z - bb.x) / UNIT_W + 1, nby = (bb.w - bb.y) / UNIT_H + 1;
             if (!EMIT) { if (lane == 0) { item_n[vi * ITEMS + 6] = 0; unit_n[vi] = nbx * nby; } }
             else {
@@ -1341,29 +1378,50 @@ __global__ void __launch_bounds__(256) k_bwd_steps(BwdParams P, Workspace ws) {
                 if (!sweep) continue;
                 const int line = line0 + d0;
                 if (!EMIT) { atomicAdd(&ws.scan_buf[line], 1); continue; }
-                const float d0f = (float)d0;
-                const bool use0 = E.p[1][0] != d0f, use1 = E.p[0][0] != d0f;
-                const float k0 = __fdiv_rn(E.dp, E.p[1][0] - d0f) * (2.0f / (float)E.is1);
-                const float k1 = __fdiv_rn(E.dp, d0f - E.p[0][0]) * (2.0f / (float)E.is1);
-                const int d1_limit = (0 < E.direction) ? E.is1 - 1 : 0;
-                Query q;
-                q.lo = max(min(d1_out, d1_limit), 0);
-                int hf = min(max(d1_out, d1_limit), E.is1 - 1);
-                if (use0) hf |= QF_USE0;
-                if (use1) hf |= QF_USE1;
-                if ((k0 > 0.0f) == (E.direction > 0) && k0 != 0.0f) hf |= QF_POS0;
-                if ((k1 > 0.0f) == (E.direction > 0) && k1 != 0.0f) hf |= QF_POS1;
-                q.hi_flags = hf;
-                q.xc = d1_cross; q.k0 = use0 ? k0 : 0.0f; q.k1 = use1 ? k1 : 0.0f;
-                float c[3] = {0.0f, 0.0f, 0.0f};
-                if (P.use_rgb) colour_at(P, b, (size_t)b * P.Hs * P.Ws + mi_in, fn, bg, c);
-                q.c0 = c[0]; q.c1 = c[1]; q.c2 = c[2];
-                ws.queries[qi] = q;
-                const int pos = atomicAdd(&ws.line_cursor[line], 1);
-                ws.line_items[ws.scan_buf[line] + pos] = qi;
+                emit_query(P, ws, E, b, fn, bg, axis, d0, d1_cross, d1_out, mi_in, qi, line);
             }
             if (!EMIT && lane == 0) item_n[vi * ITEMS + kind] = nq;
         }
+    }
+
+    // ---- (B) small faces: one LANE per (face, edge, axis) item, five faces per warp, steps walked serially
+    for (int base = gwarp * 5; base < nvis; base += nwarps * 5) {
+        const int vi = base + lane / 6, kind = lane % 6;
+        if (lane >= 30 || vi >= nvis) continue;
+        const size_t fo = (size_t)ws.vis_ids[vi];
+        const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+        if (!small_face(bb)) continue;
+        const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
+        const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+        float f[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) f[k] = __ldg(P.faces + fo * 9 + k);
+        float bg[3];
+        if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+        else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+        if (kind == 0) {        // units of k_bwd_face: none for tiny faces (its lane path), else the 4x32 blocks of the bbox
+            const int nun = tiny_face(bb) ? 0 : ((bb.z - bb.x) / UNIT_W + 1) * ((bb.w - bb.y) / UNIT_H + 1);
+            if (!EMIT) { item_n[vi * ITEMS + 6] = 0; unit_n[vi] = nun; }
+            else { const int ub = unit_n[vi] - unit_n[0]; for (int u = 0; u < nun; u++) ws.unit_tab[ub + u] = make_int2(vi, u); }
+        }
+        const int axis = kind & 1;
+        EdgeSetup E;
+        edge_setup(f, kind >> 1, axis, P.Hs, P.Ws, E);
+        const int line0 = b * (P.Hs + P.Ws) + (axis == 0 ? P.Hs : 0);
+        const int qbase = EMIT ? item_n[vi * ITEMS + kind] - q_origin : 0;
+        int nq = 0;
+        for (int d0 = E.d0_from; d0 <= E.d0_to; d0++) {
+            float d1_cross;
+            int d1_in = 0, d1_out = 0;
+            if (!step_cross(E, d0, d1_cross, d1_in, d1_out)) continue;
+            const size_t mi_in = axis == 0 ? (size_t)d1_in * P.Ws + d0 : (size_t)d0 * P.Ws + d1_in;
+            if (__ldg(fim + mi_in) != fn) continue;                // rasterize.py:601
+            const int line = line0 + d0;
+            if (!EMIT) atomicAdd(&ws.scan_buf[line], 1);
+            else emit_query(P, ws, E, b, fn, bg, axis, d0, d1_cross, d1_out, mi_in, qbase + nq, line);
+            nq++;
+        }
+        if (!EMIT) item_n[vi * ITEMS + kind] = nq;
     }
 }
 
@@ -1385,199 +1443,211 @@ __device__ __forceinline__ void eval_owned_fast(const float* f, const float* inv
 // triangle; here each owned sample asks, for the six (edge, axis) items, whether the step through its own row / column
 // would have visited it (identical float tests), so the cost is proportional to the owned area.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bwd_face_role(const BwdParams& P, const Workspace& ws) {
-    const int lane = threadIdx.x & 31;
-    if (bwd_overflow(ws)) return;                    // the direct kernel does all of it
-    const int* unit_n = unit_region(ws);
-    const int nunits = unit_n[ws.vis_count[0]] - unit_n[0];
-    const bool need_depth = P.use_depth && P.g_depth;
-    const bool need_tex = P.use_rgb && P.g_rgb && P.grad_textures;
-    const bool need_k6 = P.use_alpha || P.use_rgb;
+// per-face constants of k_bwd_face (registers)
+struct FaceCtx {
+    size_t fo, base_px;
+    int b, fn, ts;
+    const int32_t* fim;
+    const float *ga_p, *gr_p, *gd_p;
+    float f[9], inv[9], zf[9], bg[3];
+    float pc[3][2];          // pixel coordinates [vertex][x|y]
+    float slope[2][3];       // [axis][edge e = (e, e+1)]: exact IEEE quotient, orientation-independent
+    int d0_from[6], d0_to[6];
+    short4 bb;
+};
+
+__device__ __forceinline__ void face_ctx_load(const BwdParams& P, const Workspace& ws, size_t fo, bool need_depth,
+                                              FaceCtx& C) {
+    const size_t plane = (size_t)P.H * P.W;
+    C.fo = fo;
+    C.b = (int)(fo / P.F); C.fn = (int)(fo % P.F);
+    C.fim = P.face_index + (size_t)C.b * P.Hs * P.Ws;
+    C.base_px = (size_t)C.b * P.Hs * P.Ws;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { C.f[k] = __ldg(P.faces + fo * 9 + k); C.inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
+    const float* zsrc = P.faces + ((size_t)(P.batch_bug ? 0 : C.b) * P.F + C.fn) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; k++) C.zf[k] = __ldg(zsrc + k);
+    C.bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
+    if (P.bg_b) { C.bg[0] = P.bg_b[C.b * 3]; C.bg[1] = P.bg_b[C.b * 3 + 1]; C.bg[2] = P.bg_b[C.b * 3 + 2]; }
+    else { C.bg[0] = P.bg[0]; C.bg[1] = P.bg[1]; C.bg[2] = P.bg[2]; }
+    C.ga_p = (P.use_alpha && P.g_alpha) ? P.g_alpha + (size_t)C.b * plane : nullptr;
+    C.gr_p = (P.use_rgb && P.g_rgb) ? P.g_rgb + (size_t)C.b * 3 * plane : nullptr;
+    C.gd_p = need_depth ? P.g_depth + (size_t)C.b * plane : nullptr;
+    C.ts = P.ts == 1 ? 2 : P.ts;
+    // constants of the six (edge, axis) items (rasterize.py:540-566), hoisted
+#pragma unroll
+    for (int n = 0; n < 3; n++) { C.pc[n][0] = to_pixel(C.f[3 * n], P.Ws); C.pc[n][1] = to_pixel(C.f[3 * n + 1], P.Hs); }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int e = 0; e < 3; e++)
+            C.slope[a][e] = __fdiv_rn(C.pc[(e + 1) % 3][1 - a] - C.pc[e][1 - a], C.pc[(e + 1) % 3][a] - C.pc[e][a]);
+#pragma unroll
+    for (int kind = 0; kind < 6; kind++) {
+        const int e = kind >> 1, a = kind & 1;
+        const float p00 = C.pc[e][a], p10 = C.pc[(e + 1) % 3][a];
+        const int is0 = a == 0 ? P.Ws : P.Hs;
+        C.d0_from[kind] = __double2int_rz(fmax((double)ceilf(fminf(p00, p10)), 0.));
+        C.d0_to[kind] = __double2int_rz(fmin((double)fmaxf(p00, p10), is0 - 1.));
+    }
+}
+
+// everything one owned sample (xx, yy) contributes: depth / texture gathers (rasterize.py:747-844) and the in-sweeps
+// (rasterize.py:659-727: would the step through this sample's row / column have visited it?  same float tests)
+__device__ __forceinline__ void face_sample(const BwdParams& P, const FaceCtx& C, int xx, int yy, bool need_depth,
+                                            bool need_tex, bool need_k6, float* acc, float* S, float* G) {
     const float sc = (P.ss == 2) ? 0.25f : 1.0f;
     const size_t plane = (size_t)P.H * P.W;
     const float ea = (float)P.eps_a, er = (float)P.eps_r;
     const bool one_pass = !(P.split || !P.use_alpha);       // alpha and rgb summed before the > 0 test
+    const int fn = C.fn, b = C.b;
+    const size_t mi = (size_t)yy * P.Ws + xx;
+    const size_t oi = out_index(P, xx, yy);
+    // gradients at this sample (one set of loads for everything below)
+    const float ga = C.ga_p ? __ldg(C.ga_p + oi) * sc : 0.0f;
+    float g[3] = {0.0f, 0.0f, 0.0f};
+    if (C.gr_p) { g[0] = __ldg(C.gr_p + oi) * sc; g[1] = __ldg(C.gr_p + plane + oi) * sc; g[2] = __ldg(C.gr_p + 2 * plane + oi) * sc; }
 
+    if (need_depth || need_tex) {
+        float w[3], zp;
+        eval_owned_fast(C.f, C.inv, (float)xx, (float)yy, w, zp);
+        if (need_depth) {      // rasterize.py:821-824: sum_s gd * w_k * depth^2
+            const float gd = __ldg(C.gd_p + oi) * sc;
+            const float d2 = zp * zp;
+#pragma unroll
+            for (int k = 0; k < 3; k++) S[k] += gd * w[k] * d2;
+        }
+        if (need_tex) {        // rasterize.py:772-778
+            float tif[3];
+            texture_index(w, zp, C.zf, C.ts, P.eps_tex, tif);
+            if (P.ts == 1) {
+                float wsum = 0.0f;
+#pragma unroll
+                for (int pn = 0; pn < 8; pn++) { int tii[3]; wsum += corner_weight(tif, pn, tii); }
+#pragma unroll
+                for (int k = 0; k < 3; k++) G[k] += wsum * g[k];
+            } else {
+                const int ts = C.ts;
+                float* gt = P.grad_textures + C.fo * ts * ts * ts * 3;
+#pragma unroll
+                for (int pn = 0; pn < 8; pn++) {
+                    int tii[3];
+                    const float cw = corner_weight(tif, pn, tii);
+                    const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) atomicAdd(gt + isc * 3 + k, cw * g[k]);
+                }
+            }
+        }
+    }
+    if (!need_k6) return;
+
+    float csel[3] = {0.0f, 0.0f, 0.0f};
+    if (P.use_rgb) colour_at(P, b, C.base_px + mi, fn, C.bg, csel);
+    float d1c[6];
+    int d1o[6];
+    unsigned inc = 0;
+#pragma unroll
+    for (int kind = 0; kind < 6; kind++) {
+        const int e = kind >> 1, a = kind & 1;
+        const int i0 = e, i1 = (e + 1) % 3, i2 = (e + 2) % 3;
+        const float p00 = C.pc[i0][a], p01 = C.pc[i0][1 - a], p10 = C.pc[i1][a];
+        const float p20 = C.pc[i2][a], p21 = C.pc[i2][1 - a];
+        const int is1 = a == 0 ? P.Hs : P.Ws;
+        const int d0 = a == 0 ? xx : yy, d1 = a == 0 ? yy : xx;
+        const float d0f = (float)d0;
+        int direction;
+        if (a == 0) direction = (p00 < p10) ? -1 : 1; else direction = (p00 < p10) ? 1 : -1;
+        float dc = C.slope[a][e] * (d0f - p00);
+        dc = dc + p01;
+        const int d1_in = (0 < direction) ? __float2int_rz(floorf(dc)) : __float2int_rz(ceilf(dc));
+        const int d1_out = d1_in + direction;
+        float dc2;                                   // rasterize.py:662-667
+        if ((d0f - p00) * (d0f - p20) < 0) { dc2 = C.slope[a][i2] * (d0f - p00); dc2 = dc2 + p01; }
+        else { dc2 = C.slope[a][i1] * (d0f - p20); dc2 = dc2 + p21; }
+        const int d1_limit = (0 < direction) ? __float2int_rz(ceilf(dc2)) : __float2int_rz(floorf(dc2));
+        const int d1_from = max(min(d1_in, d1_limit), 0), d1_to = min(max(d1_in, d1_limit), is1 - 1);
+        const bool ok = d0 >= C.d0_from[kind] && d0 <= C.d0_to[kind] && d1_in >= 0 && d1_in < is1 &&
+                        d1_out >= 0 && d1_out < is1 && d1 >= d1_from && d1 <= d1_to;
+        d1c[kind] = dc; d1o[kind] = d1_out;
+        if (ok) inc |= 1u << kind;
+    }
+    if (!inc) return;
+    int ido[6];
+#pragma unroll
+    for (int kind = 0; kind < 6; kind++) {      // the out-pixel loads go out together
+        const int a = kind & 1;
+        const size_t mo = a == 0 ? (size_t)d1o[kind] * P.Ws + xx : (size_t)yy * P.Ws + d1o[kind];
+        ido[kind] = (inc >> kind) & 1 ? __ldg(C.fim + mo) : -1;
+    }
+#pragma unroll
+    for (int kind = 0; kind < 6; kind++) {
+        if (!((inc >> kind) & 1)) continue;
+        const int e = kind >> 1, a = kind & 1;
+        const float p00 = C.pc[e][a], p10 = C.pc[(e + 1) % 3][a];
+        const int is1 = a == 0 ? P.Hs : P.Ws;
+        const int d0 = a == 0 ? xx : yy, d1 = a == 0 ? yy : xx;
+        const float d0f = (float)d0;
+        const size_t mo = a == 0 ? (size_t)d1o[kind] * P.Ws + xx : (size_t)yy * P.Ws + d1o[kind];
+        float da = ((1.0f - (ido[kind] >= 0 ? 1.0f : 0.0f)) * ga), dr = 0.0f;     // alpha here is 1
+        if (P.use_rgb) {
+            float co[3];
+            colour_at(P, b, C.base_px + mo, ido[kind], C.bg, co);
+            const float d = (csel[0] - co[0]) * g[0] + (csel[1] - co[1]) * g[1] + (csel[2] - co[2]) * g[2];
+            if (one_pass) da += d; else dr = d;
+        }
+        const float pa = fmaxf(da, 0.0f), pr = fmaxf(dr, 0.0f);
+        if (pa <= 0.0f && pr <= 0.0f) continue;
+        const float t = (float)d1 - d1c[kind];
+        const float dp = p10 - p00, k2 = 2.0f / (float)is1;
+        const float x0 = dp * rcp_approx(p10 - d0f) * k2 * t, x1 = dp * rcp_approx(d0f - p00) * k2 * t;
+        if (p10 != d0f) {
+            const float a0 = (0.0f < x0) ? x0 + ea : x0 - ea, r0 = (0.0f < x0) ? x0 + er : x0 - er;
+            acc[kind * 2] -= __fmaf_rn(pa, rcp_approx(a0), pr * rcp_approx(r0));
+        }
+        if (p00 != d0f) {
+            const float a1 = (0.0f < x1) ? x1 + ea : x1 - ea, r1 = (0.0f < x1) ? x1 + er : x1 - er;
+            acc[kind * 2 + 1] -= __fmaf_rn(pa, rcp_approx(a1), pr * rcp_approx(r1));
+        }
+    }
+}
+
+__device__ __forceinline__ void bwd_face_role(const BwdParams& P, const Workspace& ws) {
+    const int lane = threadIdx.x & 31;
+    if (bwd_overflow(ws)) return;                    // the direct kernel does all of it
+    const int nvis = ws.vis_count[0];
+    const int* unit_n = unit_region(ws);
+    const int nunits = unit_n[nvis] - unit_n[0];
+    const bool need_depth = P.use_depth && P.g_depth;
+    const bool need_tex = P.use_rgb && P.g_rgb && P.grad_textures;
+    const bool need_k6 = P.use_alpha || P.use_rgb;
+
+    // ---- (A) larger faces: unit = one 4-row x 32-column block of the face's bbox, one warp per unit
     for (;;) {
-        // unit = one 4-row x 32-column block of a visible face's bbox: uniform, small pieces of work
         int un = 0;
         if (lane == 0) un = atomicAdd(&ws.counters[2], 1);
         un = __shfl_sync(FULL, un, 0);
         if (un >= nunits) break;
         const int2 ut = ws.unit_tab[un];
-        const size_t fo = (size_t)ws.vis_ids[ut.x];
-        const int b = (int)(fo / P.F), fn = (int)(fo % P.F);
-        const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
-        const size_t base_px = (size_t)b * P.Hs * P.Ws;
-        float f[9], inv[9], zf[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) { f[k] = __ldg(P.faces + fo * 9 + k); inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
-        const float* zsrc = P.faces + ((size_t)(P.batch_bug ? 0 : b) * P.F + fn) * 9;
-#pragma unroll
-        for (int k = 0; k < 9; k++) zf[k] = __ldg(zsrc + k);
-        const short4 bb = *reinterpret_cast<const short4*>(ws.face_bbox + fo * 4);
-        float bg[3];
-        if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
-        else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
-        const float* ga_p = (P.use_alpha && P.g_alpha) ? P.g_alpha + (size_t)b * plane : nullptr;
-        const float* gr_p = (P.use_rgb && P.g_rgb) ? P.g_rgb + (size_t)b * 3 * plane : nullptr;
-        const float* gd_p = need_depth ? P.g_depth + (size_t)b * plane : nullptr;
-        const int ts = P.ts == 1 ? 2 : P.ts;
-
-        // ---- per-face constants of the six (edge, axis) items (rasterize.py:540-566), hoisted
-        float pc[3][2];                  // pixel coordinates [vertex][x|y]
-#pragma unroll
-        for (int n = 0; n < 3; n++) { pc[n][0] = to_pixel(f[3 * n], P.Ws); pc[n][1] = to_pixel(f[3 * n + 1], P.Hs); }
-        float slope[2][3];               // [axis][edge e = (e, e+1)]: exact IEEE quotient, orientation-independent
-#pragma unroll
-        for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int e = 0; e < 3; e++)
-                slope[a][e] = __fdiv_rn(pc[(e + 1) % 3][1 - a] - pc[e][1 - a], pc[(e + 1) % 3][a] - pc[e][a]);
-        int d0_from[6], d0_to[6];
-#pragma unroll
-        for (int kind = 0; kind < 6; kind++) {
-            const int e = kind >> 1, a = kind & 1;
-            const float p00 = pc[e][a], p10 = pc[(e + 1) % 3][a];
-            const int is0 = a == 0 ? P.Ws : P.Hs;
-            d0_from[kind] = __double2int_rz(fmax((double)ceilf(fminf(p00, p10)), 0.));
-            d0_to[kind] = __double2int_rz(fmin((double)fmaxf(p00, p10), is0 - 1.));
-        }
-
+        FaceCtx C;
+        face_ctx_load(P, ws, (size_t)ws.vis_ids[ut.x], need_depth, C);
         float S[3] = {0.0f, 0.0f, 0.0f}, G[3] = {0.0f, 0.0f, 0.0f};
         float acc[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) acc[k] = 0.0f;
-
-        {
-            const int nbx = (bb.z - bb.x) / UNIT_W + 1;
-            const int yy0 = bb.y + (ut.y / nbx) * UNIT_H, xx0 = bb.x + (ut.y % nbx) * UNIT_W;
-            const int yy = yy0 + (lane >> 3);
-            {
-                int idv[4];
+        const int nbx = (C.bb.z - C.bb.x) / UNIT_W + 1;
+        const int yy0 = C.bb.y + (ut.y / nbx) * UNIT_H, xx0 = C.bb.x + (ut.y % nbx) * UNIT_W;
+        const int yy = yy0 + (lane >> 3);
+        int idv[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {           // four independent loads in flight
-                    const int xx = xx0 + 8 * u + (lane & 7);
-                    idv[u] = (yy <= bb.w && xx <= bb.z) ? __ldg(fim + (size_t)yy * P.Ws + xx) : -2;
-                }
-#pragma unroll 1
-                for (int u = 0; u < 4; u++) {
-                    if (idv[u] != fn) continue;
-                    const int xx = xx0 + 8 * u + (lane & 7);
-                    const size_t mi = (size_t)yy * P.Ws + xx;
-                    const size_t oi = out_index(P, xx, yy);
-                    // gradients at this sample (one set of loads for everything below)
-                    const float ga = ga_p ? __ldg(ga_p + oi) * sc : 0.0f;
-                    float g[3] = {0.0f, 0.0f, 0.0f};
-                    if (gr_p) { g[0] = __ldg(gr_p + oi) * sc; g[1] = __ldg(gr_p + plane + oi) * sc; g[2] = __ldg(gr_p + 2 * plane + oi) * sc; }
-
-                    if (need_depth || need_tex) {
-                        float w[3], zp;
-                        eval_owned_fast(f, inv, (float)xx, (float)yy, w, zp);
-                        if (need_depth) {      // rasterize.py:821-824: sum_s gd * w_k * depth^2
-                            const float gd = __ldg(gd_p + oi) * sc;
-                            const float d2 = zp * zp;
-#pragma unroll
-                            for (int k = 0; k < 3; k++) S[k] += gd * w[k] * d2;
-                        }
-                        if (need_tex) {        // rasterize.py:772-778
-                            float tif[3];
-                            texture_index(w, zp, zf, ts, P.eps_tex, tif);
-                            if (P.ts == 1) {
-                                float wsum = 0.0f;
-#pragma unroll
-                                for (int pn = 0; pn < 8; pn++) { int tii[3]; wsum += corner_weight(tif, pn, tii); }
-#pragma unroll
-                                for (int k = 0; k < 3; k++) G[k] += wsum * g[k];
-                            } else {
-                                float* gt = P.grad_textures + fo * ts * ts * ts * 3;
-#pragma unroll
-                                for (int pn = 0; pn < 8; pn++) {
-                                    int tii[3];
-                                    const float cw = corner_weight(tif, pn, tii);
-                                    const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
-#pragma unroll
-                                    for (int k = 0; k < 3; k++) atomicAdd(gt + isc * 3 + k, cw * g[k]);
-                                }
-                            }
-                        }
-                    }
-                    if (!need_k6) continue;
-
-                    // ---- in-sweeps (rasterize.py:659-727): would the step through this sample's row / column have
-                    //      visited it?  Same float tests as the reference, evaluated per sample.
-                    float csel[3] = {0.0f, 0.0f, 0.0f};
-                    if (P.use_rgb) colour_at(P, b, base_px + mi, fn, bg, csel);
-                    float d1c[6];
-                    int d1o[6];
-                    unsigned inc = 0;
-#pragma unroll
-                    for (int kind = 0; kind < 6; kind++) {
-                        const int e = kind >> 1, a = kind & 1;
-                        const int i0 = e, i1 = (e + 1) % 3, i2 = (e + 2) % 3;
-                        const float p00 = pc[i0][a], p01 = pc[i0][1 - a], p10 = pc[i1][a], p11 = pc[i1][1 - a];
-                        const float p20 = pc[i2][a], p21 = pc[i2][1 - a];
-                        (void)p11;
-                        const int is1 = a == 0 ? P.Hs : P.Ws;
-                        const int d0 = a == 0 ? xx : yy, d1 = a == 0 ? yy : xx;
-                        const float d0f = (float)d0;
-                        int direction;
-                        if (a == 0) direction = (p00 < p10) ? -1 : 1; else direction = (p00 < p10) ? 1 : -1;
-                        float dc = slope[a][e] * (d0f - p00);
-                        dc = dc + p01;
-                        const int d1_in = (0 < direction) ? __float2int_rz(floorf(dc)) : __float2int_rz(ceilf(dc));
-                        const int d1_out = d1_in + direction;
-                        float dc2;                                   // rasterize.py:662-667
-                        if ((d0f - p00) * (d0f - p20) < 0) { dc2 = slope[a][i2] * (d0f - p00); dc2 = dc2 + p01; }
-                        else { dc2 = slope[a][i1] * (d0f - p20); dc2 = dc2 + p21; }
-                        const int d1_limit = (0 < direction) ? __float2int_rz(ceilf(dc2)) : __float2int_rz(floorf(dc2));
-                        const int d1_from = max(min(d1_in, d1_limit), 0), d1_to = min(max(d1_in, d1_limit), is1 - 1);
-                        const bool ok = d0 >= d0_from[kind] && d0 <= d0_to[kind] && d1_in >= 0 && d1_in < is1 &&
-                                        d1_out >= 0 && d1_out < is1 && d1 >= d1_from && d1 <= d1_to;
-                        d1c[kind] = dc; d1o[kind] = d1_out;
-                        if (ok) inc |= 1u << kind;
-                    }
-                    if (!inc) continue;
-                    int ido[6];
-#pragma unroll
-                    for (int kind = 0; kind < 6; kind++) {      // the out-pixel loads go out together
-                        const int a = kind & 1;
-                        const size_t mo = a == 0 ? (size_t)d1o[kind] * P.Ws + xx : (size_t)yy * P.Ws + d1o[kind];
-                        ido[kind] = (inc >> kind) & 1 ? __ldg(fim + mo) : -1;
-                    }
-#pragma unroll
-                    for (int kind = 0; kind < 6; kind++) {
-                        if (!((inc >> kind) & 1)) continue;
-                        const int e = kind >> 1, a = kind & 1;
-                        const float p00 = pc[e][a], p10 = pc[(e + 1) % 3][a];
-                        const int is1 = a == 0 ? P.Hs : P.Ws;
-                        const int d0 = a == 0 ? xx : yy, d1 = a == 0 ? yy : xx;
-                        const float d0f = (float)d0;
-                        const size_t mo = a == 0 ? (size_t)d1o[kind] * P.Ws + xx : (size_t)yy * P.Ws + d1o[kind];
-                        float da = ((1.0f - (ido[kind] >= 0 ? 1.0f : 0.0f)) * ga), dr = 0.0f;     // alpha here is 1
-                        if (P.use_rgb) {
-                            float co[3];
-                            colour_at(P, b, base_px + mo, ido[kind], bg, co);
-                            const float d = (csel[0] - co[0]) * g[0] + (csel[1] - co[1]) * g[1] + (csel[2] - co[2]) * g[2];
-                            if (one_pass) da += d; else dr = d;
-                        }
-                        const float pa = fmaxf(da, 0.0f), pr = fmaxf(dr, 0.0f);
-                        if (pa <= 0.0f && pr <= 0.0f) continue;
-                        const float t = (float)d1 - d1c[kind];
-                        const float dp = p10 - p00, k2 = 2.0f / (float)is1;
-                        const float x0 = dp * rcp_approx(p10 - d0f) * k2 * t, x1 = dp * rcp_approx(d0f - p00) * k2 * t;
-                        if (p10 != d0f) {
-                            const float a0 = (0.0f < x0) ? x0 + ea : x0 - ea, r0 = (0.0f < x0) ? x0 + er : x0 - er;
-                            acc[kind * 2] -= __fmaf_rn(pa, rcp_approx(a0), pr * rcp_approx(r0));
-                        }
-                        if (p00 != d0f) {
-                            const float a1 = (0.0f < x1) ? x1 + ea : x1 - ea, r1 = (0.0f < x1) ? x1 + er : x1 - er;
-                            acc[kind * 2 + 1] -= __fmaf_rn(pa, rcp_approx(a1), pr * rcp_approx(r1));
-                        }
-                    }
-                }
-            }
+        for (int u = 0; u < 4; u++) {           // four independent loads in flight
+            const int xx = xx0 + 8 * u + (lane & 7);
+            idv[u] = (yy <= C.bb.w && xx <= C.bb.z) ? __ldg(C.fim + (size_t)yy * P.Ws + xx) : -2;
         }
+#pragma unroll 1
+        for (int u = 0; u < 4; u++)
+            if (idv[u] == C.fn) face_sample(P, C, xx0 + 8 * u + (lane & 7), yy, need_depth, need_tex, need_k6, acc, S, G);
 #pragma unroll
         for (int k = 0; k < 3; k++) { S[k] = warp_sum(S[k]); G[k] = warp_sum(G[k]); }
 #pragma unroll
@@ -1589,6 +1659,7 @@ __device__ __forceinline__ void bwd_face_role(const BwdParams& P, const Workspac
             o[12] = S[0]; o[13] = S[1]; o[14] = S[2]; o[15] = G[0]; o[16] = G[1]; o[17] = G[2];
         }
     }
+
 }
 
 __global__ void __launch_bounds__(128) k_bwd_face(BwdParams P, Workspace ws) { bwd_face_role(P, ws); }
@@ -1603,6 +1674,7 @@ __global__ void __launch_bounds__(256) k_face_sums(Workspace ws) {
     if (vi >= nvis) return;
     float a = 0.0f;
     const int ue = unit_n[vi + 1] - unit_n[0];
+    if (ue == unit_n[vi] - unit_n[0]) return;           // small face: k_bwd_face wrote its sums directly
     for (int u = unit_n[vi] - unit_n[0]; u < ue; u++) a += ws.upart[(size_t)u * 18 + k];
     const size_t fo = (size_t)ws.vis_ids[vi];
     if (k < 12) ws.gpart[fo * 12 + k] = a;
