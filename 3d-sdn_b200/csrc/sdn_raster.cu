@@ -1968,6 +1968,122 @@ __global__ void __launch_bounds__(LW * 32, 2) k_bwd_main(BwdParams P, Workspace 
     line_role<MODE, 8, 32>(P, ws, (int)blockIdx.x - face_ctas);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Silhouette-only line sweep with a far-field expansion.  When only the alpha gradient exists (the reference's
+// training path, derender3d/models/__init__.py:203-208), the positive part of rasterize.py:628-631 is a per-pixel
+// weight w_j >= 0 that does NOT depend on the query, so a query's sum
+//        R = sum_{j=lo..hi} w_j / (k (j - xc) + e)
+// can be evaluated blockwise: for a block of 32 pixels centred at c whose distance from the crossing is >= 64 pixels,
+//        1 / (s + k d) = (1/s) sum_n (-k d / s)^n,   s = k (c - xc) + e,  d = j - c in [-15.5, 15.5]
+// so the block contributes (1/s) sum_n M_n x^n with x = -k/s and the block moments M_n = sum_j w_j d^n (n < 8).
+// |k d / s| <= 15.5/64, hence the truncation error of the nearest far block is <= 0.24^8/(1-0.24) = 1.5e-5 of its term
+// (smaller for all others); blocks nearer than 64 pixels, and the partially covered end blocks, are summed directly.
+// One warp per line: (1) weights of the whole line -> shared memory, (2) moments, one lane per block, (3) one lane per
+// query.  ~3-4x fewer instructions than the direct sweep; results are written once, deterministic.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FF_P = 8;             // terms of the expansion
+constexpr int FF_NEAR = 64;         // pixels: blocks whose centre is nearer than this to the crossing are summed directly
+constexpr int FF_LMAX = 4096;       // longest line the shared-memory layout supports
+
+__global__ void __launch_bounds__(LW * 32) k_line_sweep_ff(BwdParams P, Workspace ws, int lcap) {
+    extern __shared__ __align__(16) float s_ff[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wcap = lcap + lcap / 32 + 32;                 // skewed layout: pixel j lives at j + (j >> 5)
+    const int nbcap = lcap / 32 + 1;
+    float* s_w = s_ff + (size_t)warp * (wcap + FF_P * nbcap);
+    float* s_m = s_w + wcap;                                // moments [n][block]
+    const int per_img = P.Hs + P.Ws;
+    const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
+    const int bundles = bundles_rows + bundles_cols;
+    const int b = blockIdx.x / bundles, bi = blockIdx.x % bundles;
+    int axis, d0;
+    if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
+    else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
+    const int line = b * per_img + (axis == 0 ? P.Hs : 0) + d0;
+    if (bwd_overflow(ws)) return;
+    const int qbeg = ws.scan_buf[line], qend = ws.scan_buf[line + 1];
+    if (qbeg == qend) return;
+    const int L = axis == 0 ? P.Hs : P.Ws;
+    const int nb = (L + 31) / 32;
+    const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+    const float sc = (P.ss == 2) ? 0.25f : 1.0f;
+    const float ea = (float)P.eps_a;
+    const float* ga_p = P.g_alpha ? P.g_alpha + (size_t)b * P.H * P.W : nullptr;
+
+    // (1) weights of the line: w_j = max(0, (alpha_j - 1) * g_j) = background ? max(0, -g_j) : 0
+    for (int j0 = 0; j0 < nb * 32; j0 += 128) {
+        int idv[4];
+        float gv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = min(j0 + u * 32 + lane, L - 1);
+            const int xi = axis == 0 ? d0 : j, yi = axis == 0 ? j : d0;
+            idv[u] = __ldg(fim + (size_t)yi * P.Ws + xi);
+            gv[u] = ga_p ? __ldg(ga_p + (size_t)(P.H - 1 - yi / P.ss) * P.W + xi / P.ss) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = j0 + u * 32 + lane;
+            if (j < nb * 32) s_w[j + (j >> 5)] = (j < L && idv[u] < 0) ? fmaxf(-(gv[u] * sc), 0.0f) : 0.0f;
+        }
+    }
+    __syncwarp();
+    // (2) block moments, one lane per block (the skew makes the 32 lanes hit 32 different banks)
+    for (int blk = lane; blk < nb; blk += 32) {
+        float m[FF_P];
+#pragma unroll
+        for (int n = 0; n < FF_P; n++) m[n] = 0.0f;
+        const float* wp = s_w + blk * 33;
+#pragma unroll 4
+        for (int i = 0; i < 32; i++) {
+            const float w = wp[i], d = (float)i - 15.5f;
+            float t = w;
+#pragma unroll
+            for (int n = 0; n < FF_P; n++) { m[n] += t; t *= d; }
+        }
+#pragma unroll
+        for (int n = 0; n < FF_P; n++) s_m[n * nbcap + blk] = m[n];
+    }
+    __syncwarp();
+    // (3) one lane per query
+    for (int qk = qbeg + lane; qk < qend; qk += 32) {
+        const int qi = ws.line_items[qk];
+        const Query q = ws.queries[qi];
+        const int lo = q.lo, hi = q.hi_flags & 0xffff;
+        float res[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            if (!(q.hi_flags & (v == 0 ? QF_USE0 : QF_USE1))) continue;
+            const float k = v == 0 ? q.k0 : q.k1;
+            const float e = (q.hi_flags & (v == 0 ? QF_POS0 : QF_POS1)) ? ea : -ea;
+            float sum = 0.0f;
+            for (int blk = lo >> 5; blk <= (hi >> 5); blk++) {
+                const int j0 = blk * 32, j1 = j0 + 31;
+                const float c = (float)j0 + 15.5f;
+                const bool whole = lo <= j0 && hi >= j1;
+                if (whole && fabsf(c - q.xc) >= (float)FF_NEAR) {
+                    const float s = __fmaf_rn(k, c - q.xc, e);
+                    const float r = rcp_approx(s), x = -k * r;
+                    float a = s_m[(FF_P - 1) * nbcap + blk];
+#pragma unroll
+                    for (int n = FF_P - 2; n >= 0; n--) a = __fmaf_rn(a, x, s_m[n * nbcap + blk]);
+                    sum = __fmaf_rn(a, r, sum);
+                } else {
+                    const int a0 = max(lo, j0), a1 = min(hi, j1);
+                    const float* wp = s_w + blk * 33 - j0;
+                    for (int j = a0; j <= a1; j++) {
+                        const float w = wp[j];
+                        if (w != 0.0f) sum = __fmaf_rn(w, rcp_approx(__fmaf_rn(k, (float)j - q.xc, e)), sum);
+                    }
+                }
+            }
+            res[v] = -sum;              // g -= diff / dist   (rasterize.py:648,653)
+        }
+        ws.qres[qi] = make_float2(res[0], res[1]);
+    }
+}
+
+
 // adds the deferred out-sweep results of every (edge, axis) item onto its in-sweep partial, in step order
 __global__ void __launch_bounds__(256) k_item_sums(Workspace ws) {
     if (bwd_overflow(ws)) return;
@@ -2277,7 +2393,18 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
             else if (lmode == LM_SPLIT) SDN_LAUNCH_MAIN(LM_SPLIT);
             else SDN_LAUNCH_MAIN(LM_SINGLE);
         } else {
-            if (lmode == LM_ALPHA) SDN_LINE_VARIANTS(LM_ALPHA);
+            // fast_math == 2 asks for the far-field variant of the silhouette-only sweep.  Measured: 10 % faster than the
+            // direct sweep on ShapeNet-sized meshes at 384x384, 10 % slower on config 2b -- so it is opt-in.
+            const int lmax = max(P.Hs, P.Ws);
+            if (lmode == LM_ALPHA && g->fast_math == 2 && lmax <= FF_LMAX) {
+                // silhouette only: far-field line sweep (block moments); shared memory sized for the longest line
+                const int lcap = (lmax + 31) / 32 * 32;
+                const size_t fsmem = sizeof(float) * LW * ((size_t)lcap + lcap / 32 + 32 + (size_t)FF_P * (lcap / 32 + 1));
+                cudaFuncSetAttribute(k_line_sweep_ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+                timing_begin("k_line_sweep_ff", st);
+                k_line_sweep_ff<<<lgrid, LW * 32, fsmem, st>>>(P, ws, lcap);
+            }
+            else if (lmode == LM_ALPHA) SDN_LINE_VARIANTS(LM_ALPHA);
             else if (lmode == LM_SPLIT) SDN_LINE_VARIANTS(LM_SPLIT);
             else SDN_LINE_VARIANTS(LM_SINGLE);
         }

@@ -200,7 +200,8 @@ class RasterConfig(object):
         self.return_rgb, self.return_alpha, self.return_depth = bool(return_rgb), bool(return_alpha), bool(return_depth)
         self.batch_bug = bool(batch_bug)
         self.split_eps = split_eps      # (eps_alpha, eps_rgb): three-Rasterize semantics of the derender3d bridge
-        self.fast_math = DEFAULT_FAST_MATH if fast_math is None else bool(fast_math)
+        fm = DEFAULT_FAST_MATH if fast_math is None else fast_math
+        self.fast_math = int(fm) if not isinstance(fm, bool) else int(fm)     # 0 exact, 1 fast, 2 fast + far field
 
     @property
     def flags(self):

@@ -86,7 +86,8 @@ typedef struct sdn_raster_grad {
     float* grad_faces;          /* [B,F,3,3] OUT (fully written) */
     float* grad_textures;       /* same shape as textures, OUT (fully written) or NULL */
     int fast_math;              /* 0: IEEE divisions in the op order of rasterize.py:646-653;
-                                   1: reciprocal-multiply distance math (<= 1e-6 relative, not bit-faithful) */
+                                   1: reciprocal-multiply distance math (<= 1e-6 relative, not bit-faithful)
+                                   2: as 1, plus the far-field (block-moment) sweep when only alpha is rendered */
 } sdn_raster_grad;
 
 int sdn_version(void);

@@ -199,8 +199,12 @@ def test_full_size_properties_config2(dev):
     assert torch.isfinite(vg.grad).all() and float(vg.grad.abs().sum()) > 0
 
 
-def test_full_size_single_image_against_oracle(dev, oracle):
-    """One 375x1242 image end to end against the oracle (a few seconds of host time)."""
+@pytest.mark.parametrize('fast', [0, 1, 2])
+def test_full_size_single_image_against_oracle(dev, oracle, fast, monkeypatch):
+    """One 375x1242 image end to end against the oracle (a few seconds of host time).  fast=1 is the packed direct line
+    sweep, fast=2 the silhouette-only far-field sweep (block moments) on full-length rows and columns."""
+    import sdn_b200
+    monkeypatch.setattr(sdn_b200, 'DEFAULT_FAST_MATH', fast)
     from sdn_b200 import workloads as wl
     from derender3d.models.renderer import Renderer, RenderType
     verts, faces = wl.vkitti_scene_batch(1, seed=9, z_range=(7.0, 9.0))
@@ -385,3 +389,45 @@ def test_analysis_by_synthesis_reduces_silhouette_error(dev):
         sdn_b200.DEFAULT_FAST_MATH = old
     assert float(hist[-1]) < 0.6 * float(hist[0]), hist.tolist()
     assert refined['_masks'].shape == target.shape
+
+
+def test_pathological_faces_match_oracle(dev, oracle):
+    """Edge cases the reference's kernels meet in the wild: faces far outside the frustum (|NDC| > 64: no bbox
+    culling), faces crossing the camera plane (negative / tiny z), NaN and infinite vertices, zero-area faces,
+    faces clipped by near / far.  Face-index map bit-exact, nothing crashes, gradients finite where the oracle's are."""
+    import sdn_b200
+    rng = np.random.RandomState(3)
+    B, F, H, W = 1, 64, 40, 56
+    faces = random_faces(rng, B, F, size=0.5)
+    faces[0, 0] *= np.array([300.0, 300.0, 1.0], np.float32)          # huge coordinates
+    faces[0, 1, :, 2] = np.array([-0.5, 1.0, 1.0], np.float32)         # one vertex behind the camera
+    faces[0, 2, :, 2] = 1e-3                                           # nearer than near
+    faces[0, 3, :, 2] = 500.0                                          # beyond far
+    faces[0, 4, 1, 0] = np.nan
+    faces[0, 5, 2, 1] = np.inf
+    faces[0, 6, 1] = faces[0, 6, 0]                                    # zero area (two coincident vertices)
+    faces[0, 7] = faces[0, 7, 0]                                       # a point
+    faces[0, 8, :, :2] = np.array([[-3, -3], [3, -3], [0, 3]], np.float32)   # covers the whole frame
+    st = oracle.raster_forward(faces, None, H, W, 0.1, 100, 1e-4, None, False, True, True)
+    cfg = sdn_b200.RasterConfig((H, W), False, return_alpha=True, return_depth=True)
+    f = torch.tensor(faces, device=dev, requires_grad=True)
+    _, alpha, depth = sdn_b200.RasterizeFunction.apply(f, None, cfg)
+    assert np.array_equal(cfg.last_face_index.cpu().numpy(), st.face_index_map)
+    assert (st.face_index_map >= 0).mean() > 0.5
+    g_a = torch.randn(alpha.shape, generator=torch.Generator().manual_seed(0))
+    (alpha * g_a.to(dev)).sum().backward()
+    gf, _ = oracle.raster_backward(st, None, g_a.flip(1).numpy().copy(), np.zeros((B, H, W), np.float32))
+    fin = np.isfinite(gf).all(axis=(2, 3))[0]                          # faces whose oracle gradient is finite
+    got = f.grad.cpu().numpy()[0]
+    assert np.isfinite(got[fin]).all()
+    assert rel_l2(torch.tensor(got[fin]), torch.tensor(gf[0][fin])) <= TOL
+
+
+def test_batch_of_one_tiny_raster_and_single_face(dev, oracle):
+    import sdn_b200
+    faces = np.array([[[[-0.9, -0.8, 1.0], [0.8, -0.7, 2.0], [0.1, 0.9, 1.5]]]], np.float32)
+    for (H, W, ss) in ((1, 1, 1), (2, 3, 2), (5, 1, 1)):
+        st = oracle.raster_forward(faces, None, H * ss, W * ss, return_alpha=True)
+        cfg = sdn_b200.RasterConfig((H, W), ss == 2, return_alpha=True)
+        sdn_b200.RasterizeFunction.apply(torch.tensor(faces, device=dev), None, cfg)
+        assert np.array_equal(cfg.last_face_index.cpu().numpy(), st.face_index_map), (H, W, ss)
