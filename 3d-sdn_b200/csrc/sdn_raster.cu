@@ -2431,6 +2431,12 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
 
 }  // namespace
 
+// launch accounting shared with the other translation units of this library (sdn_linear_tc.cu); not part of the ABI
+namespace sdn_internal {
+void launch_begin(const char* name, cudaStream_t st) { timing_begin(name, st); }
+int launch_end() { return check_launch(); }
+}  // namespace sdn_internal
+
 // ------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------

@@ -1,6 +1,8 @@
 """Image encoder of the geometric branch (reference: derender3d/models/derenderer.py:7-65): ResNet-18 trunk + three
 fully connected layers + head split.  Attribute names (net, relu, fc1, fc2, _fc3) match the reference so that its
-checkpoints load unchanged.  The convolutions are library GEMMs (cuDNN through torchvision): DESIGN.md "Encoder"."""
+checkpoints load unchanged.  The convolutions are library GEMMs (cuDNN through torchvision); the four fully
+connected layers run on the hand-written tcgen05 kernel (sdn_b200.linear_tc: bf16 operands, fp32 accumulate in TMEM)
+when the module is on a GPU and `tensor_core_head` is set (default; SDN_TC_HEAD=0 turns it off): DESIGN.md "Encoder"."""
 import os
 
 import torch
@@ -36,13 +38,29 @@ class Derenderer(Module):
         self.fc1 = torch.nn.Linear(self.hidden_size + self.in_size, self.hidden_size)
         self.fc2 = torch.nn.Linear(self.hidden_size, self.hidden_size)
         self._fc3 = torch.nn.Linear(self.hidden_size, sum(self.out_sizes.values()))
+        self.tensor_core_head = os.environ.get('SDN_TC_HEAD', '1') != '0'
+
+    def _trunk(self, images):
+        """torchvision ResNet._forward_impl without its last Linear."""
+        n = self.net
+        x = n.maxpool(n.relu(n.bn1(n.conv1(images))))
+        x = n.layer4(n.layer3(n.layer2(n.layer1(x))))
+        return torch.flatten(n.avgpool(x), 1)
 
     def forward(self, images, mroi_norms, droi_norms):
-        x = self.relu(self.net(images))
-        x = torch.cat([x.float(), mroi_norms, droi_norms], dim=1)
-        x = self.relu(self.fc1(x))
-        x = self.relu(self.fc2(x))
-        x = self._fc3(x)
+        if self.tensor_core_head and images.is_cuda:
+            from sdn_b200 import linear_tc
+            x = linear_tc(self._trunk(images), self.net.fc.weight, self.net.fc.bias, relu=True)
+            x = torch.cat([x, mroi_norms.float(), droi_norms.float()], dim=1)
+            x = linear_tc(x, self.fc1.weight, self.fc1.bias, relu=True)
+            x = linear_tc(x, self.fc2.weight, self.fc2.bias, relu=True)
+            x = linear_tc(x, self._fc3.weight, self._fc3.bias, relu=False)
+        else:
+            x = self.relu(self.net(images))
+            x = torch.cat([x.float(), mroi_norms, droi_norms], dim=1)
+            x = self.relu(self.fc1(x))
+            x = self.relu(self.fc2(x))
+            x = self._fc3(x)
         (theta, t2d, log_scales, log_depths, class_logits, ffd) = torch.split(x, list(self.out_sizes.values()), dim=1)
         return {
             '_theta_deltas': theta / torch.norm(theta, p=2, dim=1, keepdim=True),

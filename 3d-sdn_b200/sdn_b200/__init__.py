@@ -67,6 +67,7 @@ def lib():
         L.sdn_faces_backward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(_Camera), vp, vp,
                                          ctypes.c_size_t, vp]
         L.sdn_rasterize_forward.argtypes = [ctypes.POINTER(_Raster), vp]
+        L.sdn_linear_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
         L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
         L.sdn_rasterize_backward_split.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad),
                                                    ctypes.c_double, ctypes.c_double, vp]
@@ -301,3 +302,43 @@ def rasterize_faces(faces, textures, cfg):
     rgb, alpha, depth = RasterizeFunction.apply(faces, textures, cfg)
     return {'rgb': rgb if cfg.return_rgb else None, 'alpha': alpha if cfg.return_alpha else None,
             'depth': depth if cfg.return_depth else None}
+
+
+class LinearTCFunction(torch.autograd.Function):
+    """y = act(x . weight^T + bias) with the contraction on the tcgen05 tensor cores (csrc/sdn_linear_tc.cu: bf16
+    operands, fp32 accumulation in TMEM).  Stands where the reference's encoder head calls torch.nn.Linear
+    (derender3d/models/derenderer.py:26-32,35-43).  The backward is the plain fp32 matmul pair on cuBLAS."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        _need_cuda(x, weight)
+        x2 = _f32c(x.reshape(-1, x.shape[-1]))
+        w = _f32c(weight)
+        b = _f32c(bias) if bias is not None else None
+        M, K = x2.shape
+        N = w.shape[0]
+        if w.shape[1] != K:
+            raise SdnError('linear_tc: weight is [%d,%d], input has %d features' % (N, w.shape[1], K))
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        if M > 0:
+            _check(lib().sdn_linear_forward(_ptr(x2), _ptr(w), _ptr(b) if b is not None else None, _ptr(y),
+                                            M, N, K, 1 if relu else 0, _stream()))
+        ctx.save_for_backward(x2, w, y if relu else None)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = x.shape
+        return y.reshape(x.shape[:-1] + (N,))
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w, y = ctx.saved_tensors
+        g = gy.reshape(-1, gy.shape[-1]).float()
+        if y is not None:
+            g = g * (y > 0).to(g.dtype)
+        gx = (g @ w).reshape(ctx.in_shape) if ctx.needs_input_grad[0] else None
+        gw = g.t() @ x2 if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None
+
+
+def linear_tc(x, weight, bias=None, relu=False):
+    return LinearTCFunction.apply(x, weight, bias, relu)

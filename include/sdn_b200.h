@@ -131,6 +131,14 @@ int sdn_rasterize_backward_split(const sdn_raster* r, const sdn_raster_grad* g, 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long sdn_launch_count(void);
 
+/* ---- encoder fully-connected layer on the tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM) ----------
+ * y[M,N] = act(x[M,K] . weight[N,K]^T + bias[N]); all fp32 device pointers, row-major, rows 16-byte aligned when
+ * K % 4 == 0 (any K is accepted).  bias may be NULL; relu != 0 applies max(.,0).  Replaces the torch.nn.Linear calls
+ * of the encoder head: derender3d/models/derenderer.py:26-32 (net.fc, fc1, fc2, _fc3) and :35-43 (their use).
+ * Operands are rounded to bf16 (8-bit mantissa): |err| <= ~2^-8 * sum|x_k w_k|; the test states the tolerance. */
+int sdn_linear_forward(const float* x, const float* weight, const float* bias, float* y, int M, int N, int K,
+                       int relu, void* stream);
+
 /* Diagnostics: when enabled, every kernel launch is bracketed by CUDA events on the launching stream;
  * sdn_timing_read() drains them as "kernel_name total_ms launches\n" lines (returns bytes written).  Off by default. */
 int sdn_timing_enable(int on);
