@@ -3,8 +3,11 @@
 
 Same constructor, forward(images, roi_norms, focals) and render(blob) contract, same dictionary keys.  The reference
 renders objects one at a time in a Python loop with >= 7 host round trips each; here the objects of
-a batch are grouped by sampled mesh class and each group is deformed, transformed and rendered in one batched call
-(<= 8 native render calls per step, tensors never leave the GPU, one host sync for the class ids)."""
+a batch are deformed and moved to camera space by ONE native launch over the ragged batch (sdn_objects_forward, the
+mesh class is an index into a device-resident bank of templates) and rendered by ONE rasterisation; tensors never
+leave the GPU and nothing syncs with the host, so the whole step can be captured in a CUDA graph.  On the CPU (host
+tests) and with `fused_front_end = False` the objects are grouped by class and each group goes through the torch
+FFD / PerspectiveTransform modules (<= 8 render calls, one host sync for the class ids)."""
 import os
 
 import numpy as np
@@ -64,6 +67,8 @@ class Derenderer3d(Module):
             self.perspective_transform = PerspectiveTransform()
             self.renderer = Renderer(image_size=render_size)
             self._faces_dev = {}
+            self._banks = {}
+            self.fused_front_end = os.environ.get('SDN_FUSED_FRONT_END', '1') != '0'
 
     def forward(self, images, roi_norms, focals):
         _mroi_norms = torch.stack([roi_norms[:, 2] + roi_norms[:, 0], roi_norms[:, 3] + roi_norms[:, 1]], dim=1) / 2.0
@@ -137,7 +142,62 @@ class Derenderer3d(Module):
                                                       zoom_tos=p['_zoom_tos'][sel], **kw)
                 yield k, sel, verts, z
 
+    def _bank(self, dev):
+        """Device-resident template bank + the FFD's constant tensors (built once per device)."""
+        key = str(dev)
+        if key not in self._banks:
+            import sdn_b200
+            bank = sdn_b200.MeshBank([f.B for f in self.ffds], [o.faces for o in self.objs], dev)
+            f0 = self.ffds[0]
+            sig = lambda f: [(c.type, c.axis, getattr(c, 'index', None)) for c in f.constraints]  # noqa: E731
+            assert all(sig(f) == sig(f0) and f.num_grids == 4 for f in self.ffds), 'templates share one FFD lattice'
+            bank.C = f0.constraint_matrix().to(dev)
+            bank.P0 = f0.P0.reshape(1, -1).to(dev)
+            self._banks[key] = bank
+        return self._banks[key]
+
+    def render_fused(self, blob):
+        """render() with the per-object loop (reference :161-224) replaced by one ragged launch + one rasterisation."""
+        import sdn_b200
+        p = self.pose(blob)
+        _focals = blob['_focals']
+        bs, dev = len(_focals), _focals.device
+        bank = self._bank(dev)
+        classes = p['_class_samples']
+        with torch.autocast('cuda', enabled=False):
+            dP = blob['_ffd_coeffs'][torch.arange(bs, device=dev), classes].float()     # [bs,192]
+            control = (bank.P0 + dP @ bank.C).reshape(bs, 3, 64)
+            kw = dict(scales=p['_scales'].float(), rotations=p['_rotations'].float(),
+                      translations=p['_translations'].float())
+            if self.training:
+                verts = sdn_b200.object_vertices(bank, classes, control, ptrans=p['_perspective_translations'].float(),
+                                                 zooms=p['_zooms'].float(), **kw)
+                _zooms = p['_zooms']
+            else:
+                verts, _zooms = sdn_b200.object_vertices(bank, classes, control, ptrans=kw['translations'],
+                                                         zoom_tos=p['_zoom_tos'].float(), **kw)
+        faces = bank.faces.index_select(0, classes)                                      # [bs,nf_max,3]
+        want_normal = bool(self.mode & TargetType.normal)
+        want_depth = bool(self.mode & TargetType.depth)
+        self.renderer.viewing_angle = torch.atan(self.render_size / (2.0 * _focals.double().reshape(-1))) / np.pi * 180
+        if want_normal or want_depth:
+            out = self.renderer.forward_multi(verts, faces, silhouette=True, depth=want_depth, normal=want_normal)
+            _masks = out['silhouette']
+            _normals = out['normal'] if want_normal else []
+            _depth_maps = out['depth'] if want_depth else []
+        else:
+            _masks = self.renderer(vertices=verts, faces=faces, render_type=RenderType.Silhouette)
+            _normals, _depth_maps = [], []
+        return {
+            '_thetas': p['_thetas'], '_alphas': p['_alphas'], '_rotations': p['_rotations'], '_scales': p['_scales'],
+            '_depths': p['_depths'], '_center2ds': p['_center2ds'], '_translations': p['_translations'],
+            '_class_log_probs': p['_class_log_probs'], '_zooms': _zooms, '_masks': _masks, '_normals': _normals,
+            '_depth_maps': _depth_maps,
+        }
+
     def render(self, blob):
+        if self.fused_front_end and blob['_focals'].is_cuda:
+            return self.render_fused(blob)
         p = self.pose(blob)
         _focals, _ffd_coeffs = blob['_focals'], blob['_ffd_coeffs']
         bs, dev = len(_focals), _focals.device

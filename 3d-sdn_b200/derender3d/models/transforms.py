@@ -79,13 +79,22 @@ class FFD(Module):
                 dP = torch.stack(slices, dim=dim)
         return dP
 
+    def constraint_matrix(self):
+        """The constraint step is linear in the coefficients: constrain(x) == x @ C for this [3n^3, 3n^3] matrix
+        (entries are 0, +-1/2, +-1/4: products exact, only the order of a 2-4 term sum differs)."""
+        m = 3 * self.num_grids ** 3
+        eye = torch.eye(m, dtype=torch.float32)
+        n = self.num_grids
+        return self.constrain(eye.reshape(m, 3, n, n, n)).reshape(m, m)
+
     def forward(self, ffd_coeff):
         """ffd_coeff [3*n^3] -> [nv,3]   or   [N,3*n^3] -> [N,nv,3]."""
         n = self.num_grids
         single = ffd_coeff.dim() == 1
-        dP = ffd_coeff.reshape(-1, 3, n, n, n)
-        P = (self.P0.to(dP.device) + self.constrain(dP)).reshape(-1, 3, n * n * n)        # [N,3,64]
-        V = torch.matmul(self.B.to(dP.device).reshape(-1, n * n * n), P.transpose(1, 2))  # [N,nv,3]
+        with torch.autocast(ffd_coeff.device.type, enabled=False):     # vertex positions stay float32 under autocast
+            dP = ffd_coeff.float().reshape(-1, 3, n, n, n)
+            P = (self.P0.to(dP.device) + self.constrain(dP)).reshape(-1, 3, n * n * n)        # [N,3,64]
+            V = torch.matmul(self.B.to(dP.device).reshape(-1, n * n * n), P.transpose(1, 2))  # [N,nv,3]
         return V[0] if single else V
 
 

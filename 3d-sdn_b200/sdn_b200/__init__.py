@@ -46,6 +46,15 @@ class _RasterGrad(ctypes.Structure):
                 ('grad_faces', ctypes.c_void_p), ('grad_textures', ctypes.c_void_p), ('fast_math', ctypes.c_int)]
 
 
+class _Objects(ctypes.Structure):
+    _fields_ = [('N', ctypes.c_int), ('K', ctypes.c_int), ('nv_max', ctypes.c_int), ('derive_zoom', ctypes.c_int),
+                ('basis', ctypes.c_void_p), ('basis_off', ctypes.c_void_p), ('nv', ctypes.c_void_p),
+                ('classes', ctypes.c_void_p), ('control', ctypes.c_void_p), ('scales', ctypes.c_void_p),
+                ('rotations', ctypes.c_void_p), ('translations', ctypes.c_void_p), ('ptrans', ctypes.c_void_p),
+                ('zooms', ctypes.c_void_p), ('zoom_tos', ctypes.c_void_p), ('zoom_key', ctypes.c_void_p),
+                ('vertices', ctypes.c_void_p)]
+
+
 def lib():
     """Load libsdn_b200.so (built by __graft_entry__.build() / csrc/build.py).  Fails loudly when absent."""
     global _lib
@@ -68,6 +77,8 @@ def lib():
                                          ctypes.c_size_t, vp]
         L.sdn_rasterize_forward.argtypes = [ctypes.POINTER(_Raster), vp]
         L.sdn_linear_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+        L.sdn_objects_forward.argtypes = [ctypes.POINTER(_Objects), vp]
+        L.sdn_objects_backward.argtypes = [ctypes.POINTER(_Objects), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
         L.sdn_rasterize_backward_split.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad),
                                                    ctypes.c_double, ctypes.c_double, vp]
@@ -342,3 +353,86 @@ class LinearTCFunction(torch.autograd.Function):
 
 def linear_tc(x, weight, bias=None, relu=False):
     return LinearTCFunction.apply(x, weight, bias, relu)
+
+
+class MeshBank(object):
+    """The template meshes of a Derenderer3d on one device: Bernstein tables concatenated [sum nv, 64], face tables
+    padded to [K, nf_max, 3] with (0,0,0) triangles (three coincident corners: zero area, never drawn, no gradient).
+    Built once; reference re-uploads B per object per call (derender3d/models/transforms.py:97)."""
+
+    def __init__(self, bases, faces, device):
+        self.K = len(bases)
+        nv = [int(b.shape[0]) for b in bases]
+        self.nv_list, self.nf_list = nv, [int(f.shape[0]) for f in faces]
+        self.nv_max, self.nf_max = max(nv), max(self.nf_list)
+        self.basis = torch.cat([b.reshape(b.shape[0], 64).float() for b in bases]).contiguous().to(device)
+        off = [0]
+        for n in nv[:-1]:
+            off.append(off[-1] + n)
+        self.basis_off = torch.tensor(off, dtype=torch.int64, device=device)
+        self.nv = torch.tensor(nv, dtype=torch.int32, device=device)
+        fp = torch.zeros(self.K, self.nf_max, 3, dtype=torch.int32)
+        for k, f in enumerate(faces):
+            fp[k, :f.shape[0]] = f.to(torch.int32)
+        self.faces = fp.to(device)
+        self.device = torch.device(device)
+
+
+class ObjectVerticesFunction(torch.autograd.Function):
+    """(classes [N] int64, control [N,3,64], scales [N,3], rotations [N,4], translations [N,3], ptrans [N,3],
+    zoom [N,1]) -> camera-space vertices [N,nv_max,3] (+ zooms [N,1] in test mode, where `zoom` holds zoom_tos).
+    One launch for the batch; see include/sdn_b200.h `sdn_objects`."""
+
+    @staticmethod
+    def forward(ctx, bank, classes, control, scales, rotations, translations, ptrans, zoom, derive):
+        _need_cuda(classes, control, scales, rotations, translations, ptrans, zoom)
+        N = int(classes.shape[0])
+        dev = control.device
+        cl = classes.detach().to(torch.int64).contiguous()
+        t = [_f32c(x) for x in (control.reshape(N, 3, 64), scales, rotations, translations, ptrans, zoom.reshape(N))]
+        verts = torch.empty(N, bank.nv_max, 3, device=dev)
+        zooms = torch.empty(N, device=dev) if derive else t[5]
+        key = torch.empty(N, dtype=torch.int64, device=dev) if derive else None
+        o = _Objects(N, bank.K, bank.nv_max, 1 if derive else 0, bank.basis.data_ptr(), bank.basis_off.data_ptr(),
+                     bank.nv.data_ptr(), cl.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                     t[3].data_ptr(), t[4].data_ptr(), zooms.data_ptr(), t[5].data_ptr() if derive else None,
+                     key.data_ptr() if derive else None, verts.data_ptr())
+        with torch.cuda.device(dev):
+            _check(lib().sdn_objects_forward(ctypes.byref(o), _stream()))
+        ctx.bank, ctx.derive, ctx.keep = bank, derive, (cl, t, zooms, key)
+        ctx.zoom_shape = zoom.shape
+        out_z = zooms.reshape(N, 1)
+        ctx.mark_non_differentiable(out_z)
+        return verts, out_z
+
+    @staticmethod
+    def backward(ctx, gv, _gz):
+        bank, derive = ctx.bank, ctx.derive
+        cl, t, zooms, key = ctx.keep
+        N = int(cl.shape[0])
+        dev = gv.device
+        gv = _f32c(gv)
+        g_control = torch.empty(N, 3, 64, device=dev)
+        g_s, g_r, g_t, g_p = (torch.empty(N, k, device=dev) for k in (3, 4, 3, 3))
+        g_z = torch.empty(N, device=dev)
+        scratch = torch.empty(N * 24, device=dev)
+        verts_dummy = gv                     # `vertices` is not read by the backward
+        o = _Objects(N, bank.K, bank.nv_max, 1 if derive else 0, bank.basis.data_ptr(), bank.basis_off.data_ptr(),
+                     bank.nv.data_ptr(), cl.data_ptr(), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                     t[3].data_ptr(), t[4].data_ptr(), zooms.data_ptr(), t[5].data_ptr() if derive else None,
+                     key.data_ptr() if derive else None, verts_dummy.data_ptr())
+        with torch.cuda.device(dev):
+            _check(lib().sdn_objects_backward(ctypes.byref(o), _ptr(gv), _ptr(g_control), _ptr(g_s), _ptr(g_r),
+                                              _ptr(g_t), _ptr(g_p), _ptr(g_z), _ptr(scratch), scratch.numel() * 4,
+                                              _stream()))
+        return None, None, g_control, g_s, g_r, g_t, g_p, g_z.reshape(ctx.zoom_shape), None
+
+
+def object_vertices(bank, classes, control, scales, rotations, translations, ptrans, zooms=None, zoom_tos=None):
+    """Training mode: pass zooms [N,1] -> vertices.  Test mode: pass zoom_tos [N,1] -> (vertices, zooms [N,1])."""
+    if (zooms is None) == (zoom_tos is None):
+        raise SdnError('object_vertices: give exactly one of zooms / zoom_tos')
+    if zoom_tos is None:
+        return ObjectVerticesFunction.apply(bank, classes, control, scales, rotations, translations, ptrans, zooms,
+                                            False)[0]
+    return ObjectVerticesFunction.apply(bank, classes, control, scales, rotations, translations, ptrans, zoom_tos, True)

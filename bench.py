@@ -178,12 +178,56 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # host-side dispatch cost of one eager step (python + autograd + ctypes), reported next to the device time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step_resident()
+    host_ms = (time.perf_counter() - t0) / 20 * 1e3
+    torch.cuda.synchronize()
+    launches0 = sdn_b200.launch_count()
+    step_resident()
+    launches_per_step = sdn_b200.launch_count() - launches0
+
+    # the whole step (forward + backward of all three outputs) as ONE CUDA graph: shapes, launch grids and the
+    # workspace are static, nothing in the library reads back to the host
+    graph, timed_step = None, step_resident
+    if args.graph:
+        try:
+            step_resident_keep = lambda: torch.autograd.backward(      # noqa: E731 -- eager result to check against
+                list(renderer.forward_multi(v_dev, f_dev, fast_math=fast)[k] for k in ('silhouette', 'depth', 'normal')),
+                [g_dev['silhouette'], g_dev['depth'], g_dev['normal']])
+            v_dev.grad = None
+            step_resident_keep()
+            gref = v_dev.grad.clone()
+            v_dev.grad = None
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_resident()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = renderer.forward_multi(v_dev, f_dev, fast_math=fast)
+                torch.autograd.backward([out['silhouette'], out['depth'], out['normal']],
+                                        [g_dev['silhouette'], g_dev['depth'], g_dev['normal']])
+            graph.replay()
+            torch.cuda.synchronize()
+            err = float((gref - v_dev.grad).norm() / gref.norm())
+            assert err < 1e-5, 'graph replay differs from the eager step: rel-L2 %g' % err
+            timed_step = graph.replay
+        except Exception as e:      # noqa: BLE001 -- report and time the eager step instead
+            print('[bench] CUDA graph capture failed (%s); timing the eager step' % repr(e)[:300], file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+        for _ in range(3):
+            timed_step()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = sdn_b200.launch_count()
-    ms = timed(step_resident, args.steps)
-    launches = sdn_b200.launch_count() - launches0
+    ms = timed(timed_step, args.steps)
+    launches = launches_per_step * args.steps
     sampler.stop_flag = True
+    v_dev.grad = None
 
     for _ in range(3):
         step_e2e()
@@ -218,6 +262,7 @@ def run_ours(args):
                                '(3968 with fill_back), VKITTI camera f=725, silhouette+depth+normal, N(0,1) grads'
                                % B,
                    'batch_per_gpu': B, 'math': 'fast' if fast else 'exact',
+                   'launch': 'cuda graph replay' if graph is not None else 'eager', 'host_dispatch_ms_per_step': round(host_ms, 3),
                    'l2': 'inputs+outputs per step (%.0f MB) exceed the 126 MB L2' % (
                        B * sum(algorithmic_bytes()) / 1e6),
                    'sharding': 'by image, no data-path collective'},
@@ -361,6 +406,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--exact', action='store_true', help='IEEE-division distance math in the backward (default: fast)')
+    ap.add_argument('--no-graph', dest='graph', action='store_false', help='time the eager step, not its CUDA graph')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -128,6 +128,41 @@ int sdn_rasterize_backward(const sdn_raster* r, const sdn_raster_grad* g, void* 
 int sdn_rasterize_backward_split(const sdn_raster* r, const sdn_raster_grad* g, double eps_alpha, double eps_rgb,
                                  void* stream);
 
+/* ---- pre-raster stage: free-form deformation + camera-space transform of a ragged batch of objects --------------
+ * Replaces, for all N objects of a batch at once, the body of the per-object loop of Derenderer3d.render
+ * (derender3d/models/__init__.py:161-200): FFD.forward (derender3d/models/transforms.py:68-99, the sum
+ * V = sum (P0+dP) * B) and PerspectiveTransform.forward (transforms.py:102-158).  Object i deforms template mesh
+ * classes[i]; the templates' Bernstein tables B (transforms.py:57-64) are concatenated in `basis`.  The linear
+ * constraint step (transforms.py:71-95) stays with the caller: `control` is P0 + constrained dP.
+ * All pointers are device pointers; nothing is allocated. */
+typedef struct sdn_objects {
+    int N;                          /* objects in the batch */
+    int K;                          /* template meshes in the bank */
+    int nv_max;                     /* vertex stride of the output (>= every nv[k]) */
+    int derive_zoom;                /* 0: training mode, zooms given (transforms.py:151); 1: test mode, zoom_i =
+                                       min_v |z|/max(|x|,|y|) * zoom_tos[i] (transforms.py:148-149), written to zooms */
+    const float* basis;             /* [sum_k nv[k], 64] Bernstein weights, row = vertex, 64 = 4x4x4 lattice (i,j,k) */
+    const long long* basis_off;     /* [K] first row of template k in basis */
+    const int* nv;                  /* [K] vertex count of template k */
+    const long long* classes;       /* [N] template id of object i (int64, as torch.max / Categorical.sample give) */
+    const float* control;           /* [N,3,64] control points P0 + dP */
+    const float* scales;            /* [N,3] */
+    const float* rotations;         /* [N,4] quaternion (a,b,c,d), transforms.py:110-124 */
+    const float* translations;      /* [N,3] */
+    const float* ptrans;            /* [N,3] perspective_translations (principal ray), transforms.py:133-143 */
+    float* zooms;                   /* [N] read when derive_zoom == 0, written when 1 */
+    const float* zoom_tos;          /* [N] derive_zoom == 1 only */
+    unsigned long long* zoom_key;   /* [N] scratch kept between forward and backward when derive_zoom == 1 */
+    float* vertices;                /* out [N,nv_max,3]; rows >= nv[classes[i]] are (0,0,1) */
+} sdn_objects;
+
+int sdn_objects_forward(const sdn_objects* o, void* stream);
+/* gradients of everything differentiable; grad_zoom is d/d zooms (derive_zoom 0) or d/d zoom_tos (1).
+ * scratch: >= 96 * N bytes.  `o` must describe the forward's buffers (zooms / zoom_key as the forward left them). */
+int sdn_objects_backward(const sdn_objects* o, const float* grad_vertices, float* grad_control, float* grad_scales,
+                         float* grad_rotations, float* grad_translations, float* grad_ptrans, float* grad_zoom,
+                         float* scratch, size_t scratch_bytes, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long sdn_launch_count(void);
 

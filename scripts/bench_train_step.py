@@ -27,6 +27,7 @@ def main():
     ap.add_argument('--faces', type=int, default=72576, help='triangles per template mesh (ShapeNet: 29k-72k)')
     ap.add_argument('--fp32', action='store_true')
     ap.add_argument('--encoder-only', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='torch.profiler table of one step (kernel time vs wall)')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     torch.manual_seed(0)
@@ -98,6 +99,24 @@ def main():
     torch.cuda.synchronize()
     kern = {k: round(t[0] / 3, 3) for k, t in sorted(sdn_b200.timing_read().items(), key=lambda kv: -kv[1][0])[:6]}
     sdn_b200.timing_enable(False)
+    if args.profile:
+        from torch.profiler import profile, ProfilerActivity
+        import time
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            step()
+        host_ms = (time.perf_counter() - t0) / 5 * 1e3
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        ev = prof.key_averages()
+        tot = sum(e.self_device_time_total for e in ev) / 3e3
+        print('host dispatch ms/step (no sync): %.2f   device kernel ms/step: %.2f   wall ms/step: %.2f' % (host_ms, tot, ms))
+        print(ev.table(sort_by='self_cuda_time_total', row_limit=30, max_name_column_width=60))
+        print(ev.table(sort_by='self_cpu_time_total', row_limit=25, max_name_column_width=60))
     nparam = sum(p.numel() for p in model.parameters())
     print(json.dumps({'workload': 'config3: B=%d, encoder 224x224 %s, %d-triangle templates, render %dx%d, mode full, Adam'
                       % (B, 'fp32' if args.fp32 else 'bf16 autocast channels-last', len(objs[0].faces), S, S),
