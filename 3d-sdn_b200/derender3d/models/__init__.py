@@ -107,7 +107,7 @@ class Derenderer3d(Module):
         _alphas = -(_thetas - torch.atan(_translations[:, 0:1] / _translations[:, 2:3]))
         _alphas = torch.remainder(_alphas + np.pi, 2 * np.pi) - np.pi
         if self.training and not self._force_no_sample:
-            dist = Categorical(_class_probs)
+            dist = Categorical(_class_probs, validate_args=False)       # the simplex check would sync with the host
             _class_samples = dist.sample()
             _class_log_probs = dist.log_prob(_class_samples)
         else:

@@ -19,15 +19,20 @@ def pad_like(image, like, mode='constant', value=0):
     return F.pad(image, (p3 // 2, p3 // 2, p2 // 2, p2 // 2), mode=mode)
 
 
-def _partial(f, mask):
-    """main.py:97-112: apply f on the selected rows only; 0 when none is selected."""
-    def g(*args, **kw):
-        index = torch.nonzero(mask)
-        if index.numel():
-            index = index.squeeze(dim=1)
-            return f(*[a[index] for a in args], **kw)
-        return torch.zeros((), device=mask.device)
-    return g
+def _masked_mse(a, b, mask):
+    """main.py:97-112 `partial(F.mse_loss, mask)`: mean squared error over the selected rows, 0 when none is selected --
+    written without torch.nonzero so that nothing syncs with the host (the step can then be captured in a CUDA graph)."""
+    w = (mask != 0).to(a.dtype)
+    num = (((a - b) ** 2).reshape(a.shape[0], -1).sum(dim=1) * w).sum()
+    den = w.sum() * (a.numel() // max(a.shape[0], 1))
+    return torch.where(den > 0, num / den.clamp_min(1.0), torch.zeros((), device=a.device, dtype=a.dtype))
+
+
+def _masked_mean(x, mask):
+    """`partial(torch.mean, mask)` of a [B] vector."""
+    w = (mask != 0).to(x.dtype)
+    den = w.sum()
+    return torch.where(den > 0, (x * w).sum() / den.clamp_min(1.0), torch.zeros((), device=x.device, dtype=x.dtype))
 
 
 def geometric_losses(blob, batch, mode, mask_weight=MASK_WEIGHT, ffd_coeff_reg=FFD_COEFF_REG):
@@ -36,7 +41,8 @@ def geometric_losses(blob, batch, mode, mask_weight=MASK_WEIGHT, ffd_coeff_reg=F
     losses = {}
     targets = batch['targets']
     if mode & TargetType.geometry:
-        mse = _partial(F.mse_loss, targets & TargetType.pretrain)
+        pre = targets & TargetType.pretrain
+        mse = lambda a, b: _masked_mse(a, b, pre)      # noqa: E731
         theta_deltas = torch.cat([torch.cos(batch['thetas']), torch.sin(batch['thetas'])], dim=1)
         losses['theta_delta_loss'] = mse(blob['_theta_deltas'], theta_deltas)
         losses['translation2d_loss'] = mse(blob['_translation2ds'], batch['translation2ds'])
@@ -44,7 +50,7 @@ def geometric_losses(blob, batch, mode, mask_weight=MASK_WEIGHT, ffd_coeff_reg=F
         losses['depth_loss'] = mse(blob['_log_depths'], batch['log_depths'])
     if mode & TargetType.reproject:
         sel = targets & TargetType.finetune
-        mean = _partial(torch.mean, sel)
+        mean = lambda x: _masked_mean(x, sel)          # noqa: E731
         masks = pad_like(batch['masks'], blob['_masks'])
         ignores = pad_like(batch['ignores'], blob['_masks'], mode='replicate')
         mask_losses = (1 - ignores) * F.mse_loss(blob['_masks'], masks, reduction='none')
@@ -66,3 +72,46 @@ def train_step(model, optimizer, batch, mode, grad_sync=None):
         grad_sync(model)
     optimizer.step()
     return loss.detach(), losses, blob
+
+
+class GraphedTrainStep(object):
+    """The whole optimisation step -- encoder, pose algebra, class sampling, fused pre-raster stage, rasterisation,
+    losses, backward, Adam -- captured ONCE as a CUDA graph and replayed per batch (one launch per step instead of
+    ~1500).  Possible because nothing on the path syncs with the host: the mesh class is a device-side index
+    (sdn_objects), the losses use masks instead of torch.nonzero, shapes and the workspace are static.
+
+    `optimizer` must be built with capturable=True (Adam keeps its step counter on the device).  Inputs are copied
+    into static buffers; outputs (`loss`, `losses`, `blob`) are static tensors overwritten by each replay."""
+
+    def __init__(self, model, optimizer, example_batch, mode, warmup=3, autocast_dtype=None):
+        self.model, self.optimizer, self.mode = model, optimizer, mode
+        self.batch = {k: v.clone() for k, v in example_batch.items()}
+        self.autocast_dtype = autocast_dtype
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):         # lazy initialisation (mesh bank, camera cache, cuDNN plans, Adam state)
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.losses, self.blob = self._eager(zero=False)
+
+    def _eager(self, zero=True):
+        with torch.autocast('cuda', dtype=self.autocast_dtype or torch.bfloat16, enabled=self.autocast_dtype is not None):
+            blob = self.model(self.batch['images'], self.batch['roi_norms'], self.batch['focals'])
+            losses = geometric_losses(blob, self.batch, self.mode)
+            loss = sum(losses.values())
+        if zero:
+            self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach(), losses, blob
+
+    def step(self, batch=None):
+        if batch is not None:
+            for k, v in batch.items():
+                self.batch[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss

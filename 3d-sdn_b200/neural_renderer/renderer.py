@@ -66,49 +66,56 @@ class Renderer(object):
         eye_h = self._host(self.eye) if look else None
         up_h = self._host([0, 1, 0] if self.up is None else self.up) if look else None
         dir_h = self._host(self.camera_direction) if self.camera_mode == 'look' else None
-        cacheable = (not multi_angle) and (not look or (eye_h is not None and up_h is not None and
-                                                        (self.camera_mode != 'look' or dir_h is not None)))
-        key = None
-        if cacheable:
-            sig = lambda t: None if t is None else (tuple(t.shape), tuple(t.reshape(-1).tolist()))
-            key = (self.camera_mode, bool(self.perspective), float(angle), H, W, bs, str(dev), float(self.flip_x),
-                   sig(eye_h), sig(up_h), sig(dir_h))
-            hit = Renderer._camera_cache.get(key)
-            if hit is not None:
-                return hit
-        ref = vertices.new_zeros(1) if not cacheable else torch.zeros(1)      # where the glue runs
+        host_look = (not look) or (eye_h is not None and up_h is not None and
+                                   (self.camera_mode != 'look' or dir_h is not None))
+        sig = lambda t: None if t is None else (tuple(t.shape), tuple(t.reshape(-1).tolist()))    # noqa: E731
+        # (1) view rotation + eye: constants when they live on the host -> evaluated there once, device copy cached
         rot = eye = None
         if look:
-            eye = _ops.as_tensor(self.eye if eye_h is None else eye_h, ref)
-            up = _ops.as_tensor(([0, 1, 0] if self.up is None else self.up) if up_h is None else up_h, ref)
-            eye, up = (t.unsqueeze(0) if t.dim() == 1 else t for t in (eye, up))
-            if self.camera_mode == 'look_at':
-                z_dir = _ops.as_tensor([0, 0, 0], ref).unsqueeze(0) - eye
+            lkey = ('look', self.camera_mode, bs, str(dev), sig(eye_h), sig(up_h), sig(dir_h)) if host_look else None
+            hit = Renderer._camera_cache.get(lkey) if lkey is not None else None
+            if hit is not None:
+                rot, eye = hit
             else:
-                z_dir = _ops.as_tensor(self.camera_direction if dir_h is None else dir_h, ref)
-                z_dir = z_dir.unsqueeze(0) if z_dir.dim() == 1 else z_dir
-            n = max(eye.shape[0], up.shape[0], z_dir.shape[0])
-            rot = _ops.camera_rotation(z_dir.expand(n, 3), up.expand(n, 3)).expand(bs, 3, 3).contiguous().to(dev)
-            eye = eye.expand(bs, 3).contiguous().to(dev)
+                ref = torch.zeros(1) if host_look else vertices.new_zeros(1)      # where the glue runs
+                eye = _ops.as_tensor(self.eye if eye_h is None else eye_h, ref)
+                up = _ops.as_tensor(([0, 1, 0] if self.up is None else self.up) if up_h is None else up_h, ref)
+                eye, up = (t.unsqueeze(0) if t.dim() == 1 else t for t in (eye, up))
+                if self.camera_mode == 'look_at':
+                    z_dir = _ops.as_tensor([0, 0, 0], ref).unsqueeze(0) - eye
+                else:
+                    z_dir = _ops.as_tensor(self.camera_direction if dir_h is None else dir_h, ref)
+                    z_dir = z_dir.unsqueeze(0) if z_dir.dim() == 1 else z_dir
+                n = max(eye.shape[0], up.shape[0], z_dir.shape[0])
+                rot = _ops.camera_rotation(z_dir.expand(n, 3), up.expand(n, 3)).expand(bs, 3, 3).contiguous().to(dev)
+                eye = eye.expand(bs, 3).contiguous().to(dev)
+                if lkey is not None:
+                    Renderer._cache_put(lkey, (rot, eye))
+        # (2) perspective half-widths: per-image angles stay on the device (no host sync)
         wx = wy = None
         if self.perspective:
             if multi_angle:
-                # per-image angles stay on the device (no host sync): the float32 steps of perspective.py:10-13
+                # the float32 steps of perspective.py:10-13
                 a = angle.detach().to(device=dev, dtype=torch.float32).reshape(-1)
                 a = (a / 180.0) * 3.1416
                 wy = torch.tan(a.double()).float()
                 wx = wy if H == W else wy * float(np.float32(W / H))
             else:
-                wy_np = np.asarray([perspective_width(float(angle))] * bs, np.float32)
-                wx_np = wy_np if H == W else (wy_np * np.float32(W / H)).astype(np.float32)
-                wy = torch.from_numpy(wy_np).to(dev)
-                wx = torch.from_numpy(wx_np).to(dev)
-        cam = sdn_b200.Camera(rot, eye, wx, wy, self.flip_x)
-        if key is not None:
-            if len(Renderer._camera_cache) > 64:
-                Renderer._camera_cache.clear()
-            Renderer._camera_cache[key] = cam
-        return cam
+                pkey = ('persp', float(angle), H, W, bs, str(dev))
+                hit = Renderer._camera_cache.get(pkey)
+                if hit is None:
+                    wy_np = np.asarray([perspective_width(float(angle))] * bs, np.float32)
+                    wx_np = wy_np if H == W else (wy_np * np.float32(W / H)).astype(np.float32)
+                    hit = (torch.from_numpy(wx_np).to(dev), torch.from_numpy(wy_np).to(dev))
+                    Renderer._cache_put(pkey, hit)
+                wx, wy = hit
+        return sdn_b200.Camera(rot, eye, wx, wy, self.flip_x)
+
+    @staticmethod
+    def _cache_put(key, value):
+        if len(Renderer._camera_cache) > 64:
+            Renderer._camera_cache.clear()
+        Renderer._camera_cache[key] = value
 
     def _faces(self, vertices, faces, want_normals=False):
         return sdn_b200.FacesFunction.apply(vertices, faces, self._camera(vertices), self.fill_back, want_normals)

@@ -16,7 +16,7 @@ import sdn_b200  # noqa: E402
 from sdn_b200 import workloads as wl  # noqa: E402
 from derender3d import TargetType  # noqa: E402
 from derender3d.models import Derenderer3d, ShapenetObj  # noqa: E402
-from derender3d.train_step import geometric_losses  # noqa: E402
+from derender3d.train_step import geometric_losses, GraphedTrainStep  # noqa: E402
 
 
 def main():
@@ -27,6 +27,7 @@ def main():
     ap.add_argument('--faces', type=int, default=72576, help='triangles per template mesh (ShapeNet: 29k-72k)')
     ap.add_argument('--fp32', action='store_true')
     ap.add_argument('--encoder-only', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='capture the whole step in a CUDA graph (GraphedTrainStep)')
     ap.add_argument('--profile', action='store_true', help='torch.profiler table of one step (kernel time vs wall)')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -47,7 +48,7 @@ def main():
         model.derenderer._fc3.bias[0] = 1.0                      # theta
         model.derenderer._fc3.bias[4:7] = torch.tensor([1.3, 0.4, 0.5])   # log scales
         model.derenderer._fc3.bias[7] = 2.2                      # log depth
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3, capturable=bool(args.graph))
     g = torch.Generator().manual_seed(0)
     c = 0.3 * (torch.rand(B, 2, generator=g) - 0.5)
     d = 0.25 + 0.15 * torch.rand(B, 2, generator=g)
@@ -79,6 +80,13 @@ def main():
         loss.backward()
         opt.step()
         return loss, cov
+
+    if args.graph:
+        assert not args.encoder_only
+        gs = GraphedTrainStep(model, opt, batch, TargetType.full, autocast_dtype=torch.bfloat16 if amp else None)
+
+        def step():     # noqa: F811
+            return gs.step(), gs.blob['_masks']
 
     loss, cov = step()
     coverage = float((cov > 0).float().mean()) if not args.encoder_only else 0.0
@@ -120,7 +128,7 @@ def main():
     nparam = sum(p.numel() for p in model.parameters())
     print(json.dumps({'workload': 'config3: B=%d, encoder 224x224 %s, %d-triangle templates, render %dx%d, mode full, Adam'
                       % (B, 'fp32' if args.fp32 else 'bf16 autocast channels-last', len(objs[0].faces), S, S),
-                      'encoder_only': args.encoder_only, 'ms_per_step': round(ms, 3),
+                      'encoder_only': args.encoder_only, 'cuda_graph': bool(args.graph), 'ms_per_step': round(ms, 3),
                       'objects_per_s': round(B / ms * 1e3, 1), 'loss': float(loss), 'mask_coverage': round(coverage, 3),
                       'parameters': nparam, 'render_kernels_ms': kern}))
 

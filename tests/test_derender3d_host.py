@@ -116,3 +116,29 @@ def test_object_vertices_match_reference_on_real_meshes(mode):
                 assert torch.allclose(z[j], _t(g['test_zooms'][i]), rtol=1e-5)
             seen += 1
     assert seen == len(classes)
+
+
+def test_sync_free_losses_equal_the_nonzero_formulation():
+    """main.py:97-112 selects rows with torch.nonzero (a host sync); train_step uses masks.  Same values, including
+    the 'nothing selected -> 0' branch."""
+    import torch.nn.functional as F
+    from derender3d import TargetType
+    from derender3d.train_step import _masked_mse, _masked_mean
+
+    def partial(f, mask):
+        def g(*args, **kw):
+            index = torch.nonzero(mask)
+            if index.numel():
+                index = index.squeeze(dim=1)
+                return f(*[a[index] for a in args], **kw)
+            return torch.zeros(())
+        return g
+
+    g = torch.Generator().manual_seed(0)
+    for targets in (torch.tensor([3, 1, 2, 0, 3, 2]), torch.zeros(6, dtype=torch.long), torch.full((6,), 3)):
+        for bit in (TargetType.pretrain, TargetType.finetune):
+            mask = targets & bit
+            a, b = torch.randn(6, 3, generator=g), torch.randn(6, 3, generator=g)
+            x = torch.randn(6, generator=g)
+            assert torch.allclose(_masked_mse(a, b, mask), partial(F.mse_loss, mask)(a, b), atol=1e-6)
+            assert torch.allclose(_masked_mean(x, mask), partial(torch.mean, mask)(x), atol=1e-6)

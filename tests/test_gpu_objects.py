@@ -181,3 +181,54 @@ def test_derenderer3d_fused_front_end_equals_class_grouped_path(dev, training):
         assert _rel(a[0][k].float(), b[0][k].float()) <= 2e-3, k      # a 1e-7 vertex difference may move a pixel
     assert float((a[0]['_masks'] > 0).float().mean()) > 0.02
     assert _rel(a[1], b[1]) <= 2e-2
+
+
+def test_whole_train_step_as_cuda_graph_matches_eager(dev):
+    """GraphedTrainStep: encoder -> pose -> fused front end -> render -> losses -> backward -> Adam in ONE graph launch;
+    same trajectory as the eager step (float atomics reorder sums: 1e-3 on the loss after 6 steps)."""
+    import copy
+    from derender3d import TargetType
+    from derender3d.models import Derenderer3d, ShapenetObj
+    from derender3d.train_step import GraphedTrainStep, train_step
+    from sdn_b200 import workloads as wl
+    objs = []
+    for k in range(8):
+        v, f = wl.superellipsoid_mesh(12 + 2 * k, 8 + k, 0.5 + 0.05 * k, 0.6)
+        objs.append(ShapenetObj(vertices=v * np.array([1.0, 0.35, 0.45], np.float32), faces=f))
+    torch.manual_seed(0)
+    B, S = 6, 64
+    model_a = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=objs).to(dev).train()
+    with torch.no_grad():
+        model_a.derenderer._fc3.weight.mul_(0.01)
+        model_a.derenderer._fc3.bias.zero_()
+        model_a.derenderer._fc3.bias[0] = 1.0
+        model_a.derenderer._fc3.bias[4:7] = torch.tensor([1.3, 0.4, 0.5])
+        model_a.derenderer._fc3.bias[7] = 2.2
+    model_a._force_no_sample = True
+    model_b = copy.deepcopy(model_a)
+    g = torch.Generator().manual_seed(1)
+    c = 0.3 * (torch.rand(B, 2, generator=g) - 0.5)
+    d = 0.25 + 0.15 * torch.rand(B, 2, generator=g)
+    batch = {'images': torch.randn(B, 3, 224, 224, generator=g).to(dev),
+             'roi_norms': torch.cat([c - d / 2, c + d / 2], dim=1).to(dev),
+             'focals': torch.full((B, 1), 725.0, device=dev),
+             'targets': torch.tensor([3, 3, 1, 2, 3, 3], device=dev),
+             'thetas': torch.rand(B, 1, generator=g).to(dev), 'translation2ds': torch.zeros(B, 2, device=dev),
+             'log_scales': torch.tensor([1.3, 0.4, 0.5], device=dev).expand(B, 3).contiguous(),
+             'log_depths': torch.full((B, 1), 2.2, device=dev),
+             'masks': (torch.rand(B, 1, 40, 40, generator=g) > 0.5).float().to(dev),
+             'ignores': torch.zeros(B, 1, 40, 40, device=dev)}
+    opt_a = torch.optim.Adam(model_a.parameters(), lr=1e-4, weight_decay=1e-3, capturable=True)
+    opt_b = torch.optim.Adam(model_b.parameters(), lr=1e-4, weight_decay=1e-3, capturable=True)
+    for _ in range(6):
+        loss_a, _, blob_a = train_step(model_a, opt_a, batch, TargetType.full)
+    gs = GraphedTrainStep(model_b, opt_b, batch, TargetType.full, warmup=3)
+    for _ in range(3):
+        loss_b = gs.step(batch)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss_b)
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-3 * abs(float(loss_a))
+    assert float((gs.blob['_masks'] > 0).float().mean()) > 0.01
+    assert _rel(gs.blob['_masks'].float(), blob_a['_masks'].float()) <= 5e-2
+    wa, wb = model_a.derenderer._fc3.weight, model_b.derenderer._fc3.weight
+    assert _rel(wb, wa) <= 1e-3
