@@ -15,33 +15,53 @@ def shard_range(n, rank, world):
 
 
 class FlatGradSync(object):
-    """All-reduce (mean) of all gradients through one flat bucket: a single collective launch per step."""
+    """All-reduce (mean) of all gradients through one flat bucket: a single collective launch per step.
 
-    def __init__(self, model, group=None):
+    bucket_views=True makes every `p.grad` a VIEW of the flat buffer (autograd accumulates into an existing .grad in
+    place), so the step is: `zero()` (one memset) -> backward -> `__call__()` (one all-reduce + one scale, no copies).
+    Keep the views alive: clear gradients with `zero()` / `optimizer.zero_grad(set_to_none=False)`, never set_to_none.
+    Everything here is capturable in a CUDA graph (NCCL collectives included)."""
+
+    def __init__(self, model, group=None, bucket_views=False):
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.group = group
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.numel = n
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.bucket_views = bool(bucket_views)
+        if self.bucket_views:
+            self.attach()
+
+    def attach(self):
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def zero(self):
+        self.flat.zero_()
+
+    def _attached(self):
+        return all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(self.params, self.views))
 
     def __call__(self, model=None):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat[off:off + n].zero_()
-            else:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+        in_place = self.bucket_views and self._attached()
+        if not in_place:
+            have = [(v, p.grad) for p, v in zip(self.params, self.views) if p.grad is not None]
+            for p, v in zip(self.params, self.views):
+                if p.grad is None:
+                    v.zero_()
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         if world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.div_(world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                p.grad = torch.empty_like(p)
-            p.grad.copy_(self.flat[off:off + n].view_as(p))
-            off += n
+        if not in_place:
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+            torch._foreach_copy_([p.grad for p in self.params], self.views)

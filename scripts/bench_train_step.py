@@ -30,7 +30,14 @@ def main():
     ap.add_argument('--graph', action='store_true', help='capture the whole step in a CUDA graph (GraphedTrainStep)')
     ap.add_argument('--profile', action='store_true', help='torch.profiler table of one step (kernel time vs wall)')
     args = ap.parse_args()
-    dev = torch.device('cuda:0')
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:       # BASELINE config 4: one process per GPU, one flat-bucket all-reduce per step
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)
     n_lon = 192
     n_lat = max(4, args.faces // (2 * n_lon) + 1)
@@ -49,7 +56,11 @@ def main():
         model.derenderer._fc3.bias[4:7] = torch.tensor([1.3, 0.4, 0.5])   # log scales
         model.derenderer._fc3.bias[7] = 2.2                      # log depth
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3, capturable=bool(args.graph))
-    g = torch.Generator().manual_seed(0)
+    sync = None
+    if world > 1:
+        from sdn_b200.dist import FlatGradSync
+        sync = FlatGradSync(model, bucket_views=True)
+    g = torch.Generator().manual_seed(rank)
     c = 0.3 * (torch.rand(B, 2, generator=g) - 0.5)
     d = 0.25 + 0.15 * torch.rand(B, 2, generator=g)
     roi = torch.cat([c - d / 2, c + d / 2], dim=1).to(dev)
@@ -76,14 +87,20 @@ def main():
                 blob = model(batch['images'], batch['roi_norms'], batch['focals'])
                 loss = sum(geometric_losses(blob, batch, TargetType.full).values())
                 cov = blob['_masks']
-        opt.zero_grad(set_to_none=True)
+        if sync is not None:
+            sync.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         loss.backward()
+        if sync is not None:
+            sync()
         opt.step()
         return loss, cov
 
     if args.graph:
         assert not args.encoder_only
-        gs = GraphedTrainStep(model, opt, batch, TargetType.full, autocast_dtype=torch.bfloat16 if amp else None)
+        gs = GraphedTrainStep(model, opt, batch, TargetType.full, autocast_dtype=torch.bfloat16 if amp else None,
+                              grad_sync=sync)
 
         def step():     # noqa: F811
             return gs.step(), gs.blob['_masks']
@@ -92,7 +109,12 @@ def main():
     coverage = float((cov > 0).float().mean()) if not args.encoder_only else 0.0
     for _ in range(3):
         step()
-    torch.cuda.synchronize()
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -100,6 +122,11 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:       # max over ranks
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier()
     sdn_b200.timing_enable(True)
     sdn_b200.timing_read()
     for _ in range(3):
@@ -126,9 +153,18 @@ def main():
         print(ev.table(sort_by='self_cuda_time_total', row_limit=30, max_name_column_width=60))
         print(ev.table(sort_by='self_cpu_time_total', row_limit=25, max_name_column_width=60))
     nparam = sum(p.numel() for p in model.parameters())
-    print(json.dumps({'workload': 'config3: B=%d, encoder 224x224 %s, %d-triangle templates, render %dx%d, mode full, Adam'
+    if world > 1:
+        w0 = model.derenderer._fc3.weight.detach().clone()
+        dist.broadcast(w0, src=0)
+        assert torch.equal(w0, model.derenderer._fc3.weight.detach()), 'replicas diverged'
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    B = B * world
+    print(json.dumps({'workload': ('config4' if world > 1 else 'config3') + ': B=%d, encoder 224x224 %s, %d-triangle templates, render %dx%d, mode full, Adam'
                       % (B, 'fp32' if args.fp32 else 'bf16 autocast channels-last', len(objs[0].faces), S, S),
-                      'encoder_only': args.encoder_only, 'cuda_graph': bool(args.graph), 'ms_per_step': round(ms, 3),
+                      'encoder_only': args.encoder_only, 'cuda_graph': bool(args.graph), 'n_gpus': world, 'global_batch': B, 'ms_per_step': round(ms, 3),
                       'objects_per_s': round(B / ms * 1e3, 1), 'loss': float(loss), 'mask_coverage': round(coverage, 3),
                       'parameters': nparam, 'render_kernels_ms': kern}))
 

@@ -3,6 +3,7 @@ all-reduce that replaces DataParallel."""
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -16,7 +17,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, bucket_views=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,7 +28,18 @@ def _worker(rank, world, port, out):
     model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
     data = torch.randn(10, 6, generator=torch.Generator().manual_seed(1))
     lo, hi = shard_range(10, rank, world)
-    sync = FlatGradSync(model)
+    sync = FlatGradSync(model, bucket_views=bucket_views)
+    if bucket_views:
+        for _ in range(2):          # a second round checks that zero() really clears the shared bucket
+            sync.zero()
+            model(data[lo:hi]).pow(2).mean().backward()
+            sync()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(sync.params, sync.views))
+        flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        assert torch.equal(flat, sync.flat)
+        out[rank] = (lo, hi, flat.clone(), sync.numel)
+        dist.destroy_process_group()
+        return
     # per-rank loss is the MEAN over its shard; equal shard sizes -> mean of means == global mean
     model(data[lo:hi]).pow(2).mean().backward()
     sync()
@@ -36,11 +48,12 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_shard_and_flat_allreduce_two_ranks():
+@pytest.mark.parametrize('bucket_views', [False, True], ids=['copy', 'bucket_views'])
+def test_shard_and_flat_allreduce_two_ranks(bucket_views):
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, bucket_views), nprocs=world, join=True)
     assert (out[0][0], out[0][1], out[1][0], out[1][1]) == (0, 5, 5, 10)
     assert torch.equal(out[0][2], out[1][2])                         # identical gradients on every rank
     torch.manual_seed(0)
