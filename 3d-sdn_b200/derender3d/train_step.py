@@ -81,13 +81,12 @@ class GraphedTrainStep(object):
     (sdn_objects), the losses use masks instead of torch.nonzero, shapes and the workspace are static.
 
     `optimizer` must be built with capturable=True (Adam keeps its step counter on the device).  Inputs are copied
-    into static buffers; outputs (`loss`, `losses`, `blob`) are static tensors overwritten by each replay."""
+    into static buffers; outputs (`loss`, `losses`, `blob`) are static tensors overwritten by each replay.
+    Single-process only for now: with a gradient all-reduce (sdn_b200.dist.FlatGradSync) use the eager `train_step`
+    (measured at 2 GPUs: 96 % weak-scaling efficiency); a graphed multi-GPU step is not validated yet."""
 
-    def __init__(self, model, optimizer, example_batch, mode, warmup=3, autocast_dtype=None, grad_sync=None):
-        """grad_sync: a sdn_b200.dist.FlatGradSync built with bucket_views=True.  The step is then two graphs with the
-        one collective issued eagerly between them: [zero, forward, losses, backward] -> all-reduce -> [Adam]."""
+    def __init__(self, model, optimizer, example_batch, mode, warmup=3, autocast_dtype=None):
         self.model, self.optimizer, self.mode = model, optimizer, mode
-        self.grad_sync = grad_sync
         self.batch = {k: v.clone() for k, v in example_batch.items()}
         self.autocast_dtype = autocast_dtype
         side = torch.cuda.Stream()
@@ -96,34 +95,19 @@ class GraphedTrainStep(object):
             for _ in range(warmup):         # lazy initialisation (mesh bank, camera cache, cuDNN plans, Adam state)
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
-        if grad_sync is None:
-            optimizer.zero_grad(set_to_none=True)
+        optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
-        self.graph_opt = None
-        if grad_sync is None:
-            with torch.cuda.graph(self.graph):
-                self.loss, self.losses, self.blob = self._eager(zero=False)
-        else:
-            with torch.cuda.graph(self.graph):
-                self.loss, self.losses, self.blob = self._eager(zero=False, upto='backward')
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
-                self.optimizer.step()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.losses, self.blob = self._eager(zero=False)
 
-    def _eager(self, zero=True, upto='step'):
+    def _eager(self, zero=True):
         with torch.autocast('cuda', dtype=self.autocast_dtype or torch.bfloat16, enabled=self.autocast_dtype is not None):
             blob = self.model(self.batch['images'], self.batch['roi_norms'], self.batch['focals'])
             losses = geometric_losses(blob, self.batch, self.mode)
             loss = sum(losses.values())
-        if self.grad_sync is not None:
-            self.grad_sync.zero()               # gradients are views of the flat bucket: one memset, also in the graph
-        elif zero:
+        if zero:
             self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
-        if upto == 'backward':
-            return loss.detach(), losses, blob
-        if self.grad_sync is not None:
-            self.grad_sync()
         self.optimizer.step()
         return loss.detach(), losses, blob
 
@@ -132,7 +116,4 @@ class GraphedTrainStep(object):
             for k, v in batch.items():
                 self.batch[k].copy_(v, non_blocking=True)
         self.graph.replay()
-        if self.graph_opt is not None:
-            self.grad_sync()
-            self.graph_opt.replay()
         return self.loss

@@ -99,8 +99,8 @@ def main():
 
     if args.graph:
         assert not args.encoder_only
-        gs = GraphedTrainStep(model, opt, batch, TargetType.full, autocast_dtype=torch.bfloat16 if amp else None,
-                              grad_sync=sync)
+        assert world == 1, 'the graphed step is single-process for now (see GraphedTrainStep)'
+        gs = GraphedTrainStep(model, opt, batch, TargetType.full, autocast_dtype=torch.bfloat16 if amp else None)
 
         def step():     # noqa: F811
             return gs.step(), gs.blob['_masks']
