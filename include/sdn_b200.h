@@ -163,6 +163,30 @@ int sdn_objects_backward(const sdn_objects* o, const float* grad_vertices, float
                          float* grad_rotations, float* grad_translations, float* grad_ptrans, float* grad_zoom,
                          float* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- test-time scene compositor ------------------------------------------------------------------------------
+ * Replaces the per-object loop of geometric/scripts/main.py:547-606 (to_pil_image -> resize -> PIL paste -> to_tensor
+ * on the CPU, far to near) for the M drawn objects of one frame.  Bit-identical to Pillow's bilinear resize; the
+ * caller supplies Pillow's coefficient tables (Resample.c precompute_coeffs; oracle/compositor.py `pil_coeffs`).
+ * objs[] is sorted far to near.  All pointers are device pointers. */
+typedef struct sdn_composite_obj {
+    int index;              /* row of masks / normals / depth_maps / zooms this object reads */
+    int size;               /* on-screen edge: int(render_size / zoom), main.py:556 */
+    int box_x, box_y;       /* paste position of the top-left corner (may be negative), main.py:562-565 */
+    int ksize;              /* taps per output sample in the coefficient tables */
+    int id;                 /* value written to the instance map: object index + 1, main.py:570 */
+    long long row_off;      /* first row of this object in `bounds` */
+    long long k_off;        /* first element of this object in kk8 / kkd ([size][ksize]) */
+    long long tmp_off;      /* first pixel of this object's [S][size] intermediate in tmp8 / tmpf */
+} sdn_composite_obj;
+
+/* masks [N,S,S], normals [N,3,S,S] or NULL (then normal must be NULL), depth_maps [N,S,S], zooms [N];
+ * bounds [sum size][2] (first tap, count), kk8 / kkd [sum size*ksize]; tmp8: 4 bytes per intermediate pixel, tmpf:
+ * one float; max_size = max objs[].size.  Out: instance [H,W], normal [3,H,W], depth [H,W] (backgrounds 0, 0.5, 1). */
+int sdn_composite_scene(const sdn_composite_obj* objs, int M, const float* masks, const float* normals,
+                        const float* depth_maps, const float* zooms, int S, const int* bounds, const int* kk8,
+                        const double* kkd, void* tmp8, float* tmpf, int max_size, int H, int W, float* instance,
+                        float* normal, float* depth, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long sdn_launch_count(void);
 

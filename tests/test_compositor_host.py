@@ -1,0 +1,50 @@
+"""Pins the third-party arithmetic of the test-time compositor (geometric/scripts/main.py:547-606 -> torchvision ->
+Pillow's bilinear resize): the numpy restatement in oracle/compositor.py equals Pillow bit for bit (uint8 and 'F')."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+@pytest.mark.parametrize('S,out', [(64, 23), (64, 64), (64, 100), (96, 17), (50, 49), (48, 7), (32, 200), (384, 131)])
+def test_numpy_restatement_equals_pillow(S, out):
+    from PIL import Image
+    from oracle.compositor import pil_resize_f32, pil_resize_u8
+    rng = np.random.default_rng(S * 1000 + out)
+    a = rng.integers(0, 256, (S, S), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(a).resize((out, out), Image.BILINEAR))
+    assert np.array_equal(ref, pil_resize_u8(a, out))
+    f = rng.random((S, S), dtype=np.float32)
+    reff = np.asarray(Image.fromarray(f).resize((out, out), Image.BILINEAR))
+    assert np.array_equal(reff, pil_resize_f32(f, out))
+
+
+@pytest.mark.parametrize('S,out', [(64, 23), (64, 64), (64, 100), (384, 131), (48, 7), (384, 1)])
+def test_vectorised_tables_equal_the_loop_restatement(S, out):
+    sys.path.insert(0, os.path.join(ROOT, '3d-sdn_b200'))
+    from derender3d.compositor import resample_tables
+    from oracle.compositor import pil_coeffs
+    b0, kd0, k80 = pil_coeffs(S, out)
+    b1, kd1, k81 = resample_tables(S, out)
+    assert np.array_equal(b0, b1) and np.array_equal(kd0, kd1) and np.array_equal(k80, k81)
+
+
+def test_scene_files_round_trip(tmp_path):
+    import torch
+    from PIL import Image
+    sys.path.insert(0, os.path.join(ROOT, '3d-sdn_b200'))
+    from derender3d.compositor import save_scene, scene_json
+    inst = torch.zeros(1, 12, 20); inst[0, 2:5, 3:9] = 3
+    nrm = torch.full((3, 12, 20), 0.5); dep = torch.full((1, 12, 20), 1.0); dep[0, 2:5, 3:9] = 0.25
+    js = scene_json([2], [7, 7, 5], [9.0, 8.0, 7.5], [0.1, 0.2, 0.3])
+    save_scene(str(tmp_path), '00001', inst, nrm, dep, js)
+    assert np.asarray(Image.open(tmp_path / '00001.png')).max() == 3
+    assert np.asarray(Image.open(tmp_path / '00001-normal.png')).shape == (12, 20, 3)
+    d = np.asarray(Image.open(tmp_path / '00001-depth.png'))
+    assert d.dtype in (np.uint16, np.int32) and int(d[3, 4]) == int(0.25 * 65535) and int(d[0, 0]) == 65535
+    import json
+    assert json.load(open(tmp_path / '00001.json'))['3'] == {'class_id': 5, 'depth': 7.5, 'alpha': 0.3}
