@@ -233,12 +233,62 @@ def run_ours(args):
         step_e2e()
     e2e_drain()
 
+    # the same end-to-end step as one CUDA graph per pinned slot: H2D copy of the vertices, forward, loss, backward and
+    # the D2H copies of loss + vertex gradients are all nodes of the graph (pinned host memory on both ends)
+    e2e_fn, e2e_launch = step_e2e, 'eager'
+    if args.graph:
+        try:
+            ref_loss, ref_gv = float(loss_host[0][0]), gv_host[0].clone()
+            e2e_graphs, v_static = [], []
+            for slot in range(2):
+                vs = torch.empty_like(v_dev).requires_grad_(True)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    with torch.no_grad():
+                        vs.copy_(v_pin, non_blocking=True)
+                    out = renderer.forward_multi(vs, f_dev, fast_math=fast)
+                    outs = [out['silhouette'], out['depth'], out['normal']]
+                    ups = [g_dev['silhouette'], g_dev['depth'], g_dev['normal']]
+                    with torch.no_grad():
+                        loss = sum(torch.dot(o.reshape(-1), g.reshape(-1)) for o, g in zip(outs, ups))
+                    torch.autograd.backward(outs, ups)
+                    gv_host[slot].copy_(vs.grad, non_blocking=True)
+                    loss_host[slot].copy_(loss.view(1), non_blocking=True)
+                e2e_graphs.append(gr)
+                v_static.append(vs)
+                gv_host[slot].zero_()
+                loss_host[slot].zero_()
+                gr.replay()
+                torch.cuda.synchronize()
+                err = float((gv_host[slot] - ref_gv).norm() / ref_gv.norm())
+                lerr = abs(float(loss_host[slot][0]) - ref_loss) / max(abs(ref_loss), 1e-30)
+                assert err < 1e-5 and lerr < 1e-4, 'e2e graph differs from the eager step: %g %g' % (err, lerr)
+
+            def step_e2e_graph():
+                slot = e2e_state['i'] & 1
+                e2e_state['i'] += 1
+                e2e_consume(slot)
+                e2e_graphs[slot].replay()
+                done[slot] = torch.cuda.Event()
+                done[slot].record()
+                e2e_consume(slot ^ 1)
+
+            for _ in range(3):
+                step_e2e_graph()
+            e2e_drain()
+            e2e_fn, e2e_launch = step_e2e_graph, 'cuda graph replay (H2D, step, D2H are graph nodes)'
+        except Exception as e:      # noqa: BLE001
+            print('[bench] e2e graph capture failed (%s); timing the eager e2e step' % repr(e)[:300], file=sys.stderr)
+            torch.cuda.synchronize()
+            done[0] = done[1] = None
+
     def e2e_run():          # timed as one region: K pipelined steps, every result read on the host before it ends
         for _ in range(args.steps):
-            step_e2e()
+            e2e_fn()
         e2e_drain()
+    consumed0 = e2e_state['consumed']
     ms_e2e = timed(e2e_run, 1)
-    assert e2e_state['consumed'] == args.steps + 3 and math.isfinite(e2e_state['loss'])
+    assert e2e_state['consumed'] - consumed0 == args.steps and math.isfinite(e2e_state['loss'])
 
     # per-call device time of the four C-ABI calls (events on the launching stream = torch's current stream)
     seg = segment_times(renderer, v_dev, f_dev, g_dev, fast, steps=max(5, min(args.steps, 20)))
@@ -268,6 +318,7 @@ def run_ours(args):
                    'sharding': 'by image, no data-path collective'},
         'e2e': {'value': round(images / (ms_e2e * 1e-3), 1), 'unit': 'images/s',
                 'h2d_bytes_per_step': int(verts.numel() * 4), 'd2h_bytes_per_step': int(verts.numel() * 4 + 4),
+                'launch': e2e_launch,
                 'pipeline': 'two steps in flight; every step copies its vertices from pinned host memory and its '
                             'loss + vertex gradients back, each read on the host inside the timed region'},
         'gpu_launches': int(launches),
