@@ -48,3 +48,25 @@ def test_scene_files_round_trip(tmp_path):
     assert d.dtype in (np.uint16, np.int32) and int(d[3, 4]) == int(0.25 * 65535) and int(d[0, 0]) == 65535
     import json
     assert json.load(open(tmp_path / '00001.json'))['3'] == {'class_id': 5, 'depth': 7.5, 'alpha': 0.3}
+
+
+def test_placement_matches_the_reference_expressions():
+    """Draw order, on-screen size and paste box of main.py:538,556-565 (float32 tensor arithmetic, int() truncation)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, '3d-sdn_b200'))
+    from derender3d.compositor import placement
+    g = torch.Generator().manual_seed(0)
+    N = 40
+    zooms = 0.3 + 3 * torch.rand(N, 1, generator=g)
+    c2d = (torch.rand(N, 2, generator=g) - 0.5) * torch.tensor([0.5, 1.7])
+    depths = 5 + 30 * torch.rand(N, 1, generator=g)
+    interests = torch.rand(N, generator=g) > 0.2
+    focal, u0, v0, rs = 725.0, 620.5, 187.0, 384
+    got = placement(zooms, c2d, depths, interests, focal, u0, v0, rs)
+    want = []
+    for i in torch.sort(depths[:, 0], dim=0, descending=True)[1].tolist():        # the reference's loop, verbatim
+        if interests[i]:
+            size = int(rs / zooms[i])
+            want.append((i, size, int(c2d[i, 1] * focal + u0 - size // 2), int(c2d[i, 0] * focal + v0 - size // 2)))
+    assert got == want and len(got) == int(interests.sum())
+    assert [depths[i, 0] for i, *_ in got] == sorted([depths[i, 0] for i, *_ in got], reverse=True)

@@ -142,3 +142,37 @@ def test_sync_free_losses_equal_the_nonzero_formulation():
             x = torch.randn(6, generator=g)
             assert torch.allclose(_masked_mse(a, b, mask), partial(F.mse_loss, mask)(a, b), atol=1e-6)
             assert torch.allclose(_masked_mean(x, mask), partial(torch.mean, mask)(x), atol=1e-6)
+
+
+def test_ffd_constraint_matrix_is_the_constraint_step():
+    """transforms.py:71-95 is linear: constrain(x) == x @ C (what the fused front end applies as one matmul)."""
+    from derender3d.models.transforms import FFD
+    v = torch.rand(30, 3, generator=torch.Generator().manual_seed(0)) - 0.5
+    for cons in ([], [FFD.Constraint.symmetry(axis=FFD.Constraint.Axis.z)],
+                 [FFD.Constraint.symmetry(axis=FFD.Constraint.Axis.z),
+                  FFD.Constraint.homogeneity(axis=FFD.Constraint.Axis.y, index=[0, 1])]):
+        f = FFD(v, constraints=cons)
+        C = f.constraint_matrix()
+        x = torch.randn(5, 192, generator=torch.Generator().manual_seed(1))
+        want = f.constrain(x.reshape(5, 3, 4, 4, 4)).reshape(5, 192)
+        assert torch.allclose(x @ C, want, atol=1e-6)
+        assert torch.allclose(C @ C, C, atol=1e-6)          # a projection: constraining twice changes nothing
+
+
+def test_mesh_bank_layout():
+    """sdn_b200.MeshBank: concatenated Bernstein tables, row offsets, faces padded with (0,0,0) triangles."""
+    import sdn_b200
+    from derender3d.models.transforms import FFD
+    g = torch.Generator().manual_seed(0)
+    ffds = [FFD(torch.rand(nv, 3, generator=g) - 0.5) for nv in (11, 29, 5)]
+    faces = [torch.randint(0, nv, (nf, 3), generator=g, dtype=torch.int32) for nv, nf in ((11, 20), (29, 7), (5, 9))]
+    bank = sdn_b200.MeshBank([f.B for f in ffds], faces, 'cpu')
+    assert (bank.K, bank.nv_max, bank.nf_max) == (3, 29, 20)
+    assert bank.basis.shape == (45, 64) and bank.basis_off.tolist() == [0, 11, 40] and bank.nv.tolist() == [11, 29, 5]
+    for k, f in enumerate(ffds):
+        lo = int(bank.basis_off[k])
+        assert torch.equal(bank.basis[lo:lo + f.B.shape[0]], f.B.reshape(-1, 64))
+        assert torch.equal(bank.faces[k, :faces[k].shape[0]], faces[k])
+        assert int(bank.faces[k, faces[k].shape[0]:].abs().sum()) == 0
+    # each Bernstein row is a partition of unity
+    assert torch.allclose(bank.basis.sum(1), torch.ones(45), atol=1e-5)
