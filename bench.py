@@ -222,8 +222,9 @@ def run_ours(args):
             torch.cuda.synchronize()
         for _ in range(3):
             timed_step()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local)      # rank 0 samples its own GPU; eight concurrent nvidia-smi pollers only add noise
+    if rank == 0:
+        sampler.start()
     ms = timed(timed_step, args.steps)
     launches = launches_per_step * args.steps
     sampler.stop_flag = True
