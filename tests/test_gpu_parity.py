@@ -391,6 +391,30 @@ def test_analysis_by_synthesis_reduces_silhouette_error(dev):
     assert refined['_masks'].shape == target.shape
 
 
+def test_analysis_by_synthesis_as_cuda_graph_matches_eager(dev):
+    """refine(graph=True): iteration 0 eager, the rest replays of one captured iteration; same loss trajectory."""
+    from derender3d import TargetType
+    from derender3d.models import Derenderer3d
+    from derender3d.optimise import refine
+    S, B = 64, 4
+    model = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=_synthetic_objs()).to(dev)
+    blob, _ = _synthetic_blob(B, dev, seed=3)
+    model.train()
+    model._force_no_sample = True
+    with torch.no_grad():
+        target = model.render(blob)['_masks'].clone()
+    start = dict(blob)
+    start['_translation2ds'] = blob['_translation2ds'] + 0.08
+    start['_log_scales'] = blob['_log_scales'] + 0.15
+    ref_blob, ref_hist = refine(model, start, target, num_opts=12)
+    out_blob, out_hist = refine(model, start, target, num_opts=12, graph=True)
+    assert out_hist.shape == ref_hist.shape == (12,)
+    assert rel_l2(out_hist.cpu().numpy(), ref_hist.cpu().numpy()) <= 2e-2, (out_hist.tolist(), ref_hist.tolist())
+    assert float(out_hist[-1]) < float(out_hist[0])
+    for k in ('_translation2ds', '_log_scales'):
+        assert rel_l2(out_blob[k].cpu().numpy(), ref_blob[k].cpu().numpy()) <= 2e-2, k
+
+
 def test_pathological_faces_match_oracle(dev, oracle):
     """Edge cases the reference's kernels meet in the wild: faces far outside the frustum (|NDC| > 64: no bbox
     culling), faces crossing the camera plane (negative / tiny z), NaN and infinite vertices, zero-area faces,
