@@ -70,3 +70,41 @@ def test_placement_matches_the_reference_expressions():
             want.append((i, size, int(c2d[i, 1] * focal + u0 - size // 2), int(c2d[i, 0] * focal + v0 - size // 2)))
     assert got == want and len(got) == int(interests.sum())
     assert [depths[i, 0] for i, *_ in got] == sorted([depths[i, 0] for i, *_ in got], reverse=True)
+
+
+def test_random_sizes_against_pillow_through_the_product_tables():
+    """Property check over random (in, out) sizes: resizing with the tables the product uploads to the GPU
+    (derender3d.compositor.resample_tables) reproduces Pillow for the 8-bit and the float plane."""
+    from PIL import Image
+    sys.path.insert(0, os.path.join(ROOT, '3d-sdn_b200'))
+    from derender3d.compositor import PRECISION_BITS, resample_tables
+    rng = np.random.default_rng(7)
+    for _ in range(25):
+        S, out = int(rng.integers(8, 97)), int(rng.integers(1, 161))
+        b, kd, k8 = resample_tables(S, out)
+        a = rng.integers(0, 256, (S, S), dtype=np.uint8)
+        t = np.zeros((S, out), np.uint8)
+        for xx in range(out):
+            x0, n = b[xx]
+            t[:, xx] = np.clip(((1 << (PRECISION_BITS - 1)) + (a[:, x0:x0 + n].astype(np.int64) * k8[xx, :n]).sum(1)) >> PRECISION_BITS, 0, 255)
+        o = np.zeros((out, out), np.uint8)
+        for yy in range(out):
+            y0, n = b[yy]
+            o[yy] = np.clip(((1 << (PRECISION_BITS - 1)) + (t[y0:y0 + n].astype(np.int64) * k8[yy, :n, None]).sum(0)) >> PRECISION_BITS, 0, 255)
+        assert np.array_equal(o, np.asarray(Image.fromarray(a).resize((out, out), Image.BILINEAR))), (S, out)
+        f = rng.random((S, S), dtype=np.float32)
+        tf = np.zeros((S, out), np.float32)
+        for xx in range(out):
+            x0, n = b[xx]
+            acc = np.zeros(S, np.float64)
+            for j in range(n):
+                acc += f[:, x0 + j].astype(np.float64) * kd[xx, j]
+            tf[:, xx] = acc.astype(np.float32)
+        of = np.zeros((out, out), np.float32)
+        for yy in range(out):
+            y0, n = b[yy]
+            acc = np.zeros(out, np.float64)
+            for j in range(n):
+                acc += tf[y0 + j].astype(np.float64) * kd[yy, j]
+            of[yy] = acc.astype(np.float32)
+        assert np.array_equal(of, np.asarray(Image.fromarray(f).resize((out, out), Image.BILINEAR))), (S, out)
