@@ -2,13 +2,8 @@
 
 
 class TargetType:
-    """Mode bit-mask (reference: derender3d/__init__.py:1-10)."""
-    geometry = (1 << 0)
-    reproject = (1 << 1)
-    normal = (1 << 2)
-    depth = (1 << 3)
-
-    pretrain = geometry
-    finetune = reproject
-    full = geometry | reproject
-    extend = geometry | reproject | normal | depth
+    """Mode bit-mask (reference: derender3d/__init__.py:1-10): which heads are supervised / which maps are rendered."""
+    geometry, reproject, normal, depth = (1 << bit for bit in range(4))
+    pretrain, finetune = geometry, reproject        # stage names used by scripts/main.py
+    full = pretrain | finetune
+    extend = full | normal | depth

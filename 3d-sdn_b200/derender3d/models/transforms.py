@@ -12,34 +12,34 @@ import torch
 from torch.nn.modules import Module
 
 
+class _Constraint(object):
+    """A linear constraint on the lattice offsets: `symmetry` mirrors the lattice across one axis (the mirrored
+    component changes sign), `homogeneity` ties the listed lattice planes of one axis together.  Exposed as
+    FFD.Constraint with the reference's factory names (transforms.py:11-36)."""
+
+    class Type:
+        symmetry, homogeneity = 0, 1
+
+    class Axis:
+        x, y, z = 0, 1, 2
+
+    def __init__(self, type, axis=None, index=None):
+        self.type, self.axis = type, axis
+        if index is not None:
+            self.index = index
+
+    @classmethod
+    def symmetry(cls, axis):
+        return cls(cls.Type.symmetry, axis=axis)
+
+    @classmethod
+    def homogeneity(cls, axis, index):
+        return cls(cls.Type.homogeneity, axis=axis, index=index)
+
+
 class FFD(Module):
     """Free-form deformation of a fixed vertex set by a 4x4x4 Bezier lattice (transforms.py:10-99)."""
-
-    class Constraint:
-        class Type:
-            symmetry = 0
-            homogeneity = 1
-
-        class Axis:
-            x = 0
-            y = 1
-            z = 2
-
-        @staticmethod
-        def symmetry(axis):
-            c = FFD.Constraint(FFD.Constraint.Type.symmetry)
-            c.axis = axis
-            return c
-
-        @staticmethod
-        def homogeneity(axis, index):
-            c = FFD.Constraint(FFD.Constraint.Type.homogeneity)
-            c.axis = axis
-            c.index = index
-            return c
-
-        def __init__(self, type):
-            self.type = type
+    Constraint = _Constraint
 
     def __init__(self, vertices, num_grids=4, constraints=None):
         super(FFD, self).__init__()
@@ -98,36 +98,39 @@ class FFD(Module):
         return V[0] if single else V
 
 
+def quaternion_matrix(q):
+    """[N,4] (a,b,c,d) -> [N,3,3].  Products of two components are formed once; 2*(b*c) == (2*b)*c exactly, so the
+    entries equal the reference's `2 * b * c - 2 * a * d` style expressions (transforms.py:114-124) bit for bit."""
+    a, b, c, d = q.unbind(dim=1)
+    aa, bb, cc, dd = a * a, b * b, c * c, d * d
+    ab, ac, ad, bc, bd, cd = a * b, a * c, a * d, b * c, b * d, c * d
+    rows = ((aa + bb - cc - dd, 2 * bc - 2 * ad, 2 * bd + 2 * ac),
+            (2 * bc + 2 * ad, aa - bb + cc - dd, 2 * cd - 2 * ab),
+            (2 * bd - 2 * ac, 2 * cd + 2 * ab, aa - bb - cc + dd))
+    return torch.stack([torch.stack(r, dim=1) for r in rows], dim=1)
+
+
 class PerspectiveTransform(Module):
-    """Scale, rotate (unit quaternion), translate, shear along the principal ray, zoom (transforms.py:102-158)."""
+    """Scale, rotate (quaternion), translate, shear along the principal ray, zoom (transforms.py:102-158).
+    Training mode: `zooms` given.  Test mode: `zoom_tos` given, the zoom is derived from the vertices and returned."""
 
     def forward(self, vertices, scales=None, rotations=None, translations=None, perspective_translations=None,
                 zooms=None, zoom_tos=None):
+        v = vertices
         if scales is not None:
-            vertices = vertices * scales.unsqueeze(1)
+            v = v * scales[:, None, :]
         if rotations is not None:
-            a, b, c, d = rotations.unbind(dim=1)
-            T = torch.stack([
-                a * a + b * b - c * c - d * d, 2 * b * c - 2 * a * d, 2 * b * d + 2 * a * c,
-                2 * b * c + 2 * a * d, a * a - b * b + c * c - d * d, 2 * c * d - 2 * a * b,
-                2 * b * d - 2 * a * c, 2 * c * d + 2 * a * b, a * a - b * b - c * c + d * d,
-            ], dim=1).view(-1, 3, 3)
-            vertices = torch.matmul(vertices, T.transpose(1, 2))
-        if translations is not None:
-            translations = translations.unsqueeze(1)
-            vertices = vertices + translations
-        if perspective_translations is not None:
-            perspective_translations = perspective_translations.unsqueeze(1)
-        else:
-            perspective_translations = translations
-        x, y, z = vertices.unbind(dim=2)
-        x0, y0, z0 = perspective_translations.unbind(dim=2)
-        x = x - x0 / z0 * z
-        y = y - y0 / z0 * z
-        if zoom_tos is not None:
-            zooms = torch.min(torch.abs(z) / torch.max(torch.abs(x), torch.abs(y)), dim=1, keepdim=True)[0] * zoom_tos
-        z = z / zooms
-        vertices = torch.stack([x, y, z], dim=2)
-        if zoom_tos is None:
-            return vertices
-        return vertices, zooms
+            v = torch.matmul(v, quaternion_matrix(rotations).transpose(1, 2))
+        shift = None if translations is None else translations[:, None, :]
+        if shift is not None:
+            v = v + shift
+        ray = shift if perspective_translations is None else perspective_translations[:, None, :]
+        x, y, z = v.unbind(dim=2)
+        rx, ry, rz = ray.unbind(dim=2)
+        x, y = x - rx / rz * z, y - ry / rz * z                      # shear: the principal ray becomes the z axis
+        derived = zoom_tos is not None
+        if derived:                                                   # the tightest |z| / max(|x|,|y|) over the mesh
+            fit = (z.abs() / torch.max(x.abs(), y.abs())).min(dim=1, keepdim=True)[0]
+            zooms = fit * zoom_tos
+        out = torch.stack((x, y, z / zooms), dim=2)
+        return (out, zooms) if derived else out

@@ -74,3 +74,20 @@ def test_load_obj_on_reference_assets():
     v, f = nr.load_obj(path)
     assert v.dtype == np.float32 and f.dtype == np.int32 and f.min() == 0 and f.max() < len(v)
     assert 9000 < len(v) < 20000 and 29000 < len(f) < 73000
+
+
+def test_mesh_module_batches_and_parameter_groups(tmp_path):
+    """neural_renderer.Mesh (mesh.py:7-38): parameters, broadcast batch, per-parameter learning rates."""
+    import neural_renderer as nr
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3], [0, 3, 1], [1, 3, 2]], np.int32)
+    path = str(tmp_path / 'tetra.obj')
+    nr.save_obj(path, v, f)
+    mesh = nr.Mesh(path, texture_size=2)
+    assert (mesh.num_vertices, mesh.num_faces, mesh.texture_size) == (4, 4, 2)
+    vb, fb, tb = mesh.get_batch(3)
+    assert vb.shape == (3, 4, 3) and fb.shape == (3, 4, 3) and tb.shape == (3, 4, 2, 2, 2, 3)
+    assert float(tb.min()) > 0 and float(tb.max()) < 1
+    assert {id(p) for p in mesh.parameters()} == {id(mesh.vertices), id(mesh.textures)}
+    opt = torch.optim.Adam(mesh.set_lr(0.01, 0.1))
+    assert [g['lr'] for g in opt.param_groups] == [0.01, 0.1]
