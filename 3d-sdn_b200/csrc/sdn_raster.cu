@@ -49,31 +49,30 @@ std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
 struct TimedLaunch { const char* name; cudaEvent_t e0, e1; };
 std::vector<TimedLaunch> g_timed;
-const char* g_pending_name = nullptr;
-cudaEvent_t g_pending_e0 = nullptr;
-cudaStream_t g_pending_stream = nullptr;
+// the launch being bracketed belongs to the calling thread (DataParallel drives one thread per GPU): thread-local
+thread_local const char* g_pending_name = nullptr;
+thread_local cudaEvent_t g_pending_e0 = nullptr;
+thread_local cudaStream_t g_pending_stream = nullptr;
 
 // SDN_DEBUG_SYNC=1 in the environment: print every launch and synchronise after it (hang / fault localisation)
 const bool g_debug_sync = getenv("SDN_DEBUG_SYNC") != nullptr;
-const char* g_dbg_name = nullptr;
-cudaStream_t g_dbg_stream = nullptr;
+thread_local const char* g_dbg_name = nullptr;
+thread_local cudaStream_t g_dbg_stream = nullptr;
 
 inline void timing_begin(const char* name, cudaStream_t st) {
     if (g_debug_sync) { g_dbg_name = name; g_dbg_stream = st; fprintf(stderr, "[sdn] launch %s\n", name); fflush(stderr); }
     if (!g_timing.load(std::memory_order_relaxed)) return;
-    std::lock_guard<std::mutex> lk(g_timing_mu);
     cudaEvent_t e0;
     if (cudaEventCreate(&e0) != cudaSuccess) return;
     cudaEventRecord(e0, st);
     g_pending_name = name; g_pending_e0 = e0; g_pending_stream = st;
 }
 inline void timing_end() {
-    if (!g_timing.load(std::memory_order_relaxed)) return;
-    std::lock_guard<std::mutex> lk(g_timing_mu);
     if (!g_pending_name) return;
     cudaEvent_t e1;
     if (cudaEventCreate(&e1) == cudaSuccess) {
         cudaEventRecord(e1, g_pending_stream);
+        std::lock_guard<std::mutex> lk(g_timing_mu);      // the list of finished brackets is the only shared state
         g_timed.push_back({g_pending_name, g_pending_e0, e1});
     }
     g_pending_name = nullptr;
@@ -2258,7 +2257,7 @@ inline int check_launch() {
         fflush(stderr);
         g_dbg_name = nullptr;
     }
-    return (int)cudaPeekAtLastError();
+    return (int)cudaGetLastError();     // also clears a non-sticky launch error, so one bad call does not poison the next
 }
 
 Clip make_clip(double near_, double far_) {
@@ -2268,9 +2267,31 @@ Clip make_clip(double near_, double far_) {
 }
 
 int sm_count() {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
+    // asked once per device (the answer never changes); -1 = not asked yet
+    static std::atomic<int> cached[64];
+    static std::once_flag init;
+    std::call_once(init, [] { for (auto& c : cached) c.store(-1); });
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n < 0) {
+        n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is needed once per (kernel, device), not on every call
+template <typename K>
+inline void allow_smem_once(K kernel, size_t bytes) {
+    static std::atomic<size_t> granted[64];      // one table per kernel instantiation; zero-initialised
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (granted[dev].load(std::memory_order_relaxed) >= bytes && bytes > 0) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    granted[dev].store(bytes, std::memory_order_relaxed);
 }
 
 CamDev make_cam(const sdn_camera* cam) {
@@ -2370,7 +2391,7 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
 #define SDN_LAUNCH_LINE(MODE, LP_, LQ_, MINB_)                                                                          \
     do {                                                                                                                \
         const size_t lsmem = sizeof(float2) * LW * LQ_ * 33;                                                             \
-        cudaFuncSetAttribute(k_line_sweep<MODE, LP_, LQ_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem); \
+        allow_smem_once(k_line_sweep<MODE, LP_, LQ_, MINB_>, lsmem);                                                     \
         timing_begin("k_line_sweep", st);                                                                                \
         k_line_sweep<MODE, LP_, LQ_, MINB_><<<lgrid, LW * 32, lsmem, st>>>(P, ws);                                       \
     } while (0)
@@ -2385,7 +2406,7 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
             const size_t lsmem = sizeof(float2) * LW * 32 * 33;
 #define SDN_LAUNCH_MAIN(MODE)                                                                                           \
     do {                                                                                                                \
-        cudaFuncSetAttribute(k_bwd_main<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);                \
+        allow_smem_once(k_bwd_main<MODE>, lsmem);                \
         timing_begin("k_bwd_main", st);                                                                                 \
         k_bwd_main<MODE><<<lgrid + face_ctas, LW * 32, lsmem, st>>>(P, ws, face_ctas);                                  \
     } while (0)
@@ -2400,7 +2421,7 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
                 // silhouette only: far-field line sweep (block moments); shared memory sized for the longest line
                 const int lcap = (lmax + 31) / 32 * 32;
                 const size_t fsmem = sizeof(float) * LW * ((size_t)lcap + lcap / 32 + 32 + (size_t)FF_P * (lcap / 32 + 1));
-                cudaFuncSetAttribute(k_line_sweep_ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+                allow_smem_once(k_line_sweep_ff, fsmem);
                 timing_begin("k_line_sweep_ff", st);
                 k_line_sweep_ff<<<lgrid, LW * 32, fsmem, st>>>(P, ws, lcap);
             }

@@ -2,7 +2,9 @@
 fully connected layers + head split.  Attribute names (net, relu, fc1, fc2, _fc3) match the reference so that its
 checkpoints load unchanged.  The convolutions are library GEMMs (cuDNN through torchvision); the four fully
 connected layers run on the hand-written tcgen05 kernel (sdn_b200.linear_tc: bf16 operands, fp32 accumulate in TMEM)
-when the module is on a GPU and `tensor_core_head` is set (default; SDN_TC_HEAD=0 turns it off): DESIGN.md "Encoder"."""
+when the module is on a GPU and `tensor_core_head` is set.  That is OPT-IN (SDN_TC_HEAD=1, or under torch.autocast):
+the reference head is fp32 and a loaded reference checkpoint must give the same theta / class argmax, so the default
+keeps fp32 nn.Linear.  DESIGN.md "Encoder"."""
 import os
 
 import torch
@@ -38,7 +40,7 @@ class Derenderer(Module):
         self.fc1 = torch.nn.Linear(self.hidden_size + self.in_size, self.hidden_size)
         self.fc2 = torch.nn.Linear(self.hidden_size, self.hidden_size)
         self._fc3 = torch.nn.Linear(self.hidden_size, sum(self.out_sizes.values()))
-        self.tensor_core_head = os.environ.get('SDN_TC_HEAD', '1') != '0'
+        self.tensor_core_head = os.environ.get('SDN_TC_HEAD', '0') == '1'
 
     def _trunk(self, images):
         """torchvision ResNet._forward_impl without its last Linear."""
@@ -48,7 +50,7 @@ class Derenderer(Module):
         return torch.flatten(n.avgpool(x), 1)
 
     def forward(self, images, mroi_norms, droi_norms):
-        if self.tensor_core_head and images.is_cuda:
+        if images.is_cuda and (self.tensor_core_head or torch.is_autocast_enabled()):
             from sdn_b200 import linear_tc
             x = linear_tc(self._trunk(images), self.net.fc.weight, self.net.fc.bias, relu=True)
             x = torch.cat([x, mroi_norms.float(), droi_norms.float()], dim=1)

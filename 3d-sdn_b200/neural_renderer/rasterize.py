@@ -15,22 +15,29 @@ USE_UNSAFE_IMPLEMENTATION = bool(int(os.environ.get('NEURAL_RENDERER_UNSAFE', '0
 
 
 class Rasterize(object):
-    """Callable with the constructor signature of the reference's chainer.Function (rasterize.py:19-37).
-    Returns (rgb [B,Hs,Ws,3]-style outputs are NOT exposed; use rasterize_rgbad) -- kept for API presence:
-    calling it yields (rgb [B,3,H,W] | None, alpha [B,H,W] | None, depth [B,H,W] | None) at raster resolution
-    `image_size` without anti-aliasing, rows already flipped to image orientation."""
+    """The reference's chainer.Function as a callable (rasterize.py:19-64, forward_gpu :464-510): same constructor,
+    same return contract -- `Rasterize(image_size, near, far, eps, background_color, return_rgb, return_alpha,
+    return_depth)(faces[, textures])` -> (rgb_map [B,is,is,3] | None, alpha_map [B,is,is] | None,
+    depth_map [B,is,is] | None) at raster resolution `image_size`, channel-LAST and in RASTER orientation (row 0 is the
+    bottom of the image: the flip / transpose / 2x2 mean belong to rasterize_rgbad, :950-966).  Differentiable in
+    faces and textures.  `image_size` may also be (H, W)."""
 
     def __init__(self, image_size, near, far, eps, background_color, return_rgb=False, return_alpha=False,
                  return_depth=False):
         if not any((return_rgb, return_alpha, return_depth)):
             raise Exception     # nothing to draw, rasterize.py:25-27
+        self.image_size, self.near, self.far, self.eps = image_size, near, far, eps
+        self.background_color = background_color
+        self.return_rgb, self.return_alpha, self.return_depth = return_rgb, return_alpha, return_depth
         self.cfg = RasterConfig(image_size, False, near, far, eps, background_color, return_rgb, return_alpha,
                                 return_depth)
 
     def __call__(self, faces, textures=None):
-        rgb, alpha, depth = RasterizeFunction.apply(faces, textures, self.cfg)
-        c = self.cfg
-        return (rgb if c.return_rgb else None, alpha if c.return_alpha else None, depth if c.return_depth else None)
+        rgb, alpha, depth = RasterizeFunction.apply(faces, textures if self.return_rgb else None, self.cfg)
+        self.face_index_map = self.cfg.last_face_index      # int32 [B,is,is], raster orientation (rasterize.py:475)
+        return (rgb.flip(2).permute(0, 2, 3, 1) if self.return_rgb else None,
+                alpha.flip(1) if self.return_alpha else None,
+                depth.flip(1) if self.return_depth else None)
 
 
 def rasterize_rgbad(faces, textures=None, image_size=DEFAULT_IMAGE_SIZE, anti_aliasing=DEFAULT_ANTI_ALIASING,

@@ -14,10 +14,12 @@ LIB_PATH = os.path.join(HERE, 'libsdn_b200.so')
 
 SDN_RGB, SDN_ALPHA, SDN_DEPTH = 1, 2, 4
 
-# Backward distance arithmetic when a RasterConfig does not say: False = IEEE divisions in the op order of
-# rasterize.py:646-653 (bit-faithful inclusion AND arithmetic), True = line-sweep kernel with hardware reciprocals
-# (same inclusion tests, ~1e-6 relative).  SDN_FAST_MATH=1 in the environment flips the default.
-DEFAULT_FAST_MATH = bool(int(os.environ.get('SDN_FAST_MATH', '0') or 0))
+# Backward distance arithmetic when a RasterConfig does not say.  1 (default, the mode bench.py times and the full-size
+# parity tests check): line-sweep kernels, identical inclusion tests, distances through hardware reciprocals and
+# well-separated block moments (<= 1e-5 relative on the gradient, inside north_star's 1e-4 bar).  0: IEEE divisions in
+# the op order of rasterize.py:646-653 (one warp per (face, edge, axis) item; ~10x slower).  SDN_FAST_MATH=0 in the
+# environment selects the IEEE path for a whole process.
+DEFAULT_FAST_MATH = int(os.environ.get('SDN_FAST_MATH', '1') or 0)
 
 _lib = None
 
@@ -330,10 +332,14 @@ class LinearTCFunction(torch.autograd.Function):
         N = w.shape[0]
         if w.shape[1] != K:
             raise SdnError('linear_tc: weight is [%d,%d], input has %d features' % (N, w.shape[1], K))
+        _need_cuda(b)
+        if w.device != x2.device or (b is not None and b.device != x2.device):
+            raise SdnError('linear_tc: input on %s, weight on %s' % (x2.device, w.device))
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         if M > 0:
-            _check(lib().sdn_linear_forward(_ptr(x2), _ptr(w), _ptr(b) if b is not None else None, _ptr(y),
-                                            M, N, K, 1 if relu else 0, _stream()))
+            with torch.cuda.device(x2.device):
+                _check(lib().sdn_linear_forward(_ptr(x2), _ptr(w), _ptr(b) if b is not None else None, _ptr(y),
+                                                M, N, K, 1 if relu else 0, _stream()))
         ctx.save_for_backward(x2, w, y if relu else None)
         ctx.has_bias = bias is not None
         ctx.in_shape = x.shape

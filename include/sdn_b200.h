@@ -5,8 +5,11 @@
  * Boundary contract:
  *   - extern "C", raw DEVICE pointers, row-major, float32 / int32, explicit cudaStream_t (passed as void*),
  *   - every function returns int: 0 = ok, >0 = cudaError_t, <0 = SDN_E_* argument error; nothing throws or exits,
- *   - the library never allocates, frees or keeps global state; scratch comes in as (workspace, bytes),
- *     sized by sdn_workspace_bytes(); the SAME workspace that served a forward must be handed to its backward,
+ *   - the library never allocates or frees device memory and keeps no state that influences results; scratch comes
+ *     in as (workspace, bytes), sized by sdn_workspace_bytes(); the SAME workspace that served a forward must be
+ *     handed to its backward.  The only process-wide state is diagnostic: a launch counter, the opt-in per-launch
+ *     event list of sdn_timing_enable() (mutex-protected; the bracket in flight is thread-local) and per-device
+ *     caches of constant device attributes (SM count, shared-memory opt-in already granted),
  *   - re-entrant: works on the caller's current device and the stream given; no device-wide synchronisation.
  *
  * Each entry point names the reference interface it replaces (paths relative to /root/reference/geometric/).

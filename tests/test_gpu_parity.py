@@ -33,9 +33,14 @@ def _sdn_raster(faces, textures, H, W, ss, near, far, eps, bg, flags, dev, g=Non
     return res
 
 
+@pytest.mark.parametrize('math', ['fast', 'exact'])
 @pytest.mark.parametrize('path', GOLDEN, ids=lambda p: p.split('/')[-1][:-4])
-def test_golden_vectors(dev, path):
-    """Vectors produced by the reference's own kernel bodies (tests/golden/make_golden.py)."""
+def test_golden_vectors(dev, path, math, monkeypatch):
+    """Vectors produced by the reference's own kernel bodies (tests/golden/make_golden.py), in the library's default
+    backward arithmetic (fast: line sweeps) and in the IEEE-division mode."""
+    import sdn_b200
+    assert sdn_b200.DEFAULT_FAST_MATH == 1, 'the default backward mode is the one bench.py times'
+    monkeypatch.setattr(sdn_b200, 'DEFAULT_FAST_MATH', 1 if math == 'fast' else 0)
     g = load_golden(path)
     S = int(g['S'])
     flags = g['flags']
@@ -61,6 +66,40 @@ def test_golden_vectors(dev, path):
     assert rel_l2(r['faces'].grad, g['grad_faces']) <= TOL
     if rgb:
         assert rel_l2(r['textures'].grad, g['grad_textures']) <= TOL
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=lambda p: p.split('/')[-1][:-4])
+def test_rasterize_class_returns_the_reference_maps(dev, path):
+    """nr.Rasterize(...)(faces, textures) has the return contract of rasterize.py:19-64 / :464-510: channel-last maps in
+    raster orientation -- exactly what the golden files hold."""
+    import neural_renderer as nr
+    g = load_golden(path)
+    S = int(g['S'])
+    rgb, alpha, depth = [bool(x) for x in g['flags']]
+    fn = nr.Rasterize(S, float(g['near']), float(g['far']), float(g['eps']), tuple(float(x) for x in g['background']),
+                      rgb, alpha, depth)
+    f = torch.tensor(g['faces'], device=dev, requires_grad=True)
+    t = torch.tensor(g['textures'], device=dev, requires_grad=True) if rgb else None
+    o_rgb, o_alpha, o_depth = fn(f, t) if rgb else fn(f)
+    assert np.array_equal(fn.face_index_map.cpu().numpy(), g['face_index_map'])
+    loss = 0
+    if alpha:
+        assert torch.equal(o_alpha.cpu(), torch.tensor(g['alpha_map']))
+        loss = loss + (o_alpha * torch.tensor(g['grad_alpha_map'], device=dev)).sum()
+    else:
+        assert o_alpha is None
+    if depth:
+        assert torch.equal(o_depth.cpu(), torch.tensor(g['depth_map']))
+        loss = loss + (o_depth * torch.tensor(g['grad_depth_map'], device=dev)).sum()
+    else:
+        assert o_depth is None
+    if rgb:
+        assert o_rgb.shape == g['rgb_map'].shape and rel_l2(o_rgb, g['rgb_map']) <= 1e-6
+        loss = loss + (o_rgb * torch.tensor(g['grad_rgb_map'], device=dev)).sum()
+    else:
+        assert o_rgb is None
+    loss.backward()
+    assert rel_l2(f.grad, g['grad_faces']) <= TOL
 
 
 @pytest.mark.parametrize('aa', [True, False])
@@ -219,6 +258,74 @@ def test_full_size_single_image_against_oracle(dev, oracle, fast, monkeypatch):
     g = torch.randn(io.shape, generator=torch.Generator().manual_seed(2))
     (io * g).sum().backward()
     (ig * g.to(dev)).sum().backward()
+    assert rel_l2(vg.grad, vo.grad) <= TOL
+
+
+@pytest.mark.parametrize('outputs', ['sdn', 's'], ids=['config2', 'config2b'])
+def test_full_size_default_mode_against_oracle(dev, oracle, outputs):
+    """The benchmarked path IS the tested path: one 375x1242 image, 2x SSAA, in the library's default backward mode
+    (what bench.py times), through forward_multi exactly as bench.py calls it.  config2 = silhouette + depth + normal
+    (the sum of the reference's three graphs, eps 1e-4 / 1e-4 / 1e-3); config2b = silhouette only (the reference's
+    training path, derender3d/models/__init__.py:203-208).  Face index bit-exact, maps and vertex gradients <= 1e-4."""
+    import sdn_b200
+    assert sdn_b200.DEFAULT_FAST_MATH == 1
+    from sdn_b200 import workloads as wl
+    from derender3d.models.renderer import Renderer, RenderType
+    verts, faces = wl.vkitti_scene_batch(1, seed=13, z_range=(6.5, 8.0))
+    fb = faces[None].contiguous()
+    angle = wl.vkitti_viewing_angle()
+    size = (wl.VKITTI_H, wl.VKITTI_W)
+    want = {'silhouette': 's' in outputs, 'depth': 'd' in outputs, 'normal': 'n' in outputs}
+    vg = verts.clone().to(dev).requires_grad_(True)
+    out = Renderer(image_size=size, viewing_angle=angle).forward_multi(vg, fb.to(dev).int(), **want)
+    vo = verts.clone().requires_grad_(True)
+    gen = torch.Generator().manual_seed(5)
+    lo = lg = 0
+    for key, rt in (('silhouette', RenderType.Silhouette), ('depth', RenderType.Depth), ('normal', RenderType.Normal)):
+        if not want[key]:
+            continue
+        io = oracle.derender_render(vo, fb, size, angle, rt)
+        g = torch.randn(io.shape, generator=gen)
+        if key == 'silhouette':
+            assert torch.equal(out[key].cpu(), io) and float(io.sum()) > 1000
+        assert rel_l2(out[key], io) <= TOL, key
+        lo = lo + (io * g).sum()
+        lg = lg + (out[key] * g.to(dev)).sum()
+    lo.backward()
+    lg.backward()
+    assert float(vo.grad.abs().sum()) > 0
+    assert rel_l2(vg.grad, vo.grad) <= TOL
+
+
+def test_large_mesh_default_mode_against_oracle(dev, oracle):
+    """BASELINE config 2c shape: a 58k-triangle closed mesh (116k effective faces with fill_back -- the size of the
+    reference's ShapeNet templates) at the reference's own 384x384 render, default backward mode, three outputs."""
+    from sdn_b200 import workloads as wl
+    from derender3d.models.renderer import Renderer, RenderType
+    v, f = wl.superellipsoid_mesh(172, 170, 0.6, 0.8)
+    assert 57000 < f.shape[0] < 60000
+    S, focal = 384, 500.0
+    verts = torch.tensor(v * np.array([2.0, 0.8, 0.9], np.float32))[None].clone()
+    c, s_ = np.cos(0.6), np.sin(0.6)
+    R = torch.tensor([[c, 0, s_], [0, 1, 0], [-s_, 0, c]], dtype=torch.float32)
+    verts = verts @ R.T + torch.tensor([0.2, -0.1, -5.0])
+    fb = torch.tensor(f)[None].contiguous()
+    angle = wl.vkitti_viewing_angle(S, focal)
+    vg = verts.clone().to(dev).requires_grad_(True)
+    out = Renderer(image_size=S, viewing_angle=angle).forward_multi(vg, fb.to(dev).int())
+    vo = verts.clone().requires_grad_(True)
+    gen = torch.Generator().manual_seed(6)
+    lo = lg = 0
+    for key, rt in (('silhouette', RenderType.Silhouette), ('depth', RenderType.Depth), ('normal', RenderType.Normal)):
+        io = oracle.derender_render(vo, fb, S, angle, rt)
+        g = torch.randn(io.shape, generator=gen)
+        if key == 'silhouette':
+            assert torch.equal(out[key].cpu(), io) and float(io.sum()) > 2000
+        assert rel_l2(out[key], io) <= TOL, key
+        lo = lo + (io * g).sum()
+        lg = lg + (out[key] * g.to(dev)).sum()
+    lo.backward()
+    lg.backward()
     assert rel_l2(vg.grad, vo.grad) <= TOL
 
 
