@@ -37,7 +37,7 @@ __global__ void k_composite_rows(const sdn_composite_obj* __restrict__ objs, con
                                  uchar4* __restrict__ tmp8, float* __restrict__ tmpf) {
     const sdn_composite_obj o = objs[blockIdx.y];
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long)S * o.size) return;
+    if (t >= (long)S * o.size) return;             // also skips mask-only entries (size == 0)
     const int y = (int)(t / o.size), xx = (int)(t % o.size);
     const int x0 = bounds[(o.row_off + xx) * 2], n = bounds[(o.row_off + xx) * 2 + 1];
     const int* k8 = kk8 + o.k_off + (long)xx * o.ksize;
@@ -67,16 +67,29 @@ __global__ void k_composite_rows(const sdn_composite_obj* __restrict__ objs, con
 }
 
 // ---- vertical pass + paste + far-to-near composite, one thread per frame pixel ------------------------------
+// Entries with size == 0 are MASK-ONLY: a frame-resolution mask (`frame_masks[index]`, [H,W]) blended into the instance
+// map alone, `inst = (1 - m) * inst + m * id` -- what main.py:601-604 does with the ground-truth mask of an object that
+// is not "interesting" when no edit operations are given.  Rendered entries blend with a rounded 0/1 weight, so for
+// them the same expression is an overwrite; the loop therefore walks far -> near for the instance id and remembers
+// the nearest covering RENDERED entry, whose normal / depth are evaluated once afterwards.
 __global__ void k_composite_frame(const sdn_composite_obj* __restrict__ objs, int M, int S, int H, int W,
                                   const int* __restrict__ bounds, const int* __restrict__ kk8,
                                   const double* __restrict__ kkd, const uchar4* __restrict__ tmp8,
-                                  const float* __restrict__ tmpf, float* __restrict__ instance,
-                                  float* __restrict__ normal, float* __restrict__ depth) {
+                                  const float* __restrict__ tmpf, const float* __restrict__ frame_masks,
+                                  float* __restrict__ instance, float* __restrict__ normal,
+                                  float* __restrict__ depth) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
+    const size_t at = (size_t)y * W + x, plane = (size_t)H * W;
     float inst = 0.0f, n0 = 0.5f, n1 = 0.5f, n2 = 0.5f, dep = 1.0f;     // main.py:540-542
-    for (int mi = M - 1; mi >= 0; mi--) {                                 // nearest first
+    int top = -1;
+    for (int mi = 0; mi < M; mi++) {                                      // far -> near (main.py:538,543)
         const sdn_composite_obj o = objs[mi];
+        if (o.size == 0) {                                                // mask-only entry (main.py:601-604)
+            const float m = frame_masks[(size_t)o.index * plane + at];
+            inst = (1.0f - m) * inst + m * (float)o.id;
+            continue;
+        }
         const int lx = x - o.box_x, ly = y - o.box_y;
         if (lx < 0 || ly < 0 || lx >= o.size || ly >= o.size) continue;
         const int y0 = bounds[(o.row_off + ly) * 2], n = bounds[(o.row_off + ly) * 2 + 1];
@@ -85,6 +98,15 @@ __global__ void k_composite_frame(const sdn_composite_obj* __restrict__ objs, in
         int a0 = 1 << (PRECISION_BITS - 1);
         for (int j = 0; j < n; j++) a0 += (int)col[(size_t)j * o.size].x * k8[j];
         if (clip8(a0) < 128) continue;                                    // torch.round(v / 255) == 0
+        inst = (float)o.id;                                               // (1 - 1) * inst + 1 * id
+        top = mi;
+    }
+    if (top >= 0) {
+        const sdn_composite_obj o = objs[top];
+        const int lx = x - o.box_x, ly = y - o.box_y;
+        const int y0 = bounds[(o.row_off + ly) * 2], n = bounds[(o.row_off + ly) * 2 + 1];
+        const int* k8 = kk8 + o.k_off + (long)ly * o.ksize;
+        const uchar4* col = tmp8 + (size_t)o.tmp_off + (size_t)y0 * o.size + lx;
         int a1 = 1 << (PRECISION_BITS - 1), a2 = a1, a3 = a1;
         double ad = 0.0;
         const double* kd = kkd + o.k_off + (long)ly * o.ksize;
@@ -94,14 +116,11 @@ __global__ void k_composite_frame(const sdn_composite_obj* __restrict__ objs, in
             a1 += (int)c.y * k8[j]; a2 += (int)c.z * k8[j]; a3 += (int)c.w * k8[j];
             ad += (double)fcol[(size_t)j * o.size] * kd[j];
         }
-        inst = (float)o.id;
         n0 = __fdiv_rn((float)clip8(a1), 255.0f);                         // to_tensor: byte / 255
         n1 = __fdiv_rn((float)clip8(a2), 255.0f);
         n2 = __fdiv_rn((float)clip8(a3), 255.0f);
         dep = (float)ad;
-        break;
     }
-    const size_t at = (size_t)y * W + x, plane = (size_t)H * W;
     instance[at] = inst;
     if (normal) { normal[at] = n0; normal[plane + at] = n1; normal[2 * plane + at] = n2; }
     depth[at] = dep;
@@ -112,15 +131,19 @@ __global__ void k_composite_frame(const sdn_composite_obj* __restrict__ objs, in
 extern "C" int sdn_composite_scene(const sdn_composite_obj* objs, int M, const float* masks, const float* normals,
                                    const float* depth_maps, const float* zooms, int S, const int* bounds,
                                    const int* kk8, const double* kkd, void* tmp8, float* tmpf, int max_size, int H,
-                                   int W, float* instance, float* normal, float* depth, void* stream) {
-    if (M < 0 || S <= 0 || H <= 0 || W <= 0 || !instance || !depth || (normals == nullptr) != (normal == nullptr))
+                                   int W, const float* frame_masks, int n_rendered, float* instance, float* normal,
+                                   float* depth, void* stream) {
+    if (M < 0 || n_rendered < 0 || n_rendered > M || S <= 0 || H <= 0 || W <= 0 || !instance || !depth ||
+        (normals == nullptr) != (normal == nullptr))
         return SDN_E_ARG;
-    if (M > 0 && (!objs || !masks || !depth_maps || !zooms || !bounds || !kk8 || !kkd || !tmp8 || !tmpf ||
-                  max_size <= 0))
+    if (M > 0 && !objs) return SDN_E_ARG;
+    if (n_rendered > 0 && (!masks || !depth_maps || !zooms || !bounds || !kk8 || !kkd || !tmp8 || !tmpf ||
+                           max_size <= 0))
         return SDN_E_ARG;
+    if (n_rendered < M && !frame_masks) return SDN_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (M > 0) {
+    if (n_rendered > 0) {
         const dim3 grid((unsigned)(((long)S * max_size + 255) / 256), (unsigned)M);
         sdn_internal::launch_begin("k_composite_rows", st);
         k_composite_rows<<<grid, 256, 0, st>>>(objs, masks, normals, depth_maps, zooms, S, bounds, kk8, kkd,
@@ -129,6 +152,6 @@ extern "C" int sdn_composite_scene(const sdn_composite_obj* objs, int M, const f
     }
     sdn_internal::launch_begin("k_composite_frame", st);
     k_composite_frame<<<dim3((unsigned)((W + 127) / 128), (unsigned)H), 128, 0, st>>>(
-        objs, M, S, H, W, bounds, kk8, kkd, (const uchar4*)tmp8, tmpf, instance, normal, depth);
+        objs, M, S, H, W, bounds, kk8, kkd, (const uchar4*)tmp8, tmpf, frame_masks, instance, normal, depth);
     return sdn_internal::launch_end();
 }

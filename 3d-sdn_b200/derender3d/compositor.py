@@ -52,14 +52,18 @@ class _Obj(ctypes.Structure):
                 ('k_off', ctypes.c_longlong), ('tmp_off', ctypes.c_longlong)]
 
 
-def placement(zooms, center2ds, depths, interests, focal, u0, v0, render_size):
+def placement(zooms, center2ds, depths, interests, focal, u0, v0, render_size, keep_uninteresting=False):
     """Draw order (far to near, main.py:538) and the integer size / paste box of every interesting object, with the
-    reference's own float32 expressions (main.py:556-565).  Host tensors in -> list of (index, size, box_x, box_y)."""
+    reference's own float32 expressions (main.py:556-565).  Host tensors in -> list of (index, size, box_x, box_y);
+    with keep_uninteresting the objects that are not interesting stay in the list as (index, 0, 0, 0): they are
+    painted from their frame-resolution mask (main.py:601-604, the `operations is None` branch)."""
     zooms, center2ds, depths = zooms.detach().float().cpu(), center2ds.detach().float().cpu(), depths.detach().float().cpu()
     order = torch.sort(depths[:, 0], dim=0, descending=True)[1].tolist()
     out = []
     for i in order:
         if not bool(interests[i]):
+            if keep_uninteresting:
+                out.append((i, 0, 0, 0))
             continue
         size = int(render_size / zooms[i])
         bx = int(center2ds[i, 1] * focal + u0 - size // 2)
@@ -69,21 +73,32 @@ def placement(zooms, center2ds, depths, interests, focal, u0, v0, render_size):
 
 
 def compose_scene(masks, normals, depth_maps, zooms, center2ds, depths, interests, height, width, focal, u0, v0,
-                  render_size=None):
+                  render_size=None, image_masks=None, operations_given=True):
     """masks [N,1,S,S], normals [N,3,S,S] or None, depth_maps [N,1,S,S], zooms [N,1], center2ds [N,2], depths [N,1]
-    (CUDA tensors), interests [N] -> instance [1,H,W], normal [3,H,W] (or None), depth [1,H,W] on the same device."""
+    (CUDA tensors), interests [N] -> instance [1,H,W], normal [3,H,W] (or None), depth [1,H,W] on the same device.
+
+    `operations_given=False` is the reference's default test mode (`operations is None`, main.py:597-604): objects
+    that are not interesting are still painted into the INSTANCE map, in the same far-to-near order, from their
+    frame-resolution input masks `image_masks` [N,1,H,W] -- they get an instance id and occlude farther objects."""
     if not masks.is_cuda:
         raise sdn_b200.SdnError('compose_scene runs on CUDA tensors only (no CPU fallback)')
     dev = masks.device
     S = int(masks.shape[-1])
     render_size = S if render_size is None else render_size
     interests = torch.as_tensor(interests).cpu()
-    place = [p for p in placement(zooms, center2ds, depths, interests, focal, u0, v0, render_size) if p[1] > 0]
+    keep = not operations_given
+    if keep and image_masks is None:
+        raise sdn_b200.SdnError('compose_scene: operations_given=False needs image_masks [N,1,H,W] (main.py:601-604)')
+    place = [p for p in placement(zooms, center2ds, depths, interests, focal, u0, v0, render_size, keep)
+             if p[1] > 0 or (keep and not bool(interests[p[0]]))]
     objs = (_Obj * max(len(place), 1))()
     bounds, kkd, kk8 = [], [], []
     row_off = k_off = tmp_off = 0
     cache = {}
     for m, (i, size, bx, by) in enumerate(place):
+        if size == 0:               # mask-only entry: reads image_masks[i]
+            objs[m] = _Obj(i, 0, 0, 0, 0, i + 1, 0, 0, 0)
+            continue
         if size not in cache:
             cache[size] = resample_tables(S, size)
         b, kd, k8 = cache[size]
@@ -93,9 +108,13 @@ def compose_scene(masks, normals, depth_maps, zooms, center2ds, depths, interest
         k_off += kd.size
         tmp_off += S * size
     M = len(place)
-    t_bounds = torch.from_numpy(np.concatenate(bounds) if M else np.zeros((1, 2), np.int32)).to(dev)
-    t_kkd = torch.from_numpy(np.concatenate(kkd) if M else np.zeros(1)).to(dev)
-    t_kk8 = torch.from_numpy(np.concatenate(kk8) if M else np.zeros(1, np.int32)).to(dev)
+    n_rendered = len(bounds)
+    t_bounds = torch.from_numpy(np.concatenate(bounds) if n_rendered else np.zeros((1, 2), np.int32)).to(dev)
+    t_kkd = torch.from_numpy(np.concatenate(kkd) if n_rendered else np.zeros(1)).to(dev)
+    t_kk8 = torch.from_numpy(np.concatenate(kk8) if n_rendered else np.zeros(1, np.int32)).to(dev)
+    frame_masks = None
+    if n_rendered < M:
+        frame_masks = image_masks.detach().to(dev).float().reshape(-1, height, width).contiguous()
     t_objs = torch.frombuffer(bytearray(bytes(objs)), dtype=torch.uint8).to(dev)
     tmp8 = torch.empty(max(tmp_off, 1) * 4, dtype=torch.uint8, device=dev)
     tmpf = torch.empty(max(tmp_off, 1), dtype=torch.float32, device=dev)
@@ -107,11 +126,11 @@ def compose_scene(masks, normals, depth_maps, zooms, center2ds, depths, interest
     p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())           # noqa: E731
     lib = sdn_b200.lib()
     lib.sdn_composite_scene.argtypes = [ctypes.c_void_p] * 1 + [ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int] + \
-        [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 4
+        [ctypes.c_void_p] * 5 + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4
     with torch.cuda.device(dev):
         rc = lib.sdn_composite_scene(p(t_objs), M, p(masks), p(normals), p(depth_maps), p(zooms), S, p(t_bounds),
                                      p(t_kk8), p(t_kkd), p(tmp8), p(tmpf), max([q[1] for q in place] + [1]), height,
-                                     width, p(instance), p(normal), p(depth),
+                                     width, p(frame_masks), n_rendered, p(instance), p(normal), p(depth),
                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         raise sdn_b200.SdnError('sdn_composite_scene: %s (code %d)' % (lib.sdn_error_string(rc).decode(), rc))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDN_VERSION 100            /* 0.1.0 */
+#define SDN_VERSION 200            /* 0.2.0: sdn_composite_scene takes frame masks */
 
 /* what to render: rasterize.py:21-22 return_rgb / return_alpha / return_depth */
 #define SDN_RGB    1
@@ -173,7 +173,8 @@ int sdn_objects_backward(const sdn_objects* o, const float* grad_vertices, float
  * objs[] is sorted far to near.  All pointers are device pointers. */
 typedef struct sdn_composite_obj {
     int index;              /* row of masks / normals / depth_maps / zooms this object reads */
-    int size;               /* on-screen edge: int(render_size / zoom), main.py:556 */
+    int size;               /* on-screen edge: int(render_size / zoom), main.py:556; 0 = MASK-ONLY entry: `index` is a
+                               row of frame_masks, blended into the instance map alone (main.py:601-604) */
     int box_x, box_y;       /* paste position of the top-left corner (may be negative), main.py:562-565 */
     int ksize;              /* taps per output sample in the coefficient tables */
     int id;                 /* value written to the instance map: object index + 1, main.py:570 */
@@ -184,11 +185,15 @@ typedef struct sdn_composite_obj {
 
 /* masks [N,S,S], normals [N,3,S,S] or NULL (then normal must be NULL), depth_maps [N,S,S], zooms [N];
  * bounds [sum size][2] (first tap, count), kk8 / kkd [sum size*ksize]; tmp8: 4 bytes per intermediate pixel, tmpf:
- * one float; max_size = max objs[].size.  Out: instance [H,W], normal [3,H,W], depth [H,W] (backgrounds 0, 0.5, 1). */
+ * one float; max_size = max objs[].size.  frame_masks [*,H,W] (may be NULL when every entry is rendered): the
+ * frame-resolution masks of the mask-only entries -- objects that are not "interesting" still occlude and get an
+ * instance id when no edit operations are given (main.py:601-604); n_rendered = number of entries with size > 0.
+ * Out: instance [H,W], normal [3,H,W], depth [H,W] (backgrounds 0, 0.5, 1). */
 int sdn_composite_scene(const sdn_composite_obj* objs, int M, const float* masks, const float* normals,
                         const float* depth_maps, const float* zooms, int S, const int* bounds, const int* kk8,
-                        const double* kkd, void* tmp8, float* tmpf, int max_size, int H, int W, float* instance,
-                        float* normal, float* depth, void* stream);
+                        const double* kkd, void* tmp8, float* tmpf, int max_size, int H, int W,
+                        const float* frame_masks, int n_rendered, float* instance, float* normal, float* depth,
+                        void* stream);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long sdn_launch_count(void);

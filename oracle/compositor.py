@@ -87,9 +87,11 @@ def pil_resize_f32(a, out):
 
 
 def composite_reference(masks, normals, depth_maps, zooms, center2ds, depths, interests, height, width, focal, u0, v0,
-                        render_size):
-    """main.py:547-606 with operations given (only interesting objects are drawn), through torchvision + Pillow exactly
-    as the reference calls them.  CPU tensors in; -> instance map [1,H,W], normal map [3,H,W], depth map [1,H,W]."""
+                        render_size, image_masks=None, operations_given=True):
+    """main.py:547-606 through torchvision + Pillow exactly as the reference calls them.  With operations given only
+    interesting objects are drawn; with `operations_given=False` (the reference's default test mode, `operations is
+    None`) the others are blended into the instance map from their frame masks `image_masks` [N,1,H,W] (:601-604).
+    CPU tensors in; -> instance map [1,H,W], normal map [3,H,W], depth map [1,H,W]."""
     import PIL.Image
     import torchvision.transforms.functional as TF
     index_objs = torch.sort(depths[:, 0], dim=0, descending=True)[1]
@@ -98,6 +100,9 @@ def composite_reference(masks, normals, depth_maps, zooms, center2ds, depths, in
     dep = torch.full((1, height, width), 1.0)
     for index_obj in index_objs.tolist():
         if not bool(interests[index_obj]):
+            if not operations_given:                                      # main.py:601-604
+                image_mask = image_masks[index_obj].float()
+                inst = (1 - image_mask) * inst + image_mask * (1 + index_obj)
             continue
         size = int(render_size / zooms[index_obj])
         box = (int(center2ds[index_obj, 1] * focal + u0 - size // 2), int(center2ds[index_obj, 0] * focal + v0 - size // 2))

@@ -71,3 +71,40 @@ def test_composite_nothing_to_draw(dev):
     assert float(i.abs().max()) == 0 and torch.all(n == 0.5) and torch.all(d == 1.0)
     with pytest.raises(Exception):
         compose_scene(masks, normals, dmaps, zooms, center2ds, depths, none, 30, 50, 100.0, 24.5, 14.5, 32)   # CPU tensors
+
+
+@pytest.mark.parametrize('N,S,H,W,seed', [(7, 64, 75, 200, 11), (5, 48, 375, 1242, 12)])
+def test_composite_default_test_mode_paints_uninteresting_objects(dev, N, S, H, W, seed):
+    """`operations is None` (the reference's default test mode, main.py:597-604): an object that is not interesting is
+    still blended into the instance map from its frame-resolution input mask, in far-to-near order -- it gets an
+    instance id and occludes what lies behind it.  Normal / depth maps are unaffected by such objects."""
+    from derender3d.compositor import compose_scene
+    from oracle.compositor import composite_reference
+    focal, u0, v0 = 100.0 if W < 1000 else 725.0, W / 2.0 - 0.5, H / 2.0 - 0.5
+    masks, normals, dmaps, zooms, center2ds, depths, interests = _scene(N, S, seed, H, W, focal)
+    g = torch.Generator().manual_seed(seed + 100)
+    interests = (torch.rand(N, generator=g) > 0.4).to(torch.uint8)
+    interests[0], interests[1] = 1, 0
+    yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing='ij')
+    image_masks = []
+    for i in range(N):          # ground-truth style 0/1 masks around each object's centre
+        cy, cx = float(center2ds[i, 0]) * focal + v0, float(center2ds[i, 1]) * focal + u0
+        r = 0.25 * S / float(zooms[i])
+        image_masks.append((((yy - cy) / r) ** 2 + ((xx - cx) / (1.5 * r)) ** 2 <= 1).float()[None])
+    image_masks = torch.stack(image_masks)
+    sc = (masks, normals, dmaps, zooms, center2ds, depths, interests)
+    ref_i, ref_n, ref_d = composite_reference(*sc, H, W, focal, u0, v0, S, image_masks=image_masks,
+                                              operations_given=False)
+    edit_i, edit_n, edit_d = composite_reference(*sc, H, W, focal, u0, v0, S)
+    assert not torch.equal(ref_i, edit_i)                                 # the two modes differ on this scene
+    assert torch.equal(ref_n, edit_n) and torch.equal(ref_d, edit_d)
+    out_i, out_n, out_d = compose_scene(masks.to(dev), normals.to(dev), dmaps.to(dev), zooms.to(dev), center2ds.to(dev),
+                                        depths.to(dev), interests, H, W, focal, u0, v0, S,
+                                        image_masks=image_masks.to(dev), operations_given=False)
+    assert torch.equal(out_i.cpu(), ref_i)
+    assert torch.equal(out_n.cpu(), ref_n) and torch.equal(out_d.cpu(), ref_d)
+    ids = set(torch.unique(out_i).tolist())
+    assert any((i + 1.0) in ids for i in range(N) if not interests[i])    # an uninteresting object owns pixels
+    with pytest.raises(Exception):
+        compose_scene(masks.to(dev), normals.to(dev), dmaps.to(dev), zooms.to(dev), center2ds.to(dev), depths.to(dev),
+                      interests, H, W, focal, u0, v0, S, operations_given=False)      # needs image_masks
