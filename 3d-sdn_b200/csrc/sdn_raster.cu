@@ -1968,29 +1968,67 @@ __global__ void __launch_bounds__(LW * 32, 2) k_bwd_main(BwdParams P, Workspace 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Silhouette-only line sweep with a far-field expansion.  When only the alpha gradient exists (the reference's
-// training path, derender3d/models/__init__.py:203-208), the positive part of rasterize.py:628-631 is a per-pixel
-// weight w_j >= 0 that does NOT depend on the query, so a query's sum
-//        R = sum_{j=lo..hi} w_j / (k (j - xc) + e)
-// can be evaluated blockwise: for a block of 32 pixels centred at c whose distance from the crossing is >= 64 pixels,
-//        1 / (s + k d) = (1/s) sum_n (-k d / s)^n,   s = k (c - xc) + e,  d = j - c in [-15.5, 15.5]
-// so the block contributes (1/s) sum_n M_n x^n with x = -k/s and the block moments M_n = sum_j w_j d^n (n < 8).
-// |k d / s| <= 15.5/64, hence the truncation error of the nearest far block is <= 0.24^8/(1-0.24) = 1.5e-5 of its term
-// (smaller for all others); blocks nearer than 64 pixels, and the partially covered end blocks, are summed directly.
-// One warp per line: (1) weights of the whole line -> shared memory, (2) moments, one lane per block, (3) one lane per
-// query.  ~3-4x fewer instructions than the direct sweep; results are written once, deterministic.
+// Alpha (silhouette) out-sweeps by WELL-SEPARATED BLOCK MOMENTS.
+//
+// For an alpha pass the out-sweep only runs when the in-pixel belongs to the face (rasterize.py:601), so alpha_in == 1
+// and the positive part of rasterize.py:628-631, max(0, (alpha_j - 1) * g_j), is a per-pixel weight
+//        A_j = background_j ? max(0, -g_j) : 0
+// that does NOT depend on the query.  A query (crossing xc, slopes k_v, pads e_v, range = from the crossing to the
+// border of the line) needs  R_v = sum_j A_j / (k_v (j - xc) + e_v) = (dir / k_v) sum_j A_j / D_v(j),
+// D_v(j) = |j - xc| + |e_v / k_v| > 0.  The line is cut into a binary hierarchy of blocks (16, 32, 64, ... pixels);
+// every block keeps the first AM_P scaled moments  M_n = sum_j A_j ((j - c) / h)^n  about its centre c (h = half
+// width).  A block whose nearest pixel is at least two block sizes away from the crossing contributes
+//        sum_j A_j / (U + dir (j - c)) = (1 / U) sum_n M_n (-dir h / U)^n,      U = D_v(c),   h / U <= 0.2025,
+// truncated after AM_P = 8 terms: relative error of that block's (positive) term <= 0.2025^8 / (1 - 0.2025) = 3.6e-6.
+// Walking outwards from the crossing, a query therefore sums <= 47 pixels directly (the arithmetic of the direct
+// sweep: fma(k, t, e), hardware reciprocal) and then <= ~3 blocks per octave of distance: O(log L) work instead of
+// O(L).  One warp per raster line: (1) weights of the line -> shared memory, (2) level-0 moments, one lane per block,
+// (3) parents from children (binomial shift), (4) one lane per query.  Every result is written exactly once by one
+// lane in a fixed order: deterministic.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int FF_P = 8;             // terms of the expansion
-constexpr int FF_NEAR = 64;         // pixels: blocks whose centre is nearer than this to the crossing are summed directly
-constexpr int FF_LMAX = 4096;       // longest line the shared-memory layout supports
+constexpr int AM_P = 8;                 // moments per block
+constexpr int AM_LOG0 = 4;              // level-0 block: 16 pixels
+constexpr int AM_S0 = 1 << AM_LOG0;
+constexpr int AM_MAXLEV = 10;           // 16 ... 8192
+constexpr int AM_LMAX = 4096;           // longest line the shared-memory layout is sized for (else: direct sweep)
 
-__global__ void __launch_bounds__(LW * 32) k_line_sweep_ff(BwdParams P, Workspace ws, int lcap) {
-    extern __shared__ __align__(16) float s_ff[];
+__host__ __device__ constexpr float am_binom(int n, int k) {
+    float r = 1.0f;
+    for (int i = 1; i <= k; i++) r = r * (float)(n - k + i) / (float)i;
+    return r;
+}
+__host__ __device__ constexpr float am_pow(float x, int n) {
+    float r = 1.0f;
+    for (int i = 0; i < n; i++) r *= x;
+    return r;
+}
+// number of levels for a line of L pixels: the largest block that can ever be used has 3 s <= L
+inline int am_levels(int L) {
+    int lv = 1;
+    while (lv < AM_MAXLEV && 3 * (AM_S0 << lv) <= L) lv++;
+    return lv;
+}
+inline size_t am_smem_floats(int lcap, int levels) {
+    const int nb0 = lcap >> AM_LOG0;
+    return (size_t)(2 * nb0 + levels + 1) * AM_P;
+}
+
+// weight of sample j of the line: background ? max(0, -g) : 0   (alpha_in == 1, rasterize.py:601,628-631)
+__device__ __forceinline__ float am_weight(int idx, float g, float sc) { return idx < 0 ? fmaxf(-(g * sc), 0.0f) : 0.0f; }
+
+__global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace ws, int lcap, int levels) {
+    extern __shared__ __align__(16) float s_am[];
+    __shared__ int s_off[AM_MAXLEV + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wcap = lcap + lcap / 32 + 32;                 // skewed layout: pixel j lives at j + (j >> 5)
-    const int nbcap = lcap / 32 + 1;
-    float* s_w = s_ff + (size_t)warp * (wcap + FF_P * nbcap);
-    float* s_m = s_w + wcap;                                // moments [n][block]
+    const int nb0 = lcap >> AM_LOG0;
+    const int mcap = (2 * nb0 + levels + 1) * AM_P;
+    float* s_m = s_am + (size_t)warp * mcap;                // moments [level][block][n]
+    if (threadIdx.x == 0) {
+        int off = 0, nb = nb0;
+        for (int l = 0; l < levels; l++) { s_off[l] = off; off += nb * AM_P; nb = (nb + 1) >> 1; }
+        s_off[levels] = off;
+    }
+    __syncthreads();
     const int per_img = P.Hs + P.Ws;
     const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
     const int bundles = bundles_rows + bundles_cols;
@@ -2003,82 +2041,406 @@ __global__ void __launch_bounds__(LW * 32) k_line_sweep_ff(BwdParams P, Workspac
     const int qbeg = ws.scan_buf[line], qend = ws.scan_buf[line + 1];
     if (qbeg == qend) return;
     const int L = axis == 0 ? P.Hs : P.Ws;
-    const int nb = (L + 31) / 32;
-    const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+    const int nbl0 = (L + AM_S0 - 1) >> AM_LOG0;
     const float sc = (P.ss == 2) ? 0.25f : 1.0f;
     const float ea = (float)P.eps_a;
-    const float* ga_p = P.g_alpha ? P.g_alpha + (size_t)b * P.H * P.W : nullptr;
+    // sample j of the line lives at fim[j * fstep] and reads the upstream gradient at ga[(j / ss) * gstep]
+    const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws + (axis == 0 ? (size_t)d0 : (size_t)d0 * P.Ws);
+    const long fstep = axis == 0 ? P.Ws : 1;
+    const float* ga = P.g_alpha + (size_t)b * P.H * P.W +
+                      (axis == 0 ? (size_t)(P.H - 1) * P.W + d0 / P.ss : (size_t)(P.H - 1 - d0 / P.ss) * P.W);
+    const long gstep = axis == 0 ? -(long)P.W : 1;
+    const int ssh = P.ss == 2 ? 1 : 0;
 
-    // (1) weights of the line: w_j = max(0, (alpha_j - 1) * g_j) = background ? max(0, -g_j) : 0
-    for (int j0 = 0; j0 < nb * 32; j0 += 128) {
-        int idv[4];
-        float gv[4];
+    // (1) level-0 moments, one lane per block of 16 samples, straight from global memory (all loads first).
+    // Even / odd moments use the mirrored sums and differences: x_i = (i - 7.5) / 8 = -x_(15 - i).
+    for (int blk = lane; blk < nbl0; blk += 32) {
+        const int j0 = blk << AM_LOG0;
+        float w[AM_S0];
+        if (axis == 1 && j0 + AM_S0 <= L && (((size_t)(fim + j0)) & 15) == 0) {
+            const int4* ip = reinterpret_cast<const int4*>(fim + j0);
+            const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1), i2 = __ldg(ip + 2), i3 = __ldg(ip + 3);
+            const int id[16] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w, i3.x, i3.y, i3.z, i3.w};
+            if (ssh) {
+                const float4* gp = reinterpret_cast<const float4*>(ga + (j0 >> 1));
+                float g[8];
+                if ((((size_t)(ga + (j0 >> 1))) & 15) == 0) {
+                    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+                    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+                } else {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int j = min(j0 + u * 32 + lane, L - 1);
-            const int xi = axis == 0 ? d0 : j, yi = axis == 0 ? j : d0;
-            idv[u] = __ldg(fim + (size_t)yi * P.Ws + xi);
-            gv[u] = ga_p ? __ldg(ga_p + (size_t)(P.H - 1 - yi / P.ss) * P.W + xi / P.ss) : 0.0f;
-        }
+                    for (int i = 0; i < 8; i++) g[i] = __ldg(ga + (j0 >> 1) + i);
+                }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int j = j0 + u * 32 + lane;
-            if (j < nb * 32) s_w[j + (j >> 5)] = (j < L && idv[u] < 0) ? fmaxf(-(gv[u] * sc), 0.0f) : 0.0f;
+                for (int i = 0; i < AM_S0; i++) w[i] = am_weight(id[i], g[i >> 1], sc);
+            } else {
+                float g[16];
+#pragma unroll
+                for (int i = 0; i < AM_S0; i++) g[i] = __ldg(ga + j0 + i);
+#pragma unroll
+                for (int i = 0; i < AM_S0; i++) w[i] = am_weight(id[i], g[i], sc);
+            }
+        } else {
+            int id[AM_S0];
+            float g[AM_S0];
+#pragma unroll
+            for (int i = 0; i < AM_S0; i++) {
+                const int j = min(j0 + i, L - 1);
+                id[i] = __ldg(fim + (long)j * fstep);
+                g[i] = __ldg(ga + (long)(j >> ssh) * gstep);
+            }
+#pragma unroll
+            for (int i = 0; i < AM_S0; i++) w[i] = (j0 + i < L) ? am_weight(id[i], g[i], sc) : 0.0f;
         }
+        float m[AM_P];
+#pragma unroll
+        for (int n = 0; n < AM_P; n++) m[n] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < AM_S0 / 2; i++) {
+            const float sp = w[AM_S0 - 1 - i] + w[i], sm = w[AM_S0 - 1 - i] - w[i];     // x of the upper sample is +|x|
+#pragma unroll
+            for (int n = 0; n < AM_P; n++) {
+                const float xp = am_pow((0.5f * (AM_S0 - 1) - (float)i) / (0.5f * AM_S0), n);
+                m[n] = __fmaf_rn((n & 1) ? sm : sp, xp, m[n]);
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(s_m + blk * AM_P);
+        o[0] = make_float4(m[0], m[1], m[2], m[3]); o[1] = make_float4(m[4], m[5], m[6], m[7]);
     }
     __syncwarp();
-    // (2) block moments, one lane per block (the skew makes the 32 lanes hit 32 different banks)
-    for (int blk = lane; blk < nb; blk += 32) {
-        float m[FF_P];
+    // (2) parents: x_parent = (y_child -+ 1) / 2  ->  M_n = 2^-n sum_k C(n,k) (-+1)^(n-k) m_k
+    {
+        int nb = nbl0;
+        for (int l = 1; l < levels; l++) {
+            const int nbc = nb;
+            nb = (nb + 1) >> 1;
+            const float* src = s_m + s_off[l - 1];
+            float* dst = s_m + s_off[l];
+            for (int blk = lane; blk < nb; blk += 32) {
+                float cl[AM_P], cr[AM_P];
+                const float4* pl = reinterpret_cast<const float4*>(src + (2 * blk) * AM_P);
+                const float4 l0 = pl[0], l1 = pl[1];
+                cl[0] = l0.x; cl[1] = l0.y; cl[2] = l0.z; cl[3] = l0.w; cl[4] = l1.x; cl[5] = l1.y; cl[6] = l1.z; cl[7] = l1.w;
+                if (2 * blk + 1 < nbc) {
+                    const float4 r0 = pl[2], r1 = pl[3];
+                    cr[0] = r0.x; cr[1] = r0.y; cr[2] = r0.z; cr[3] = r0.w; cr[4] = r1.x; cr[5] = r1.y; cr[6] = r1.z; cr[7] = r1.w;
+                } else {
 #pragma unroll
-        for (int n = 0; n < FF_P; n++) m[n] = 0.0f;
-        const float* wp = s_w + blk * 33;
-#pragma unroll 4
-        for (int i = 0; i < 32; i++) {
-            const float w = wp[i], d = (float)i - 15.5f;
-            float t = w;
+                    for (int n = 0; n < AM_P; n++) cr[n] = 0.0f;
+                }
+                // sums and differences of the two children halve the work: even (n-k) terms take (cr + cl), odd (cr - cl)
+                float se[AM_P], so[AM_P];
 #pragma unroll
-            for (int n = 0; n < FF_P; n++) { m[n] += t; t *= d; }
+                for (int n = 0; n < AM_P; n++) { se[n] = cr[n] + cl[n]; so[n] = cr[n] - cl[n]; }
+                float m[AM_P];
+#pragma unroll
+                for (int n = 0; n < AM_P; n++) {
+                    float a = 0.0f;
+#pragma unroll
+                    for (int k = 0; k <= n; k++)
+                        a = __fmaf_rn(am_binom(n, k) * am_pow(0.5f, n), ((n - k) & 1) ? so[k] : se[k], a);
+                    m[n] = a;
+                }
+                float4* o = reinterpret_cast<float4*>(dst + blk * AM_P);
+                o[0] = make_float4(m[0], m[1], m[2], m[3]); o[1] = make_float4(m[4], m[5], m[6], m[7]);
+            }
+            __syncwarp();
         }
-#pragma unroll
-        for (int n = 0; n < FF_P; n++) s_m[n * nbcap + blk] = m[n];
     }
-    __syncwarp();
     // (3) one lane per query
     for (int qk = qbeg + lane; qk < qend; qk += 32) {
         const int qi = ws.line_items[qk];
         const Query q = ws.queries[qi];
         const int lo = q.lo, hi = q.hi_flags & 0xffff;
-        float res[2] = {0.0f, 0.0f};
+        const bool use0 = (q.hi_flags & QF_USE0) != 0, use1 = (q.hi_flags & QF_USE1) != 0;
+        const float e0 = (q.hi_flags & QF_POS0) ? ea : -ea, e1 = (q.hi_flags & QF_POS1) ? ea : -ea;
+        const int dir = (hi == L - 1) ? 1 : -1;                    // the sweep always ends at a border of the line
+        const float fdir = (float)dir;
+        const float p0 = use0 ? fabsf(__fdiv_rn(e0, q.k0)) : 0.0f, p1 = use1 ? fabsf(__fdiv_rn(e1, q.k1)) : 0.0f;
+        float near0 = 0.0f, near1 = 0.0f;       // sum A_j / dist_v(j), samples next to the crossing
+        float far0 = 0.0f, far1 = 0.0f;         // sum A_j / D_v(j), well-separated blocks
+        int pos = dir > 0 ? lo : hi;
+        int n = hi - lo + 1;
+        // direct samples until the position is block-aligned and two level-0 blocks away: their count is known up front
+        {
+            const float tt0 = fabsf((float)pos - q.xc);
+            int nd = 0;
+            for (;;) {      // <= 3 iterations: advance to the first aligned position that is far enough
+                const int al = dir > 0 ? pos + nd : pos - nd + 1;
+                const int pad = (dir > 0 ? -al : al) & (AM_S0 - 1);
+                nd += pad;
+                if (tt0 + (float)nd >= (float)(2 * AM_S0) || nd >= n) break;
+                nd += AM_S0;
+            }
+            nd = min(nd, n);
+            for (int i0 = 0; i0 < nd; i0 += 4) {        // four samples per trip: their loads fly together
+                int id[4];
+                float g[4];
 #pragma unroll
-        for (int v = 0; v < 2; v++) {
-            if (!(q.hi_flags & (v == 0 ? QF_USE0 : QF_USE1))) continue;
-            const float k = v == 0 ? q.k0 : q.k1;
-            const float e = (q.hi_flags & (v == 0 ? QF_POS0 : QF_POS1)) ? ea : -ea;
-            float sum = 0.0f;
-            for (int blk = lo >> 5; blk <= (hi >> 5); blk++) {
-                const int j0 = blk * 32, j1 = j0 + 31;
-                const float c = (float)j0 + 15.5f;
-                const bool whole = lo <= j0 && hi >= j1;
-                if (whole && fabsf(c - q.xc) >= (float)FF_NEAR) {
-                    const float s = __fmaf_rn(k, c - q.xc, e);
-                    const float r = rcp_approx(s), x = -k * r;
-                    float a = s_m[(FF_P - 1) * nbcap + blk];
+                for (int u = 0; u < 4; u++) {
+                    const int j = pos + dir * min(i0 + u, nd - 1);
+                    id[u] = __ldg(fim + (long)j * fstep);
+                    g[u] = __ldg(ga + (long)(j >> ssh) * gstep);
+                }
 #pragma unroll
-                    for (int n = FF_P - 2; n >= 0; n--) a = __fmaf_rn(a, x, s_m[n * nbcap + blk]);
-                    sum = __fmaf_rn(a, r, sum);
-                } else {
-                    const int a0 = max(lo, j0), a1 = min(hi, j1);
-                    const float* wp = s_w + blk * 33 - j0;
-                    for (int j = a0; j <= a1; j++) {
-                        const float w = wp[j];
-                        if (w != 0.0f) sum = __fmaf_rn(w, rcp_approx(__fmaf_rn(k, (float)j - q.xc, e)), sum);
-                    }
+                for (int u = 0; u < 4; u++) {
+                    // a trip's spare slots repeat the last sample with weight 0 (its distance is never zero)
+                    const float w = (i0 + u < nd) ? am_weight(id[u], g[u], sc) : 0.0f;
+                    const float tt = (float)(pos + dir * min(i0 + u, nd - 1)) - q.xc;
+                    const float d0v = __fmaf_rn(q.k0, tt, e0), d1v = __fmaf_rn(q.k1, tt, e1);
+                    const float r = rcp_approx(d0v * d1v) * w;
+                    near0 = __fmaf_rn(r, d1v, near0); near1 = __fmaf_rn(r, d0v, near1);
                 }
             }
-            res[v] = -sum;              // g -= diff / dist   (rasterize.py:648,653)
+            pos += dir * nd; n -= nd;
         }
-        ws.qres[qi] = make_float2(res[0], res[1]);
+        while (n > 0) {                          // blocks: the largest aligned one that is two sizes away
+            const float att = fabsf((float)pos - q.xc);
+            const int al = dir > 0 ? pos : pos + 1;
+            int lv = min(__ffs(al) - 1 - AM_LOG0, ((__float_as_int(att) >> 23) - 127) - (AM_LOG0 + 1));
+            lv = min(lv, levels - 1);
+            const int s = AM_S0 << lv;
+            const int blk = (dir > 0 ? pos : pos - s + 1) >> (AM_LOG0 + lv);
+            const float4* mp = reinterpret_cast<const float4*>(s_m + s_off[lv] + blk * AM_P);
+            const float4 m0 = mp[0], m1 = mp[1];
+            const float half = 0.5f * (float)(s - 1);
+            const float U0 = att + half + p0, U1 = att + half + p1;
+            const float r = rcp_approx(U0 * U1);
+            const float i0 = r * U1, i1 = r * U0;
+            const float hz = -fdir * (float)(s >> 1);
+            const float z0 = hz * i0, z1 = hz * i1;
+            float a0 = m1.w, a1 = m1.w;
+            a0 = __fmaf_rn(a0, z0, m1.z); a1 = __fmaf_rn(a1, z1, m1.z);
+            a0 = __fmaf_rn(a0, z0, m1.y); a1 = __fmaf_rn(a1, z1, m1.y);
+            a0 = __fmaf_rn(a0, z0, m1.x); a1 = __fmaf_rn(a1, z1, m1.x);
+            a0 = __fmaf_rn(a0, z0, m0.w); a1 = __fmaf_rn(a1, z1, m0.w);
+            a0 = __fmaf_rn(a0, z0, m0.z); a1 = __fmaf_rn(a1, z1, m0.z);
+            a0 = __fmaf_rn(a0, z0, m0.y); a1 = __fmaf_rn(a1, z1, m0.y);
+            a0 = __fmaf_rn(a0, z0, m0.x); a1 = __fmaf_rn(a1, z1, m0.x);
+            far0 = __fmaf_rn(a0, i0, far0); far1 = __fmaf_rn(a1, i1, far1);
+            pos += dir * s; n -= s;
+        }
+        // 1 / dist_v = dir / (k_v D_v);   g -= diff / dist   (rasterize.py:648,653)
+        const float r0 = use0 ? -(near0 + fdir * __fdiv_rn(far0, q.k0)) : 0.0f;
+        const float r1 = use1 ? -(near1 + fdir * __fdiv_rn(far1, q.k1)) : 0.0f;
+        ws.qres[qi] = make_float2(r0, r1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Colour (rgb / normal) out-sweeps at 2x SSAA, pairwise but lean.  The positive part of rasterize.py:632-635,
+//        max(0, D_j - c_in . g_j),      D_j = c_j . g_j,
+// depends on the query through c_in (the colour of the face that owns the in-pixel), so it cannot be tabulated per
+// line; what CAN be shared is everything that does not depend on the sample inside an OUTPUT pixel: with 2x SSAA the
+// two samples (2o, 2o+1) of an output pixel o on a line read the same upstream gradient g_o, so c_in . g_o is computed
+// once per output pixel, and where both samples are background (D equal) the two distances fold into one reciprocal:
+//        1/(u - 1/2) + 1/(u + 1/2) = 2u / (u^2 - 1/4),        u = (2o + 1/2 - xc) + e_v / k_v
+// (for |u| >= 160 the 1/4 is dropped: relative error <= 1e-5).  Distances are kept in unit-slope form
+// dist_v = k_v ((j - xc) + e_v / k_v); the 1 / k_v is applied once per query.  The two vertex distances of a sample
+// share one hardware reciprocal, r = 1 / (d0 d1), 1/d0 = r d1, 1/d1 = r d0.  Packed FP32x2 arithmetic throughout
+// (two output pixels per instruction).  One warp per raster line, passes of 32 x OP output pixels in registers, the
+// line's queries looped inside a pass; per-lane partial sums in shared memory, reduced once per query chunk in lane
+// order -- no atomics, every result written once: deterministic.
+// ------------------------------------------------------------------------------------------------------------
+struct __align__(16) QueryR {
+    int lo, hi, flags;
+    float xc, s0, s1, nc0, nc1, nc2, ik0, ik1;
+    float pad_;
+};
+constexpr float RGB_FAR = 160.0f;       // samples: beyond this distance 2u/(u^2 - 1/4) -> 2/u
+
+template <int OP, int LQ>
+__global__ void __launch_bounds__(LW * 32, 2) k_line_rgb(BwdParams P, Workspace ws, int accumulate) {
+    extern __shared__ __align__(16) unsigned char s_line_dyn[];
+    float2 (*s_acc)[LQ][33] = reinterpret_cast<float2 (*)[LQ][33]>(s_line_dyn);
+    __shared__ QueryR s_q[LW][LQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_img = P.Hs + P.Ws;
+    const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
+    const int bundles = bundles_rows + bundles_cols;
+    const int b = blockIdx.x / bundles, bi = blockIdx.x % bundles;
+    int axis, d0;
+    if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
+    else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
+    const int line = b * per_img + (axis == 0 ? P.Hs : 0) + d0;
+    if (bwd_overflow(ws)) return;
+    const int qbeg = ws.scan_buf[line], qend = ws.scan_buf[line + 1];
+    if (qbeg == qend) return;
+    const int L = axis == 0 ? P.Hs : P.Ws;          // samples on the line (even: ss == 2)
+    const int Lo = L >> 1;                           // output pixels on the line
+    const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws;
+    const float sc = 0.25f;
+    float bg[3];
+    if (P.bg_b) { bg[0] = P.bg_b[b * 3]; bg[1] = P.bg_b[b * 3 + 1]; bg[2] = P.bg_b[b * 3 + 2]; }
+    else { bg[0] = P.bg[0]; bg[1] = P.bg[1]; bg[2] = P.bg[2]; }
+    const float er = (float)P.eps_r;
+    const size_t plane = (size_t)P.H * P.W;
+    const float* gr_p = P.g_rgb + (size_t)b * 3 * plane;
+    constexpr int OP2 = OP / 2;
+    constexpr int PASS_O = 32 * OP;                  // output pixels per pass
+    constexpr int PASS_S = 2 * PASS_O;               // samples per pass
+
+    for (int qchunk = qbeg; qchunk < qend; qchunk += LQ) {
+        const int qn = min(LQ, qend - qchunk);
+        int ulo = 0x7fffffff, uhi = -1;
+        for (int k = lane; k < qn; k += 32) {
+            const Query q = ws.queries[ws.line_items[qchunk + k]];
+            QueryR x;
+            x.lo = q.lo; x.hi = q.hi_flags & 0xffff; x.flags = q.hi_flags;
+            x.xc = q.xc; x.nc0 = -q.c0; x.nc1 = -q.c1; x.nc2 = -q.c2;
+            const bool u0 = (q.hi_flags & QF_USE0) != 0, u1 = (q.hi_flags & QF_USE1) != 0;
+            const float e0 = (q.hi_flags & QF_POS0) ? er : -er, e1 = (q.hi_flags & QF_POS1) ? er : -er;
+            // unit-slope pads e_v / k_v; an unused vertex borrows the other one's (finite, same sign; result dropped)
+            float s0 = u0 ? __fdiv_rn(e0, q.k0) : 0.0f, s1 = u1 ? __fdiv_rn(e1, q.k1) : 0.0f;
+            if (!u0) s0 = u1 ? s1 : ((x.hi == L - 1) ? 1.0f : -1.0f);
+            if (!u1) s1 = s0;
+            x.s0 = s0; x.s1 = s1;
+            x.ik0 = u0 ? __fdiv_rn(1.0f, q.k0) : 0.0f; x.ik1 = u1 ? __fdiv_rn(1.0f, q.k1) : 0.0f;
+            s_q[warp][k] = x;
+            ulo = min(ulo, x.lo); uhi = max(uhi, x.hi);
+        }
+#pragma unroll 4
+        for (int k = 0; k < LQ; k++) s_acc[warp][k][lane] = make_float2(0.0f, 0.0f);
+        __syncwarp();
+        ulo = __reduce_min_sync(FULL, ulo); uhi = __reduce_max_sync(FULL, uhi);
+
+        for (int sbase = (ulo / PASS_S) * PASS_S; sbase <= uhi; sbase += PASS_S) {
+            // ---- records of this pass.  Output pixel o = sbase/2 + i*32 + lane owns samples 2o, 2o+1; pairs (i, i+1)
+            // of output pixels are packed in one float2.  All loads are issued before anything is consumed.
+            float2 G0[OP2], G1[OP2], G2[OP2], DA[OP2], DB[OP2];
+            bool mybg = true;
+            {
+                int ia[OP], ib[OP];
+                float r0[OP], r1[OP], r2[OP];
+                const int obase = sbase >> 1;
+#pragma unroll
+                for (int i = 0; i < OP; i++) {
+                    const int o = min(obase + i * 32 + lane, Lo - 1);
+                    if (axis == 1) {
+                        const int2 v = __ldg(reinterpret_cast<const int2*>(fim + (size_t)d0 * P.Ws + 2 * o));
+                        ia[i] = v.x; ib[i] = v.y;
+                    } else {
+                        ia[i] = __ldg(fim + (size_t)(2 * o) * P.Ws + d0);
+                        ib[i] = __ldg(fim + (size_t)(2 * o + 1) * P.Ws + d0);
+                    }
+                    const size_t oi = axis == 1 ? (size_t)(P.H - 1 - (d0 >> 1)) * P.W + o
+                                                : (size_t)(P.H - 1 - o) * P.W + (d0 >> 1);
+                    r0[i] = __ldg(gr_p + oi); r1[i] = __ldg(gr_p + plane + oi); r2[i] = __ldg(gr_p + 2 * plane + oi);
+                }
+#pragma unroll
+                for (int i = 0; i < OP; i++) {
+                    const int o = obase + i * 32 + lane;
+                    float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, dA = 0.0f, dB = 0.0f;
+                    if (o < Lo) {
+                        g0 = r0[i] * sc; g1 = r1[i] * sc; g2 = r2[i] * sc;
+                        const int xa = axis == 1 ? 2 * o : d0, ya = axis == 1 ? d0 : 2 * o;
+                        const int xb = axis == 1 ? 2 * o + 1 : d0, yb = axis == 1 ? d0 : 2 * o + 1;
+                        float c[3];
+                        colour_at(P, b, (size_t)b * P.Hs * P.Ws + (size_t)ya * P.Ws + xa, ia[i], bg, c);
+                        dA = __fmaf_rn(c[0], g0, __fmaf_rn(c[1], g1, c[2] * g2));
+                        if (ib[i] == ia[i] && P.ts < 2) dB = dA;
+                        else {
+                            colour_at(P, b, (size_t)b * P.Hs * P.Ws + (size_t)yb * P.Ws + xb, ib[i], bg, c);
+                            dB = __fmaf_rn(c[0], g0, __fmaf_rn(c[1], g1, c[2] * g2));
+                        }
+                        if (ia[i] >= 0 || ib[i] >= 0) mybg = false;
+                    } else mybg = false;
+                    if (i & 1) { G0[i / 2].y = g0; G1[i / 2].y = g1; G2[i / 2].y = g2; DA[i / 2].y = dA; DB[i / 2].y = dB; }
+                    else { G0[i / 2].x = g0; G1[i / 2].x = g1; G2[i / 2].x = g2; DA[i / 2].x = dA; DB[i / 2].x = dB; }
+                }
+            }
+            const bool allbg = __all_sync(FULL, mybg);      // every sample of the pass is background (and on the line)
+            const float jbase = (float)(sbase + 2 * lane);   // first sample of this lane's first output pixel
+            const int pass_hi = sbase + PASS_S - 1;
+            for (int k = 0; k < qn; k++) {
+                const int lo = s_q[warp][k].lo, hi = s_q[warp][k].hi;       // broadcast reads
+                if (hi < sbase || lo > pass_hi) continue;
+                const QueryR q = s_q[warp][k];
+                const bool full = (lo <= sbase) && (hi >= pass_hi);
+                const float2 nc0 = f2(q.nc0), nc1 = f2(q.nc1), nc2 = f2(q.nc2);
+                // signed unit-slope offset of the pair's first sample: (j - xc), elements 64 samples apart
+                float2 tt = make_float2(jbase - q.xc, (jbase + 64.0f) - q.xc);
+                float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+                if (full && allbg) {
+                    // nearest sample of the pass to the crossing
+                    const float near = fminf(fabsf((float)sbase - q.xc), fabsf((float)pass_hi - q.xc));
+                    float2 u0 = __fadd2_rn(tt, f2(0.5f + q.s0)), u1 = __fadd2_rn(tt, f2(0.5f + q.s1));
+                    if (near >= RGB_FAR) {
+#pragma unroll
+                        for (int m = 0; m < OP2; m++) {
+                            float2 x = __fmul2_rn(nc0, G0[m]);
+                            x = __ffma2_rn(nc1, G1[m], x);
+                            x = __ffma2_rn(nc2, G2[m], x);
+                            const float2 v = relu2(__fadd2_rn(DA[m], x));
+                            const float2 a = __fmul2_rn(v, rcp2(__fmul2_rn(u0, u1)));
+                            a0 = __ffma2_rn(a, u1, a0);
+                            a1 = __ffma2_rn(a, u0, a1);
+                            u0 = __fadd2_rn(u0, f2(128.0f)); u1 = __fadd2_rn(u1, f2(128.0f));
+                        }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < OP2; m++) {
+                            float2 x = __fmul2_rn(nc0, G0[m]);
+                            x = __ffma2_rn(nc1, G1[m], x);
+                            x = __ffma2_rn(nc2, G2[m], x);
+                            const float2 v = relu2(__fadd2_rn(DA[m], x));
+                            const float2 p0 = __ffma2_rn(u0, u0, f2(-0.25f)), p1 = __ffma2_rn(u1, u1, f2(-0.25f));
+                            const float2 a = __fmul2_rn(v, rcp2(__fmul2_rn(p0, p1)));
+                            a0 = __ffma2_rn(a, __fmul2_rn(u0, p1), a0);
+                            a1 = __ffma2_rn(a, __fmul2_rn(u1, p0), a1);
+                            u0 = __fadd2_rn(u0, f2(128.0f)); u1 = __fadd2_rn(u1, f2(128.0f));
+                        }
+                    }
+                    a0 = __fadd2_rn(a0, a0); a1 = __fadd2_rn(a1, a1);       // two samples per output pixel
+                } else {
+                    const float2 s0 = f2(q.s0), s1 = f2(q.s1);
+#pragma unroll
+                    for (int m = 0; m < OP2; m++) {
+                        // iteration m covers the 128 contiguous samples [sbase + 128 m, +127] across the warp: skip it,
+                        // run it unmasked, or (the one span holding the end of the range) run it masked -- warp-uniform
+                        const int span_lo = sbase + 128 * m, span_hi = span_lo + 127;
+                        if (hi >= span_lo && lo <= span_hi) {
+                            float2 x = __fmul2_rn(nc0, G0[m]);
+                            x = __ffma2_rn(nc1, G1[m], x);
+                            x = __ffma2_rn(nc2, G2[m], x);
+                            const float2 pA = relu2(__fadd2_rn(DA[m], x)), pB = relu2(__fadd2_rn(DB[m], x));
+                            const float2 dA0 = __fadd2_rn(tt, s0), dA1 = __fadd2_rn(tt, s1);
+                            const float2 dB0 = __fadd2_rn(dA0, f2(1.0f)), dB1 = __fadd2_rn(dA1, f2(1.0f));
+                            float2 aA = __fmul2_rn(pA, rcp2(__fmul2_rn(dA0, dA1)));
+                            float2 aB = __fmul2_rn(pB, rcp2(__fmul2_rn(dB0, dB1)));
+                            if (lo > span_lo || hi < span_hi) {
+                                // drop the samples outside [lo, hi].  The QUOTIENT is zeroed, not the numerator: on the
+                                // far side of the crossing t + s_v can be exactly 0 (0 * inf = NaN)
+                                const int jA0 = span_lo + 2 * lane, jA1 = jA0 + 64;
+                                if (jA0 < lo || jA0 > hi) aA.x = 0.0f;
+                                if (jA0 + 1 < lo || jA0 + 1 > hi) aB.x = 0.0f;
+                                if (jA1 < lo || jA1 > hi) aA.y = 0.0f;
+                                if (jA1 + 1 < lo || jA1 + 1 > hi) aB.y = 0.0f;
+                            }
+                            a0 = __ffma2_rn(aA, dA1, a0); a0 = __ffma2_rn(aB, dB1, a0);
+                            a1 = __ffma2_rn(aA, dA0, a1); a1 = __ffma2_rn(aB, dB0, a1);
+                        }
+                        tt = __fadd2_rn(tt, f2(128.0f));
+                    }
+                }
+                float2 v = s_acc[warp][k][lane];
+                v.x += a0.x + a0.y; v.y += a1.x + a1.y;
+                s_acc[warp][k][lane] = v;
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < qn; k += 32) {   // one lane reduces query k over the 32 per-lane partials, in lane order
+            float r0 = 0.0f, r1 = 0.0f;
+#pragma unroll 8
+            for (int l = 0; l < 32; l++) { const float2 v = s_acc[warp][k][l]; r0 += v.x; r1 += v.y; }
+            const QueryR q = s_q[warp][k];
+            // dist_v = k_v (t + s_v);   g -= diff / dist   (rasterize.py:648,653)
+            float2 o = make_float2((q.flags & QF_USE0) ? -(r0 * q.ik0) : 0.0f, (q.flags & QF_USE1) ? -(r1 * q.ik1) : 0.0f);
+            const int qi = ws.line_items[qchunk + k];
+            if (accumulate) { const float2 p = ws.qres[qi]; o.x += p.x; o.y += p.y; }
+            ws.qres[qi] = o;
+        }
+        __syncwarp();
     }
 }
 
@@ -2414,20 +2776,43 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
             else if (lmode == LM_SPLIT) SDN_LAUNCH_MAIN(LM_SPLIT);
             else SDN_LAUNCH_MAIN(LM_SINGLE);
         } else {
-            // fast_math == 2 asks for the far-field variant of the silhouette-only sweep.  Measured: 10 % faster than the
-            // direct sweep on ShapeNet-sized meshes at 384x384, 10 % slower on config 2b -- so it is opt-in.
+            // SDN_LINE_OLD=1: the round-1 direct sweeps (A/B measurements); default: block moments for the alpha term,
+            // the lean paired sweep for the colour term (2x SSAA), the direct sweep for what neither covers
+            static const bool old_line = getenv("SDN_LINE_OLD") != nullptr;
             const int lmax = max(P.Hs, P.Ws);
-            if (lmode == LM_ALPHA && g->fast_math == 2 && lmax <= FF_LMAX) {
-                // silhouette only: far-field line sweep (block moments); shared memory sized for the longest line
-                const int lcap = (lmax + 31) / 32 * 32;
-                const size_t fsmem = sizeof(float) * LW * ((size_t)lcap + lcap / 32 + 32 + (size_t)FF_P * (lcap / 32 + 1));
-                allow_smem_once(k_line_sweep_ff, fsmem);
-                timing_begin("k_line_sweep_ff", st);
-                k_line_sweep_ff<<<lgrid, LW * 32, fsmem, st>>>(P, ws, lcap);
+            const bool alpha_moments = !old_line && lmax <= AM_LMAX && (lmode == LM_ALPHA || lmode == LM_SPLIT);
+            const bool rgb_pairs = !old_line && P.ss == 2 && P.use_rgb && P.g_rgb &&
+                                   (lmode == LM_SPLIT || (lmode == LM_SINGLE && (P.split || !P.use_alpha)));
+            if (lmode == LM_SPLIT && alpha_moments != rgb_pairs) {
+                SDN_LINE_VARIANTS(LM_SPLIT);                    // one of the two halves is unavailable: direct split sweep
+            } else {
+                if (alpha_moments) {
+                    const int lcap = (lmax + AM_S0 - 1) / AM_S0 * AM_S0;
+                    const int levels = am_levels(lmax);
+                    const size_t asmem = sizeof(float) * LW * am_smem_floats(lcap, levels);
+                    allow_smem_once(k_line_alpha, asmem);
+                    timing_begin("k_line_alpha", st);
+                    k_line_alpha<<<lgrid, LW * 32, asmem, st>>>(P, ws, lcap, levels);
+                    if (rgb_pairs && (rc = check_launch())) return rc;
+                }
+                if (rgb_pairs) {
+                    static const int op = getenv("SDN_RGB_OP") ? atoi(getenv("SDN_RGB_OP")) : 8;
+                    const size_t lsmem = sizeof(float2) * LW * 32 * 33;
+                    if (op == 4) {
+                        allow_smem_once(k_line_rgb<4, 32>, lsmem);
+                        timing_begin("k_line_rgb", st);
+                        k_line_rgb<4, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                    } else {
+                        allow_smem_once(k_line_rgb<8, 32>, lsmem);
+                        timing_begin("k_line_rgb", st);
+                        k_line_rgb<8, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                    }
+                }
+                if (!alpha_moments && !rgb_pairs) {
+                    if (lmode == LM_ALPHA) SDN_LINE_VARIANTS(LM_ALPHA);
+                    else SDN_LINE_VARIANTS(LM_SINGLE);
+                }
             }
-            else if (lmode == LM_ALPHA) SDN_LINE_VARIANTS(LM_ALPHA);
-            else if (lmode == LM_SPLIT) SDN_LINE_VARIANTS(LM_SPLIT);
-            else SDN_LINE_VARIANTS(LM_SINGLE);
         }
         if ((rc = check_launch())) return rc;
         timing_begin("k_face_sums", st);
