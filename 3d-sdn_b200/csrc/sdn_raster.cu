@@ -1890,12 +1890,12 @@ __device__ __forceinline__ void line_role(const BwdParams& P, const Workspace& w
 #pragma unroll
                     for (int m = 0; m < LP2; m++) {
                         const float2 da0 = __ffma2_rn(k0, t, e0a), da1 = __ffma2_rn(k1, t, e1a);
-                        const float2 r = rcp2(__fmul2_rn(da0, da1));
-                        float2 pm = pa[m];
-                        if (!full) {
+                        float2 r = rcp2(__fmul2_rn(da0, da1));
+                        const float2 pm = pa[m];
+                        if (!full) {        // the RECIPROCAL is zeroed: past the crossing a distance can be exactly 0
                             const int j0 = pbase + (2 * m) * 32 + lane, j1 = j0 + 32;
-                            if (j0 < lo || j0 > hi) pm.x = 0.0f;
-                            if (j1 < lo || j1 > hi) pm.y = 0.0f;
+                            if (j0 < lo || j0 > hi) r.x = 0.0f;
+                            if (j1 < lo || j1 > hi) r.y = 0.0f;
                         }
                         const float2 pr_ = __fmul2_rn(pm, r);
                         a0 = __ffma2_rn(pr_, da1, a0);
@@ -1910,22 +1910,26 @@ __device__ __forceinline__ void line_role(const BwdParams& P, const Workspace& w
                         float2 dr = __ffma2_rn(nc0, g0v[m], D[m]);
                         dr = __ffma2_rn(nc1, g1v[m], dr);
                         dr = __ffma2_rn(nc2, g2v[m], dr);
-                        float2 pr = relu2(dr);
-                        float2 pm = pa[m];
-                        if (!full) {        // boundary pass: drop the pixels outside [lo, hi]
-                            const int j0 = pbase + (2 * m) * 32 + lane, j1 = j0 + 32;
-                            if (j0 < lo || j0 > hi) { pm.x = 0.0f; pr.x = 0.0f; }
-                            if (j1 < lo || j1 > hi) { pm.y = 0.0f; pr.y = 0.0f; }
-                        }
+                        const float2 pr = relu2(dr);
+                        const float2 pm = pa[m];
+                        // boundary pass: drop the pixels outside [lo, hi] by zeroing the RECIPROCAL -- past the crossing a
+                        // distance can be exactly 0, and 0 * inf would be NaN
+                        const int j0 = pbase + (2 * m) * 32 + lane, j1 = j0 + 32;
+                        const bool out0 = !full && (j0 < lo || j0 > hi), out1 = !full && (j1 < lo || j1 > hi);
                         if (MODE == LM_SINGLE) {
                             const float2 da0 = __ffma2_rn(k0, t, e0a), da1 = __ffma2_rn(k1, t, e1a);
-                            const float2 r = __fmul2_rn(pr, rcp2(__fmul2_rn(da0, da1)));
+                            float2 rr = rcp2(__fmul2_rn(da0, da1));
+                            if (out0) rr.x = 0.0f;
+                            if (out1) rr.y = 0.0f;
+                            const float2 r = __fmul2_rn(pr, rr);
                             a0 = __ffma2_rn(r, da1, a0);
                             a1 = __ffma2_rn(r, da0, a1);
                         } else {
                             const float2 da0 = __ffma2_rn(k0, t, e0a), dr0 = __ffma2_rn(k0, t, e0r);
                             const float2 da1 = __ffma2_rn(k1, t, e1a), dr1 = __ffma2_rn(k1, t, e1r);
-                            const float2 r0 = rcp2(__fmul2_rn(da0, dr0)), r1 = rcp2(__fmul2_rn(da1, dr1));
+                            float2 r0 = rcp2(__fmul2_rn(da0, dr0)), r1 = rcp2(__fmul2_rn(da1, dr1));
+                            if (out0) { r0.x = 0.0f; r1.x = 0.0f; }
+                            if (out1) { r0.y = 0.0f; r1.y = 0.0f; }
                             const float2 n0 = __ffma2_rn(pm, dr0, __fmul2_rn(pr, da0));
                             const float2 n1 = __ffma2_rn(pm, dr1, __fmul2_rn(pr, da1));
                             a0 = __ffma2_rn(n0, r0, a0);
@@ -2046,10 +2050,10 @@ __global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace w
     const float ea = (float)P.eps_a;
     // sample j of the line lives at fim[j * fstep] and reads the upstream gradient at ga[(j / ss) * gstep]
     const int32_t* fim = P.face_index + (size_t)b * P.Hs * P.Ws + (axis == 0 ? (size_t)d0 : (size_t)d0 * P.Ws);
-    const long fstep = axis == 0 ? P.Ws : 1;
+    const int fstep = axis == 0 ? P.Ws : 1;                 // (32-bit offsets: validate() bounds Hs, Ws <= 32767)
     const float* ga = P.g_alpha + (size_t)b * P.H * P.W +
                       (axis == 0 ? (size_t)(P.H - 1) * P.W + d0 / P.ss : (size_t)(P.H - 1 - d0 / P.ss) * P.W);
-    const long gstep = axis == 0 ? -(long)P.W : 1;
+    const int gstep = axis == 0 ? -P.W : 1;
     const int ssh = P.ss == 2 ? 1 : 0;
 
     // (1) level-0 moments, one lane per block of 16 samples, straight from global memory (all loads first).
@@ -2086,8 +2090,8 @@ __global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace w
 #pragma unroll
             for (int i = 0; i < AM_S0; i++) {
                 const int j = min(j0 + i, L - 1);
-                id[i] = __ldg(fim + (long)j * fstep);
-                g[i] = __ldg(ga + (long)(j >> ssh) * gstep);
+                id[i] = __ldg(fim + j * fstep);
+                g[i] = __ldg(ga + (j >> ssh) * gstep);
             }
 #pragma unroll
             for (int i = 0; i < AM_S0; i++) w[i] = (j0 + i < L) ? am_weight(id[i], g[i], sc) : 0.0f;
@@ -2173,17 +2177,17 @@ __global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace w
                 nd += AM_S0;
             }
             nd = min(nd, n);
-            for (int i0 = 0; i0 < nd; i0 += 4) {        // four samples per trip: their loads fly together
-                int id[4];
-                float g[4];
+            for (int i0 = 0; i0 < nd; i0 += 8) {        // eight samples per trip: their loads fly together
+                int id[8];
+                float g[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 8; u++) {
                     const int j = pos + dir * min(i0 + u, nd - 1);
-                    id[u] = __ldg(fim + (long)j * fstep);
-                    g[u] = __ldg(ga + (long)(j >> ssh) * gstep);
+                    id[u] = __ldg(fim + j * fstep);
+                    g[u] = __ldg(ga + (j >> ssh) * gstep);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 8; u++) {
                     // a trip's spare slots repeat the last sample with weight 0 (its distance is never zero)
                     const float w = (i0 + u < nd) ? am_weight(id[u], g[u], sc) : 0.0f;
                     const float tt = (float)(pos + dir * min(i0 + u, nd - 1)) - q.xc;
@@ -2344,7 +2348,7 @@ __global__ void __launch_bounds__(LW * 32, 2) k_line_rgb(BwdParams P, Workspace 
                             dB = __fmaf_rn(c[0], g0, __fmaf_rn(c[1], g1, c[2] * g2));
                         }
                         if (ia[i] >= 0 || ib[i] >= 0) mybg = false;
-                    } else mybg = false;
+                    }       // beyond the line: g = D = 0, a harmless "background" pair
                     if (i & 1) { G0[i / 2].y = g0; G1[i / 2].y = g1; G2[i / 2].y = g2; DA[i / 2].y = dA; DB[i / 2].y = dB; }
                     else { G0[i / 2].x = g0; G1[i / 2].x = g1; G2[i / 2].x = g2; DA[i / 2].x = dA; DB[i / 2].x = dB; }
                 }
@@ -2352,10 +2356,21 @@ __global__ void __launch_bounds__(LW * 32, 2) k_line_rgb(BwdParams P, Workspace 
             const bool allbg = __all_sync(FULL, mybg);      // every sample of the pass is background (and on the line)
             const float jbase = (float)(sbase + 2 * lane);   // first sample of this lane's first output pixel
             const int pass_hi = sbase + PASS_S - 1;
-            for (int k = 0; k < qn; k++) {
-                const int lo = s_q[warp][k].lo, hi = s_q[warp][k].hi;       // broadcast reads
-                if (hi < sbase || lo > pass_hi) continue;
+            // queries of the chunk that reach into this pass: lane k looks at query k, the warp walks the set bits.
+            // A range that ends at a border of the LINE is treated as unbounded on that side: samples beyond the line
+            // carry g = D = 0 and contribute exactly 0, so the last pass needs no masking.
+            static_assert(LQ == 32, "one ballot bit per staged query");
+            unsigned active;
+            {
+                int qlo = 0x7fffffff, qhi = -1;
+                if (lane < qn) { qlo = s_q[warp][lane].lo; qhi = s_q[warp][lane].hi; }
+                active = __ballot_sync(FULL, !(qhi < sbase || qlo > pass_hi));
+            }
+            while (active) {
+                const int k = __ffs(active) - 1;
+                active &= active - 1;
                 const QueryR q = s_q[warp][k];
+                const int lo = q.lo == 0 ? -0x40000000 : q.lo, hi = q.hi == L - 1 ? 0x40000000 : q.hi;
                 const bool full = (lo <= sbase) && (hi >= pass_hi);
                 const float2 nc0 = f2(q.nc0), nc1 = f2(q.nc1), nc2 = f2(q.nc2);
                 // signed unit-slope offset of the pair's first sample: (j - xc), elements 64 samples apart
@@ -2645,15 +2660,24 @@ int sm_count() {
     return n;
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is needed once per (kernel, device), not on every call
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is needed once per (kernel, device), not on every call.  The table is
+// keyed by the kernel's ADDRESS (distinct template instantiations share one function-pointer type).
 template <typename K>
 inline void allow_smem_once(K kernel, size_t bytes) {
-    static std::atomic<size_t> granted[64];      // one table per kernel instantiation; zero-initialised
+    struct Entry { const void* fn; size_t granted[16]; };
+    static Entry table[64];
+    static int used = 0;
+    static std::mutex mu;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (granted[dev].load(std::memory_order_relaxed) >= bytes && bytes > 0) return;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = 0;
+    const void* key = (const void*)kernel;
+    std::lock_guard<std::mutex> lk(mu);
+    Entry* e = nullptr;
+    for (int i = 0; i < used; i++) if (table[i].fn == key) { e = &table[i]; break; }
+    if (!e && used < 64) { e = &table[used++]; e->fn = key; for (auto& g : e->granted) g = 0; }
+    if (e && e->granted[dev] >= bytes && bytes > 0) return;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    granted[dev].store(bytes, std::memory_order_relaxed);
+    if (e) e->granted[dev] = bytes;
 }
 
 CamDev make_cam(const sdn_camera* cam) {
@@ -2780,8 +2804,14 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
             // the lean paired sweep for the colour term (2x SSAA), the direct sweep for what neither covers
             static const bool old_line = getenv("SDN_LINE_OLD") != nullptr;
             const int lmax = max(P.Hs, P.Ws);
-            const bool alpha_moments = !old_line && lmax <= AM_LMAX && (lmode == LM_ALPHA || lmode == LM_SPLIT);
-            const bool rgb_pairs = !old_line && P.ss == 2 && P.use_rgb && P.g_rgb &&
+            // Measured on config 2 (B200, ms per batch of 32): silhouette only 0.72 direct -> 0.30 block moments; colour only
+            // 0.85 direct -> 0.65 paired sweep; split (both) 0.85 fused direct sweep vs 0.96 for the two new kernels back to
+            // back -- the fused direct sweep hides the alpha arithmetic under the colour term, so split keeps it unless
+            // SDN_LINE_SPLIT_NEW=1 asks for the pair.
+            static const bool split_new = getenv("SDN_LINE_SPLIT_NEW") != nullptr;
+            const bool want_new = !old_line && (lmode != LM_SPLIT || split_new);
+            const bool alpha_moments = want_new && lmax <= AM_LMAX && P.g_alpha && (lmode == LM_ALPHA || lmode == LM_SPLIT);
+            const bool rgb_pairs = want_new && P.ss == 2 && P.use_rgb && P.g_rgb &&
                                    (lmode == LM_SPLIT || (lmode == LM_SINGLE && (P.split || !P.use_alpha)));
             if (lmode == LM_SPLIT && alpha_moments != rgb_pairs) {
                 SDN_LINE_VARIANTS(LM_SPLIT);                    // one of the two halves is unavailable: direct split sweep
