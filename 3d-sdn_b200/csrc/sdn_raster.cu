@@ -110,6 +110,7 @@ struct Workspace {
     int* line_items;        // [qmax]    query indices grouped by line
     struct Query* queries;  // [qmax]
     float2* qres;           // [qmax]    (g0, g1) of each query
+    float2* qres2;          // [qmax]    second addend (colour role of the split launch)
     int2* unit_tab;         // [umax]    (visible-face slot, block index) of every 4x32-sample unit of k_bwd_face
     float* upart;           // [umax,18] per-unit partial sums
     int lines, qmax, scan_n, umax;
@@ -160,6 +161,7 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.line_items = (int*)(p + off); off = align_up(off + (size_t)w.qmax * 4, 256);
     w.queries = (struct Query*)(p + off); off = align_up(off + (size_t)w.qmax * 32, 256);
     w.qres = (float2*)(p + off); off = align_up(off + (size_t)w.qmax * 8, 256);
+    w.qres2 = (float2*)(p + off); off = align_up(off + (size_t)w.qmax * 8, 256);
     w.unit_tab = (int2*)(p + off); off = align_up(off + (size_t)w.umax * 8, 256);
     w.upart = (float*)(p + off); off = align_up(off + (size_t)w.umax * 72, 256);
     w.total = off;
@@ -2020,8 +2022,8 @@ inline size_t am_smem_floats(int lcap, int levels) {
 // weight of sample j of the line: background ? max(0, -g) : 0   (alpha_in == 1, rasterize.py:601,628-631)
 __device__ __forceinline__ float am_weight(int idx, float g, float sc) { return idx < 0 ? fmaxf(-(g * sc), 0.0f) : 0.0f; }
 
-__global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace ws, int lcap, int levels) {
-    extern __shared__ __align__(16) float s_am[];
+__device__ __forceinline__ void line_alpha_role(const BwdParams& P, const Workspace& ws, int lcap, int levels,
+                                                const int block_index, float* s_am) {
     __shared__ int s_off[AM_MAXLEV + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb0 = lcap >> AM_LOG0;
@@ -2036,7 +2038,7 @@ __global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace w
     const int per_img = P.Hs + P.Ws;
     const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
     const int bundles = bundles_rows + bundles_cols;
-    const int b = blockIdx.x / bundles, bi = blockIdx.x % bundles;
+    const int b = block_index / bundles, bi = block_index % bundles;
     int axis, d0;
     if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
     else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
@@ -2231,6 +2233,11 @@ __global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace w
     }
 }
 
+__global__ void __launch_bounds__(LW * 32) k_line_alpha(BwdParams P, Workspace ws, int lcap, int levels) {
+    extern __shared__ __align__(16) float s_am_dyn[];
+    line_alpha_role(P, ws, lcap, levels, (int)blockIdx.x, s_am_dyn);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Colour (rgb / normal) out-sweeps at 2x SSAA, pairwise but lean.  The positive part of rasterize.py:632-635,
 //        max(0, D_j - c_in . g_j),      D_j = c_j . g_j,
@@ -2254,15 +2261,15 @@ struct __align__(16) QueryR {
 constexpr float RGB_FAR = 160.0f;       // samples: beyond this distance 2u/(u^2 - 1/4) -> 2/u
 
 template <int OP, int LQ>
-__global__ void __launch_bounds__(LW * 32, 2) k_line_rgb(BwdParams P, Workspace ws, int accumulate) {
-    extern __shared__ __align__(16) unsigned char s_line_dyn[];
+__device__ __forceinline__ void line_rgb_role(const BwdParams& P, const Workspace& ws, const int block_index,
+                                              const int accumulate, float2* __restrict__ out, unsigned char* s_line_dyn) {
     float2 (*s_acc)[LQ][33] = reinterpret_cast<float2 (*)[LQ][33]>(s_line_dyn);
     __shared__ QueryR s_q[LW][LQ];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_img = P.Hs + P.Ws;
     const int bundles_rows = (P.Hs + LW - 1) / LW, bundles_cols = (P.Ws + LW - 1) / LW;
     const int bundles = bundles_rows + bundles_cols;
-    const int b = blockIdx.x / bundles, bi = blockIdx.x % bundles;
+    const int b = block_index / bundles, bi = block_index % bundles;
     int axis, d0;
     if (bi < bundles_rows) { axis = 1; d0 = bi * LW + warp; if (d0 >= P.Hs) return; }
     else { axis = 0; d0 = (bi - bundles_rows) * LW + warp; if (d0 >= P.Ws) return; }
@@ -2452,16 +2459,32 @@ __global__ void __launch_bounds__(LW * 32, 2) k_line_rgb(BwdParams P, Workspace 
             // dist_v = k_v (t + s_v);   g -= diff / dist   (rasterize.py:648,653)
             float2 o = make_float2((q.flags & QF_USE0) ? -(r0 * q.ik0) : 0.0f, (q.flags & QF_USE1) ? -(r1 * q.ik1) : 0.0f);
             const int qi = ws.line_items[qchunk + k];
-            if (accumulate) { const float2 p = ws.qres[qi]; o.x += p.x; o.y += p.y; }
-            ws.qres[qi] = o;
+            if (accumulate) { const float2 p = out[qi]; o.x += p.x; o.y += p.y; }
+            out[qi] = o;
         }
         __syncwarp();
     }
 }
 
+template <int OP, int LQ>
+__global__ void __launch_bounds__(LW * 32, 2) k_line_rgb(BwdParams P, Workspace ws, int accumulate) {
+    extern __shared__ __align__(16) unsigned char s_rgb_dyn[];
+    line_rgb_role<OP, LQ>(P, ws, (int)blockIdx.x, accumulate, ws.qres, s_rgb_dyn);
+}
+
+// Split backward (alpha pass + colour pass): the two sweeps of a bundle of lines as ONE launch whose even CTAs take the
+// colour role and odd CTAs the alpha role.  The colour sweep is issue-bound, the block-moment sweep latency-bound
+// (one lane per query, dependent shared-memory reads): co-resident on an SM they fill each other's idle issue slots.
+// The colour role writes ws.qres2, the alpha role ws.qres; k_item_sums adds the two.
+template <int OP, int LQ>
+__global__ void __launch_bounds__(LW * 32, 2) k_line_split(BwdParams P, Workspace ws, int lcap, int levels) {
+    extern __shared__ __align__(16) unsigned char s_split_dyn[];
+    if (blockIdx.x & 1) line_alpha_role(P, ws, lcap, levels, (int)(blockIdx.x >> 1), reinterpret_cast<float*>(s_split_dyn));
+    else line_rgb_role<OP, LQ>(P, ws, (int)(blockIdx.x >> 1), 0, ws.qres2, s_split_dyn);
+}
 
 // adds the deferred out-sweep results of every (edge, axis) item onto its in-sweep partial, in step order
-__global__ void __launch_bounds__(256) k_item_sums(Workspace ws) {
+__global__ void __launch_bounds__(256) k_item_sums(Workspace ws, int two) {
     if (bwd_overflow(ws)) return;
     const int n = ws.vis_count[0] * ITEMS;
     const int* item_n = ws.scan_buf + ws.lines + 1;
@@ -2471,7 +2494,11 @@ __global__ void __launch_bounds__(256) k_item_sums(Workspace ws) {
         if (kind == 6) continue;
         float a0 = 0.0f, a1 = 0.0f;
         const int qe = item_n[it + 1] - q0;
-        for (int q = item_n[it] - q0; q < qe; q++) { const float2 r = ws.qres[q]; a0 += r.x; a1 += r.y; }
+        for (int q = item_n[it] - q0; q < qe; q++) {
+            float2 r = ws.qres[q];
+            if (two) { const float2 r2 = ws.qres2[q]; r.x += r2.x; r.y += r2.y; }
+            a0 += r.x; a1 += r.y;
+        }
         float* part = ws.gpart + (size_t)ws.vis_ids[it / ITEMS] * 12 + kind * 2;
         part[0] += a0; part[1] += a1;
     }
@@ -2738,6 +2765,7 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
         if ((e = cudaMemsetAsync(P.grad_textures, 0, nb, st)) != cudaSuccess) return (int)e;
     }
     const long BF = (long)r->B * r->F;
+    int two_results = 0;            // the line stage left its result in two arrays (qres + qres2)
     timing_begin("k_compact_visible", st);
     k_compact_visible<<<(unsigned)((BF + 255) / 256), 256, 0, st>>>(r->B, r->F, ws);
     if ((rc = check_launch())) return rc;
@@ -2805,41 +2833,52 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
             static const bool old_line = getenv("SDN_LINE_OLD") != nullptr;
             const int lmax = max(P.Hs, P.Ws);
             // Measured on config 2 (B200, ms per batch of 32): silhouette only 0.72 direct -> 0.30 block moments; colour only
-            // 0.85 direct -> 0.65 paired sweep; split (both) 0.85 fused direct sweep vs 0.96 for the two new kernels back to
-            // back -- the fused direct sweep hides the alpha arithmetic under the colour term, so split keeps it unless
-            // SDN_LINE_SPLIT_NEW=1 asks for the pair.
-            static const bool split_new = getenv("SDN_LINE_SPLIT_NEW") != nullptr;
-            const bool want_new = !old_line && (lmode != LM_SPLIT || split_new);
+            // 0.85 direct -> 0.65 paired sweep; split = the two new kernels back to back.
+            const bool want_new = !old_line;
             const bool alpha_moments = want_new && lmax <= AM_LMAX && P.g_alpha && (lmode == LM_ALPHA || lmode == LM_SPLIT);
             const bool rgb_pairs = want_new && P.ss == 2 && P.use_rgb && P.g_rgb &&
                                    (lmode == LM_SPLIT || (lmode == LM_SINGLE && (P.split || !P.use_alpha)));
             if (lmode == LM_SPLIT && alpha_moments != rgb_pairs) {
                 SDN_LINE_VARIANTS(LM_SPLIT);                    // one of the two halves is unavailable: direct split sweep
             } else {
-                if (alpha_moments) {
-                    const int lcap = (lmax + AM_S0 - 1) / AM_S0 * AM_S0;
-                    const int levels = am_levels(lmax);
-                    const size_t asmem = sizeof(float) * LW * am_smem_floats(lcap, levels);
-                    allow_smem_once(k_line_alpha, asmem);
-                    timing_begin("k_line_alpha", st);
-                    k_line_alpha<<<lgrid, LW * 32, asmem, st>>>(P, ws, lcap, levels);
-                    if (rgb_pairs && (rc = check_launch())) return rc;
-                }
-                if (rgb_pairs) {
-                    static const int op = getenv("SDN_RGB_OP") ? atoi(getenv("SDN_RGB_OP")) : 8;
-                    const size_t lsmem = sizeof(float2) * LW * 32 * 33;
+                static const int op = getenv("SDN_RGB_OP") ? atoi(getenv("SDN_RGB_OP")) : 8;
+                static const bool no_fuse = getenv("SDN_LINE_NO_FUSE") != nullptr;
+                const int lcap = (lmax + AM_S0 - 1) / AM_S0 * AM_S0;
+                const int levels = am_levels(lmax);
+                const size_t asmem = sizeof(float) * LW * am_smem_floats(lcap, levels);
+                const size_t lsmem = sizeof(float2) * LW * 32 * 33;
+                if (alpha_moments && rgb_pairs && !no_fuse) {
+                    const size_t ssmem = asmem > lsmem ? asmem : lsmem;
+                    two_results = 1;
+                    timing_begin("k_line_split", st);
                     if (op == 4) {
-                        allow_smem_once(k_line_rgb<4, 32>, lsmem);
-                        timing_begin("k_line_rgb", st);
-                        k_line_rgb<4, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                        allow_smem_once(k_line_split<4, 32>, ssmem);
+                        k_line_split<4, 32><<<2 * lgrid, LW * 32, ssmem, st>>>(P, ws, lcap, levels);
                     } else {
-                        allow_smem_once(k_line_rgb<8, 32>, lsmem);
+                        allow_smem_once(k_line_split<8, 32>, ssmem);
+                        k_line_split<8, 32><<<2 * lgrid, LW * 32, ssmem, st>>>(P, ws, lcap, levels);
+                    }
+                } else {
+                    if (alpha_moments) {
+                        allow_smem_once(k_line_alpha, asmem);
+                        timing_begin("k_line_alpha", st);
+                        k_line_alpha<<<lgrid, LW * 32, asmem, st>>>(P, ws, lcap, levels);
+                        if (rgb_pairs && (rc = check_launch())) return rc;
+                    }
+                    if (rgb_pairs) {
                         timing_begin("k_line_rgb", st);
-                        k_line_rgb<8, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                        if (op == 4) {
+                            allow_smem_once(k_line_rgb<4, 32>, lsmem);
+                            k_line_rgb<4, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                        } else {
+                            allow_smem_once(k_line_rgb<8, 32>, lsmem);
+                            k_line_rgb<8, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                        }
                     }
                 }
                 if (!alpha_moments && !rgb_pairs) {
                     if (lmode == LM_ALPHA) SDN_LINE_VARIANTS(LM_ALPHA);
+                    else if (lmode == LM_SPLIT) SDN_LINE_VARIANTS(LM_SPLIT);
                     else SDN_LINE_VARIANTS(LM_SINGLE);
                 }
             }
@@ -2857,7 +2896,7 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
     if ((rc = check_launch())) return rc;
     if (P.line_path) {
         timing_begin("k_item_sums", st);
-        k_item_sums<<<sm_count() * 8, 256, 0, st>>>(ws);
+        k_item_sums<<<sm_count() * 8, 256, 0, st>>>(ws, two_results);
         if ((rc = check_launch())) return rc;
     }
     timing_begin("k_grad_assemble", st);

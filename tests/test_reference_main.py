@@ -49,7 +49,8 @@ def test_reference_main_imports_against_this_package():
     # ... everything else of derender3d, bulb and maskrcnn is the reference's own file
     assert os.path.abspath(derender3d.datasets.__file__).startswith(ref)
     assert main.Transforms is derender3d.datasets.Transforms
-    assert os.path.abspath(main.Net.__module__ and __import__('bulb.net').net.__file__).startswith(ref)
+    import bulb.net
+    assert os.path.abspath(bulb.net.__file__).startswith(ref) and main.Net is bulb.net.Net
     assert issubclass(main.Model, derender3d.models.Derenderer3d)
     assert main.TargetType.full == 3 and main.TargetType.extend == 15
     for name in ('train', 'test', '_test', '_test_2d', 'BaseNet', 'TrainNet', 'TestNet', 'TrainLoader'):
@@ -80,7 +81,8 @@ def test_reference_train_net_steps_on_a_synthetic_batch():
     repo's encoder + fused front end + rasteriser, the reference's losses, backward through the native kernels, Adam."""
     compat, ref, main = _main()
     assert torch.cuda.is_available()
-    main.FLAGS(['main.py', '--do', 'train', '--mode', 'full', '--dataset', 'vkitti', '--render_size', '128'])
+    main.FLAGS(['main.py', '--do', 'train', '--mode', 'full', '--dataset', 'vkitti', '--render_size', '128',
+                '--image_steps', '1000000'])
     main.FLAGS.mode = main.TargetType.__dict__[main.FLAGS.mode] if isinstance(main.FLAGS.mode, str) else main.FLAGS.mode
     torch.manual_seed(0)
     model = torch.nn.DataParallel(main.Model(), device_ids=[0]).cuda()
@@ -101,7 +103,7 @@ def test_reference_train_net_steps_on_a_synthetic_batch():
         'ignores': np.zeros((B, 1, 100, 100), np.float32),
     }
     net = main.TrainNet(optimizer=torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3), model=model,
-                        writer=None, data_loader=[batch], lr_decay_epochs=None, summarize_steps=1, save_steps=None,
+                        writer=compat._NullWriter(), data_loader=[batch], lr_decay_epochs=None, summarize_steps=1, save_steps=None,
                         saver=None)
     before = model.module.derenderer._fc3.weight.detach().clone()
     import sdn_b200
