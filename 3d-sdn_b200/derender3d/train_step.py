@@ -82,34 +82,75 @@ class GraphedTrainStep(object):
 
     `optimizer` must be built with capturable=True (Adam keeps its step counter on the device).  Inputs are copied
     into static buffers; outputs (`loss`, `losses`, `blob`) are static tensors overwritten by each replay.
-    Single-process only for now: with a gradient all-reduce (sdn_b200.dist.FlatGradSync) use the eager `train_step`
-    (measured at 2 GPUs: 96 % weak-scaling efficiency); a graphed multi-GPU step is not validated yet."""
 
-    def __init__(self, model, optimizer, example_batch, mode, warmup=3, autocast_dtype=None):
+    The warm-up steps that lazy initialisation needs (mesh bank, camera cache, cuDNN plans, Adam state, NCCL
+    communicator) do NOT leak into the training trajectory: parameters, buffers (BatchNorm running statistics) and the
+    optimizer state are snapshotted before and restored after them, so replay k equals eager step k.
+
+    Multi-GPU (BASELINE config 4): pass `grad_sync` = sdn_b200.dist.FlatGradSync(model, bucket_views=True).  The
+    gradients are then views of one flat fp32 bucket and the captured step is
+    zero bucket -> forward -> backward -> ONE all-reduce (NCCL, captured in the graph) -> Adam; every rank replays the
+    same graph, so the replicas stay bit-identical (checked by `replicas_in_sync`)."""
+
+    def __init__(self, model, optimizer, example_batch, mode, warmup=3, autocast_dtype=None, grad_sync=None):
+        import copy
         self.model, self.optimizer, self.mode = model, optimizer, mode
         self.batch = {k: v.clone() for k, v in example_batch.items()}
         self.autocast_dtype = autocast_dtype
+        self.grad_sync = grad_sync
+        snap_model = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        snap_opt = copy.deepcopy(optimizer.state_dict())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):         # lazy initialisation (mesh bank, camera cache, cuDNN plans, Adam state)
+            for _ in range(max(warmup, 1)):     # lazy initialisation; undone below
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
-        optimizer.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for k, v in model.state_dict().items():
+                v.copy_(snap_model[k])
+        if snap_opt['state']:
+            optimizer.load_state_dict(snap_opt)
+        else:                                   # first use: forget the moments and step count of the warm-up
+            with torch.no_grad():
+                for st in optimizer.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+        if grad_sync is None:
+            optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss, self.losses, self.blob = self._eager(zero=False)
+            self.loss, self.losses, self.blob = self._eager(zero=grad_sync is not None)
 
     def _eager(self, zero=True):
         with torch.autocast('cuda', dtype=self.autocast_dtype or torch.bfloat16, enabled=self.autocast_dtype is not None):
             blob = self.model(self.batch['images'], self.batch['roi_norms'], self.batch['focals'])
             losses = geometric_losses(blob, self.batch, self.mode)
             loss = sum(losses.values())
-        if zero:
+        if self.grad_sync is not None:
+            self.grad_sync.zero()               # gradients are views of the flat bucket: one memset, views stay alive
+        elif zero:
             self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.model)
         self.optimizer.step()
         return loss.detach(), losses, blob
+
+    def replicas_in_sync(self):
+        """True when every rank holds bit-identical parameters (all-gather of a checksum per rank)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return True
+        with torch.no_grad():
+            flat = torch.cat([p.detach().reshape(-1).float() for p in self.model.parameters()])
+            sig = torch.stack([flat.double().sum(), flat.double().abs().sum(), (flat.double() * torch.arange(
+                flat.numel(), device=flat.device, dtype=torch.float64).remainder(97.0)).sum()])
+            sigs = [torch.empty_like(sig) for _ in range(dist.get_world_size())]
+            dist.all_gather(sigs, sig)
+        return all(torch.equal(sigs[0], s) for s in sigs[1:])
 
     def step(self, batch=None):
         if batch is not None:

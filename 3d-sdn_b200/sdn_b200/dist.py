@@ -42,6 +42,8 @@ class FlatGradSync(object):
             p.grad = v
 
     def zero(self):
+        if self.bucket_views and not self._attached():
+            self.attach()       # something (zero_grad(set_to_none=True), a layout change) dropped the views: re-attach
         self.flat.zero_()
 
     def _attached(self):

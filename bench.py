@@ -18,6 +18,11 @@ import threading
 import time
 import math
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use the host's cores
+    # (set before libgomp / torch are loaded; `cores` in the JSON line reports what OpenMP then really used)
+    os.environ['OMP_NUM_THREADS'] = str(max(1, (os.cpu_count() or 2) // 2))
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, '3d-sdn_b200')):
     if _p not in sys.path:
@@ -106,7 +111,9 @@ def run_ours(args):
     sdn_b200.lib()
 
     B = args.batch
-    verts, faces, grads = make_inputs(B, rank, dev)
+    # every rank renders the SAME 32 scenes unless --rank-seeds: the weak-scaling line then measures the machine and not
+    # the heaviest rank's scenes (the work per image is data dependent); results per rank are printed either way
+    verts, faces, grads = make_inputs(B, rank if args.rank_seeds else 0, dev)
     renderer = Renderer(image_size=(H, W), viewing_angle=wl.vkitti_viewing_angle())
     fast = not args.exact
     v_dev = verts.to(dev).requires_grad_(True)
@@ -160,6 +167,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    rank_ms = []
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -169,10 +178,13 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        rank_ms[:] = [ms]
         if world > 1:
             t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            all_t = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(all_t, t)
+            rank_ms[:] = [float(x.item()) for x in all_t]
+            ms = max(rank_ms)
         barrier()
         return ms
 
@@ -226,6 +238,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms = timed(timed_step, args.steps)
+    step_rank_ms = sorted(x / args.steps for x in rank_ms)
     launches = launches_per_step * args.steps
     sampler.stop_flag = True
     v_dev.grad = None
@@ -316,7 +329,10 @@ def run_ours(args):
                    'launch': 'cuda graph replay' if graph is not None else 'eager', 'host_dispatch_ms_per_step': round(host_ms, 3),
                    'l2': 'inputs+outputs per step (%.0f MB) exceed the 126 MB L2' % (
                        B * sum(algorithmic_bytes()) / 1e6),
-                   'sharding': 'by image, no data-path collective'},
+                   'sharding': 'by image, no data-path collective',
+                   'scenes': 'per-rank seeds' if args.rank_seeds else 'the same 32 scenes on every rank',
+                   'rank_ms_per_step': {'min': round(step_rank_ms[0], 4), 'median': round(step_rank_ms[len(step_rank_ms) // 2], 4),
+                                        'max': round(step_rank_ms[-1], 4)}},
         'e2e': {'value': round(images / (ms_e2e * 1e-3), 1), 'unit': 'images/s',
                 'h2d_bytes_per_step': int(verts.numel() * 4), 'd2h_bytes_per_step': int(verts.numel() * 4 + 4),
                 'launch': e2e_launch,
@@ -325,7 +341,14 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
     }
+    extra = None
+    if not args.no_extra:
+        del graph
+        torch.cuda.empty_cache()
+        extra = other_configs(renderer, dev, world, rank, fast, args)
     if rank == 0:
+        if extra:
+            line.update(extra)
         fwd_b, bwd_b = algorithmic_bytes()
         peak, how = measured_peaks()
         dom = max(kern, key=lambda k: kern[k])
@@ -346,6 +369,93 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time_steps(fn, steps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def other_configs(renderer, dev, world, rank, fast, args):
+    """The other BASELINE configs, measured briefly in the same process so that the driver's JSON carries them:
+    N = 1: config 2 in exact (IEEE-division) mode, config 2b (silhouette only: the reference's training path), config 2c
+    (the reference's real 58k-145k-face templates at its own 384x384) and config 3 (full training step);
+    N > 1: config 4 = config 3 per rank + ONE flat-bucket gradient all-reduce inside the timed step."""
+    from sdn_b200 import workloads as wl
+    from derender3d.bench_setup import measure_train, template_meshes
+    from derender3d.models.renderer import Renderer
+    out = {}
+    if world > 1:
+        out['config4'] = measure_train(dev, world, rank, B=16, S=384, steps=10, graph=not args.no_train_graph)
+        return out
+    B = args.batch
+    verts, faces, grads = make_inputs(B, 0, dev)
+    v = verts.to(dev).requires_grad_(True)
+    f = faces.to(dev).int()
+    g = {k: t.to(dev) for k, t in grads.items()}
+
+    def step(want, fm):
+        def fn():
+            o = renderer.forward_multi(v, f, fast_math=fm, **want)
+            keys = [k for k in ('silhouette', 'depth', 'normal') if want[k]]
+            torch.autograd.backward([o[k] for k in keys], [g[k] for k in keys])
+            v.grad = None
+        return fn
+    all3 = dict(silhouette=True, depth=True, normal=True)
+    ms = _time_steps(step(all3, False), 3, warm=1)
+    out['config2_exact_math'] = {'images_per_s': round(B / ms * 1e3, 1), 'ms_per_step': round(ms, 3),
+                                 'what': 'same step with fast_math=0: IEEE divisions in the op order of rasterize.py:646-653 '
+                                         '(one warp per (face, edge, axis) item), eager'}
+    ms = _time_steps(step(dict(silhouette=True, depth=False, normal=False), fast), 20)
+    fb, bb = algorithmic_bytes(c_out=1)
+    out['config2b'] = {'workload': 'config 2 with the silhouette output only (the reference training path, '
+                                   'derender3d/models/__init__.py:203-208), eager',
+                       'images_per_s': round(B / ms * 1e3, 1), 'ms_per_step': round(ms, 3),
+                       'hbm_roofline_frac': round(B / ms * 1e3 * (fb + bb) / 1e9 / measured_peaks()[0], 4)}
+    # config 2c: the real templates (or 72.6k-triangle stand-ins) at the reference's own 384x384, B = 32, three outputs
+    objs, desc = template_meshes()
+    S, Bc = 384, 32
+    nv_max = max(o.vertices.shape[0] for o in objs)
+    nf_max = max(o.faces.shape[0] for o in objs)
+    gen = torch.Generator().manual_seed(3)
+    vb = torch.zeros(Bc, nv_max, 3)
+    fbt = torch.zeros(Bc, nf_max, 3, dtype=torch.int32)
+    for i in range(Bc):
+        o = objs[i % len(objs)]
+        yaw = float(torch.rand(1, generator=gen)) * 6.283
+        c, s_ = math.cos(yaw), math.sin(yaw)
+        R = torch.tensor([[c, 0, s_], [0, 1, 0], [-s_, 0, c]])
+        size = torch.tensor([4.0, 1.6, 1.8])
+        vv = (o.vertices * size) @ R.T + torch.tensor([0.0, 0.0, -(5.5 + 3.0 * float(torch.rand(1, generator=gen)))])
+        vb[i, :vv.shape[0]] = vv
+        vb[i, vv.shape[0]:] = vv[0]
+        fbt[i, :o.faces.shape[0]] = o.faces
+    vc = vb.to(dev).requires_grad_(True)
+    fc = fbt.to(dev)
+    gc = {'silhouette': torch.randn(Bc, 1, S, S, generator=gen).to(dev), 'depth': torch.randn(Bc, 1, S, S, generator=gen).to(dev),
+          'normal': torch.randn(Bc, 3, S, S, generator=gen).to(dev)}
+    rc = Renderer(image_size=S, viewing_angle=wl.vkitti_viewing_angle(S, 500.0))
+
+    def step_c():
+        o = rc.forward_multi(vc, fc, fast_math=fast)
+        torch.autograd.backward([o['silhouette'], o['depth'], o['normal']], [gc['silhouette'], gc['depth'], gc['normal']])
+        vc.grad = None
+    ms = _time_steps(step_c, 10)
+    cov = float((rc.forward_multi(vc, fc)['silhouette'] > 0).float().mean())
+    out['config2c'] = {'workload': 'B=32, %s, 384x384 (768x768 2xSSAA), silhouette+depth+normal fwd+bwd, eager' % desc,
+                       'images_per_s': round(Bc / ms * 1e3, 1), 'ms_per_step': round(ms, 3), 'coverage': round(cov, 3)}
+    del vc, fc, gc, rc
+    torch.cuda.empty_cache()
+    out['config3'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph)
+    return out
 
 
 def segment_times(renderer, v_dev, f_dev, g_dev, fast, steps):
@@ -479,6 +589,9 @@ def main():
     ap.add_argument('--exact', action='store_true', help='IEEE-division distance math in the backward (default: fast)')
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='time the eager step, not its CUDA graph')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-extra', action='store_true', help='skip the other configs (2b, 2c, 3 / 4) measured after the headline')
+    ap.add_argument('--no-train-graph', action='store_true', help='config 3 / 4: time the eager step, not its CUDA graph')
+    ap.add_argument('--rank-seeds', action='store_true', help='N > 1: different synthetic scenes on every rank')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

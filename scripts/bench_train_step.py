@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--render-size', type=int, default=384)
     ap.add_argument('--faces', type=int, default=72576, help='triangles per template mesh (ShapeNet: 29k-72k)')
     ap.add_argument('--fp32', action='store_true')
+    ap.add_argument('--synthetic', action='store_true', help='synthetic templates even when the real OBJ files are present')
     ap.add_argument('--encoder-only', action='store_true')
     ap.add_argument('--graph', action='store_true', help='capture the whole step in a CUDA graph (GraphedTrainStep)')
     ap.add_argument('--profile', action='store_true', help='torch.profiler table of one step (kernel time vs wall)')
@@ -38,41 +39,15 @@ def main():
     if world > 1:       # BASELINE config 4: one process per GPU, one flat-bucket all-reduce per step
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
-    torch.manual_seed(0)
-    n_lon = 192
-    n_lat = max(4, args.faces // (2 * n_lon) + 1)
-    objs = []
-    for k in range(8):
-        v, f = wl.superellipsoid_mesh(n_lon, n_lat, 0.5 + 0.04 * k, 0.6)
-        objs.append(ShapenetObj(vertices=v * np.array([1.0, 0.35, 0.45], np.float32), faces=f))
+    from derender3d.bench_setup import train_setup
     B, S = args.batch, args.render_size
-    model = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=objs).to(dev).train()
-    model.derenderer.net = model.derenderer.net.to(memory_format=torch.channels_last)
-    # start from a pose head that puts objects in view (a real run starts from the pre-trained pose stage)
-    with torch.no_grad():
-        model.derenderer._fc3.weight.mul_(0.01)
-        model.derenderer._fc3.bias.zero_()
-        model.derenderer._fc3.bias[0] = 1.0                      # theta
-        model.derenderer._fc3.bias[4:7] = torch.tensor([1.3, 0.4, 0.5])   # log scales
-        model.derenderer._fc3.bias[7] = 2.2                      # log depth
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3, capturable=bool(args.graph))
+    st = train_setup(dev, B, S, args.faces, seed=rank, real=not args.synthetic, capturable=bool(args.graph))
+    model, opt, batch, objs = st['model'], st['opt'], st['batch'], st['objs']
+    roi = batch['roi_norms']
     sync = None
     if world > 1:
         from sdn_b200.dist import FlatGradSync
         sync = FlatGradSync(model, bucket_views=True)
-    g = torch.Generator().manual_seed(rank)
-    c = 0.3 * (torch.rand(B, 2, generator=g) - 0.5)
-    d = 0.25 + 0.15 * torch.rand(B, 2, generator=g)
-    roi = torch.cat([c - d / 2, c + d / 2], dim=1).to(dev)
-    batch = {'images': torch.randn(B, 3, 224, 224, generator=g).to(dev).contiguous(memory_format=torch.channels_last),
-             'roi_norms': roi, 'focals': torch.full((B, 1), 725.0, device=dev),
-             'targets': torch.full((B,), TargetType.full, device=dev, dtype=torch.long),
-             'thetas': torch.rand(B, 1, generator=g).to(dev), 'translation2ds': torch.zeros(B, 2, device=dev),
-             'log_scales': torch.tensor([1.3, 0.4, 0.5], device=dev).expand(B, 3).contiguous(),
-             'log_depths': torch.full((B, 1), 2.2, device=dev),
-             'masks': (torch.rand(B, 1, 256, 256, generator=g) > 0.5).float().to(dev),
-             'ignores': torch.zeros(B, 1, 256, 256, device=dev)}
-    sdn_b200.DEFAULT_FAST_MATH = True
     amp = not args.fp32
 
     def step():
@@ -99,8 +74,8 @@ def main():
 
     if args.graph:
         assert not args.encoder_only
-        assert world == 1, 'the graphed step is single-process for now (see GraphedTrainStep)'
-        gs = GraphedTrainStep(model, opt, batch, TargetType.full, autocast_dtype=torch.bfloat16 if amp else None)
+        gs = GraphedTrainStep(model, opt, batch, TargetType.full, autocast_dtype=torch.bfloat16 if amp else None,
+                              grad_sync=sync)
 
         def step():     # noqa: F811
             return gs.step(), gs.blob['_masks']
