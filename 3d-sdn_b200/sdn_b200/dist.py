@@ -31,7 +31,14 @@ class FlatGradSync(object):
         self.numel = n
         self.views, off = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            chunk = self.flat[off:off + p.numel()]
+            if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+                # channels-last parameter: give its gradient view the same strides (autograd's layout contract), so
+                # AccumulateGrad adds in place instead of re-striding through a temporary
+                n, c, h, w = p.shape
+                self.views.append(chunk.view(n, h, w, c).permute(0, 3, 1, 2))
+            else:
+                self.views.append(chunk.view_as(p))
             off += p.numel()
         self.bucket_views = bool(bucket_views)
         if self.bucket_views:

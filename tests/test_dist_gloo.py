@@ -76,3 +76,29 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_flat_bucket_views_follow_channels_last_parameters():
+    """Gradient views of the flat bucket take the strides of channels-last parameters (autograd's layout contract), so
+    backward accumulates in place: after backward every p.grad still IS its view, and the bucket holds the gradients."""
+    import torch
+    from sdn_b200.dist import FlatGradSync
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 4, 3, padding=1))
+    net = net.to(memory_format=torch.channels_last)
+    ref = [p.detach().clone() for p in net.parameters()]
+    x = torch.randn(2, 3, 8, 8)
+    net(x).square().sum().backward()
+    want = [p.grad.detach().clone() for p in net.parameters()]
+    for p in net.parameters():
+        p.grad = None
+    sync = FlatGradSync(net, bucket_views=True)
+    for p, v in zip(sync.params, sync.views):
+        assert v.stride() == p.stride() and v.shape == p.shape
+    sync.zero()
+    net(x).square().sum().backward()
+    assert sync._attached()
+    sync()                                  # world size 1: no collective, gradients stay where they are
+    for p, w, r in zip(net.parameters(), want, ref):
+        assert torch.allclose(p.grad, w, rtol=1e-5, atol=1e-6) and torch.equal(p.detach(), r)
+    assert abs(float(sync.flat.abs().sum()) - float(sum(w.abs().sum() for w in want))) < 1e-2
