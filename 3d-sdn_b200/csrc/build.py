@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(os.path.dirname(HERE), 'sdn_b200', 'libsdn_b200.so')
 SOURCES = [os.path.join(HERE, 'sdn_raster.cu'), os.path.join(HERE, 'sdn_linear_tc.cu'),
-           os.path.join(HERE, 'sdn_objects.cu'), os.path.join(HERE, 'sdn_composite.cu')]
+           os.path.join(HERE, 'sdn_objects.cu'), os.path.join(HERE, 'sdn_composite.cu'),
+           os.path.join(HERE, 'sdn_conv_tc.cu')]
 # -fmad=false: visibility arithmetic must not be contracted (DESIGN.md "arithmetic contract")
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false', '-std=c++17',
          '-Xcompiler', '-fPIC', '-shared', '-I' + os.path.join(ROOT, 'include')]

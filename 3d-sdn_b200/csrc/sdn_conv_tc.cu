@@ -1,0 +1,386 @@
+// sdn_conv_tc.cu -- 2-D convolution as an implicit GEMM on Blackwell's 5th-generation tensor cores, hand-written for
+// sm_100a:  TMA tensor-map loads (cp.async.bulk.tensor, 128-byte swizzle) -> shared memory -> tcgen05.mma (bf16 x bf16
+// -> fp32 in tensor memory) -> tcgen05.ld epilogue (per-channel scale / shift = folded BatchNorm or bias, optional
+// residual add, optional ReLU) -> bf16 NHWC.
+//
+// It serves the convolution trunk of the image encoder (reference: geometric/derender3d/models/derenderer.py:25-27,
+// torchvision resnet18: 3x3 / 1x1 convolutions, stride 1 and 2, 64..512 channels) and the textural branch's generator
+// (reference: textural/models/networks.py:211-283: 7x7 stem, 3x3 stride-2 down-sampling, 3x3 ResnetBlocks at 1024
+// channels, transposed convolutions).
+//
+// GEMM view:  D[M, N] = A[M, K] . B[N, K]^T,  M = output pixels (n, ho, wo), N = Cout, K = (kh, kw, cin).
+//   * Activations are NHWC bf16.  An M tile is a PATCH of bn x bh x bw output pixels (bn*bh*bw = 128): for filter tap
+//     (kh, kw) and 64 input channels its A operand is the input box of that patch shifted by the tap -- one 4-D TMA
+//     box load {64 ch, bw, bh, bn} (traversal stride = the convolution stride) whose out-of-bounds elements TMA fills
+//     with zeros: zero padding costs nothing and no im2col buffer exists.
+//   * Weights are [Cout, KH*KW*Cin] bf16 (K contiguous): the K-major B operand, one 2-D TMA box {64, TN} per K block.
+//   * Both land in the 128-byte-swizzled K-major layout (row r of the tile = 128 bytes at r*128, 16-byte chunks XOR-ed
+//     with r mod 8) that the UMMA shared-memory descriptor names with layout_type = SWIZZLE_128B, SBO = 1024 B; a
+//     K = 16 slice is selected by advancing the descriptor's start address by 32 bytes.
+//   * Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; also owns the TMEM
+//     allocation), warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = tile rows).  A 4-stage ring of
+//     (A | B) tiles is handed back and forth with mbarriers: `full` (TMA complete_tx) and `empty` (tcgen05.commit).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "sdn_b200.h"
+
+namespace sdn_internal {     // sdn_raster.cu: launch counter + optional per-kernel event timing
+void launch_begin(const char* name, cudaStream_t st);
+int launch_end();
+}  // namespace sdn_internal
+
+namespace {
+
+constexpr int TM = 128;                 // output pixels per tile (= TMEM lanes)
+constexpr int TK = 64;                  // K block: 64 bf16 = 128 bytes = one swizzle row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * TK * 2;    // 16 KB
+constexpr int NTHREADS = 192;
+
+struct ConvParams {
+    int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad;
+    int bw, bh, bn, tiles_w, tiles_h, tiles_n;
+    __nv_bfloat16* out;                 // [N, Ho, Wo, Cout]
+    const float* scale;                 // [Cout] or null (= 1)
+    const float* shift;                 // [Cout] or null (= 0)
+    const __nv_bfloat16* residual;      // [N, Ho, Wo, Cout] or null
+    int relu;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp `SmemDescriptor`), K-major tile of 128-byte rows with the
+// 128-byte swizzle: start address >> 4 in bits [0,14), LBO unused (0), SBO = 1024 B (one 8-row group) in bits [32,46),
+// version 1 in bits [46,48), layout_type SWIZZLE_128B = 2 in bits [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr_bytes & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (`InstrDescriptor`): D = F32 (bit 4), A = BF16 (bits 7..9 = 1), B = BF16 (bits 10..12 = 1),
+// both K-major, N >> 3 in bits [17,23), M >> 4 in bits [24,29)
+template <int TN>
+__device__ __forceinline__ constexpr uint32_t idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+template <int TN>
+__global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    // the swizzle pattern is a function of the address bits [4,10): tiles must start on 1024-byte boundaries
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int B_BYTES = TN * TK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // tile coordinates: blockIdx.x -> (tile_n, tile_h, tile_w); blockIdx.y -> output-channel block
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int tn = t;
+    const int wo0 = tw * p.bw, ho0 = th * p.bh, n0 = tn * p.bn;
+    const int co0 = blockIdx.y * TN;
+    const int cblocks = p.Cin / TK;
+    const int kblocks = p.KH * p.KW * cblocks;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        mbar_init(&s_tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {        // the MMA warp owns the accumulator columns in tensor memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)TN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+            for (int kb = 0; kb < kblocks; kb++) {
+                const int st = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(&s_empty[st], (uint32_t)(((kb / STAGES) - 1) & 1));
+                const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                unsigned char* sA = smem + st * STAGE_BYTES;
+                unsigned char* sB = sA + A_BYTES;
+                mbar_expect_tx(&s_full[st], (uint32_t)STAGE_BYTES);
+                tma_load_4d(sA, &tmA, &s_full[st], cb * TK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, n0);
+                tma_load_2d(sB, &tmB, &s_full[st], kb * TK, co0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; kb++) {
+                const int st = kb % STAGES;
+                mbar_wait(&s_full[st], (uint32_t)((kb / STAGES) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_BYTES;
+#pragma unroll
+                for (int j = 0; j < TK / 16; j++) {     // K = 16 per UMMA = 32 bytes along the swizzled row
+                    const uint64_t da = make_desc_sw128(a0 + j * 32), db = make_desc_sw128(b0 + j * 32);
+                    const uint32_t accumulate = (kb > 0 || j > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem), "l"(da), "l"(db), "r"(idesc<TN>()), "r"(accumulate) : "memory");
+                }
+                // frees the stage when every UMMA issued so far has completed (implies fence::before_thread_sync)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             ::"r"(smem_u32(&s_empty[st])) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         ::"r"(smem_u32(&s_tmem_full)) : "memory");
+        }
+    } else {
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31; lane = tile row = one output pixel =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int per_img = p.bh * p.bw;
+        const int nl = row / per_img, rem = row - nl * per_img;
+        const int hl = rem / p.bw, wl = rem - hl * p.bw;
+        const int n = n0 + nl, ho = ho0 + hl, wo = wo0 + wl;
+        const bool valid = n < p.N && ho < p.Ho && wo < p.Wo;
+        const size_t pix = ((size_t)n * p.Ho + ho) * p.Wo + wo;
+        mbar_wait(&s_tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int c = co0 + c0;
+            if (valid && c < p.Cout) {
+                float y[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float sc = p.scale ? __ldg(p.scale + c + j) : 1.0f;
+                    const float sh = p.shift ? __ldg(p.shift + c + j) : 0.0f;
+                    y[j] = __fmaf_rn(__uint_as_float(v[j]), sc, sh);
+                }
+                if (p.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + c);
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint4 r = __ldg(rp + g);
+                        const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int h = 0; h < 4; h++) {
+                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[h]);
+                            y[g * 8 + h * 2] += __low2float(b2);
+                            y[g * 8 + h * 2 + 1] += __high2float(b2);
+                        }
+                    }
+                }
+                uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c);
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        float a = y[g * 8 + h * 2], b = y[g * 8 + h * 2 + 1];
+                        if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+                        w4[h] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    op[g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TN));
+}
+
+// im2col for convolutions whose input has too few channels for a 64-wide K block (the 7x7 stem of ResNet-18, Cin = 3):
+// out[n, ho, wo, (kh*KW + kw)*Cin + c] = in[n, ho*s + kh - p, wo*s + kw - p, c] (zero outside, zero beyond KH*KW*Cin up
+// to Kpad); the stem then runs as a 1x1 convolution over Kpad channels.
+__global__ void __launch_bounds__(256) k_im2col_nhwc(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                     int N, int H, int W, int Cin, int Ho, int Wo, int KH, int KW,
+                                                     int stride, int pad, int Kpad) {
+    const long total = (long)N * Ho * Wo * Kpad;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        long r = i / Kpad;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int n = (int)(r / Ho);
+        __nv_bfloat16 v = __float2bfloat16(0.0f);
+        if (k < KH * KW * Cin) {
+            const int c = k % Cin, tap = k / Cin, kw = tap % KW, kh = tap / KW;
+            const int hi = ho * stride + kh - pad, wi = wo * stride + kw - pad;
+            if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = in[(((size_t)n * H + hi) * W + wi) * Cin + c];
+        }
+        out[i] = v;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;      // resolved once; the driver entry point never changes
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int pick_patch(int Ho, int Wo, int N, int stride, int* bw, int* bh, int* bn) {
+    // 128 output pixels per tile as bn x bh x bw; choose the shape that wastes the fewest rows.  TMA boxes are at most 256
+    // elements per dimension before the traversal stride: bw * stride <= 256.
+    long best = -1;
+    for (int w = 128; w >= 1; w >>= 1) {
+        if (w * stride > 256) continue;
+        for (int h = 128 / w; h >= 1; h >>= 1) {
+            if (h * stride > 256) continue;
+            const int n = 128 / (w * h);
+            const long tiles = (long)((Wo + w - 1) / w) * ((Ho + h - 1) / h) * ((N + n - 1) / n);
+            if (best < 0 || tiles < best) { best = tiles; *bw = w; *bh = h; *bn = n; }
+        }
+    }
+    return best > 0 ? 0 : SDN_E_ARG;
+}
+
+}  // namespace
+
+extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
+    if (!c || !c->input || !c->weight || !c->output) return SDN_E_ARG;
+    if (c->N <= 0 || c->H <= 0 || c->W <= 0 || c->Cin <= 0 || c->Cout <= 0 || c->KH <= 0 || c->KW <= 0 || c->stride <= 0 ||
+        c->pad < 0)
+        return SDN_E_ARG;
+    if (c->Cin % TK != 0 || c->Cout % 64 != 0) return SDN_E_ARG;        // pad channels on the caller's side
+    if ((reinterpret_cast<uintptr_t>(c->input) & 15) || (reinterpret_cast<uintptr_t>(c->weight) & 15) ||
+        (reinterpret_cast<uintptr_t>(c->output) & 15) || (reinterpret_cast<uintptr_t>(c->residual) & 15))
+        return SDN_E_ARG;
+    const int Ho = (c->H + 2 * c->pad - c->KH) / c->stride + 1, Wo = (c->W + 2 * c->pad - c->KW) / c->stride + 1;
+    if (Ho <= 0 || Wo <= 0) return SDN_E_ARG;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return (int)cudaErrorNotSupported;
+
+    ConvParams p;
+    p.N = c->N; p.H = c->H; p.W = c->W; p.Cin = c->Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = c->Cout;
+    p.KH = c->KH; p.KW = c->KW; p.stride = c->stride; p.pad = c->pad;
+    int rc = pick_patch(Ho, Wo, c->N, c->stride, &p.bw, &p.bh, &p.bn);
+    if (rc) return rc;
+    p.tiles_w = (Wo + p.bw - 1) / p.bw; p.tiles_h = (Ho + p.bh - 1) / p.bh; p.tiles_n = (c->N + p.bn - 1) / p.bn;
+    p.out = (__nv_bfloat16*)c->output; p.scale = c->scale; p.shift = c->shift;
+    p.residual = (const __nv_bfloat16*)c->residual; p.relu = c->relu;
+
+    const int TN = (c->Cout % 128 == 0) ? 128 : 64;
+    alignas(64) CUtensorMap tmA, tmB;
+    {   // activations: dims (fastest first) {C, W, H, N}
+        const cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
+        const cuuint64_t strides[3] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)c->W * c->Cin * 2,
+                                       (cuuint64_t)c->H * c->W * c->Cin * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)TK, (cuuint32_t)(p.bw * c->stride), (cuuint32_t)(p.bh * c->stride),
+                                   (cuuint32_t)p.bn};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)c->stride, (cuuint32_t)c->stride, 1};
+        const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c->input, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return SDN_E_ARG;
+    }
+    {   // weights: [Cout, KH*KW*Cin], dims {K, Cout}
+        const cuuint64_t K = (cuuint64_t)c->KH * c->KW * c->Cin;
+        const cuuint64_t dims[2] = {K, (cuuint64_t)c->Cout};
+        const cuuint64_t strides[1] = {K * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TN};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c->weight, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return SDN_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(c->Cout / TN));
+    const size_t smem = (size_t)STAGES * (A_BYTES + TN * TK * 2) + 1024;
+    cudaError_t e;
+    if (TN == 128) {
+        e = cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return (int)e;
+        sdn_internal::launch_begin("k_conv_tc", st);
+        k_conv_tc<128><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+    } else {
+        e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return (int)e;
+        sdn_internal::launch_begin("k_conv_tc", st);
+        k_conv_tc<64><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+    }
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_im2col_nhwc(const void* input, void* output, int N, int H, int W, int Cin, int KH, int KW, int stride,
+                               int pad, int Kpad, void* stream) {
+    if (!input || !output || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || pad < 0 ||
+        Kpad < KH * KW * Cin)
+        return SDN_E_ARG;
+    const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return SDN_E_ARG;
+    const long total = (long)N * Ho * Wo * Kpad;
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    sdn_internal::launch_begin("k_im2col_nhwc", (cudaStream_t)stream);
+    k_im2col_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)input, (__nv_bfloat16*)output, N, H, W, Cin,
+                                                            Ho, Wo, KH, KW, stride, pad, Kpad);
+    return sdn_internal::launch_end();
+}

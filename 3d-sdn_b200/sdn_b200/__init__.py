@@ -57,6 +57,14 @@ class _Objects(ctypes.Structure):
                 ('vertices', ctypes.c_void_p)]
 
 
+class _Conv2d(ctypes.Structure):
+    _fields_ = [('N', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('Cin', ctypes.c_int),
+                ('Cout', ctypes.c_int), ('KH', ctypes.c_int), ('KW', ctypes.c_int), ('stride', ctypes.c_int),
+                ('pad', ctypes.c_int), ('relu', ctypes.c_int), ('input', ctypes.c_void_p), ('weight', ctypes.c_void_p),
+                ('scale', ctypes.c_void_p), ('shift', ctypes.c_void_p), ('residual', ctypes.c_void_p),
+                ('output', ctypes.c_void_p)]
+
+
 def lib():
     """Load libsdn_b200.so (built by __graft_entry__.build() / csrc/build.py).  Fails loudly when absent."""
     global _lib
@@ -79,6 +87,8 @@ def lib():
                                          ctypes.c_size_t, vp]
         L.sdn_rasterize_forward.argtypes = [ctypes.POINTER(_Raster), vp]
         L.sdn_linear_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
+        L.sdn_conv2d_forward.argtypes = [ctypes.POINTER(_Conv2d), vp]
+        L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_objects_forward.argtypes = [ctypes.POINTER(_Objects), vp]
         L.sdn_objects_backward.argtypes = [ctypes.POINTER(_Objects), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
@@ -359,6 +369,61 @@ class LinearTCFunction(torch.autograd.Function):
 
 def linear_tc(x, weight, bias=None, relu=False):
     return LinearTCFunction.apply(x, weight, bias, relu)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# convolution on the tcgen05 tensor cores (csrc/sdn_conv_tc.cu)
+# --------------------------------------------------------------------------------------------------------------
+def pack_conv_weight(weight, cin_pad=None, cout_pad=None):
+    """torch Conv2d weight [Cout, Cin, KH, KW] -> the kernel's K-major operand [Cout_pad, KH, KW, Cin_pad] bf16
+    (zero rows / channels for the padding; Cin_pad, Cout_pad multiples of 64)."""
+    co, ci, kh, kw = weight.shape
+    cin_pad = cin_pad or (ci + 63) // 64 * 64
+    cout_pad = cout_pad or (co + 63) // 64 * 64
+    w = torch.zeros(cout_pad, kh, kw, cin_pad, device=weight.device, dtype=torch.bfloat16)
+    w[:co, :, :, :ci] = weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
+    return w.contiguous()
+
+
+def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False):
+    """x [N, H, W, Cin] bf16 NHWC (Cin a multiple of 64), w_packed [Cout, KH, KW, Cin] bf16 (pack_conv_weight) ->
+    [N, Ho, Wo, Cout] bf16:  act(scale * conv(x, w) + shift (+ residual)).  sdn_conv2d_forward: implicit GEMM, TMA
+    loads, tcgen05.mma with fp32 accumulation in tensor memory.  Inference-path operator (no autograd)."""
+    _need_cuda(x, w_packed, scale, shift, residual)
+    if x.dtype != torch.bfloat16 or w_packed.dtype != torch.bfloat16 or x.dim() != 4 or w_packed.dim() != 4:
+        raise SdnError('conv2d_tc: x [N,H,W,Cin] and w [Cout,KH,KW,Cin] must be bf16')
+    x, w_packed = x.contiguous(), w_packed.contiguous()
+    N, H, W, Cin = x.shape
+    Cout, KH, KW, Cw = w_packed.shape
+    if Cw != Cin or Cin % 64 or Cout % 64:
+        raise SdnError('conv2d_tc: channels must match and be multiples of 64 (got Cin %d / %d, Cout %d)' % (Cin, Cw, Cout))
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=torch.bfloat16)
+    f32 = lambda t: None if t is None else t.detach().float().contiguous()      # noqa: E731
+    scale, shift = f32(scale), f32(shift)
+    if residual is not None:
+        residual = residual.contiguous()
+        if residual.shape != out.shape or residual.dtype != torch.bfloat16:
+            raise SdnError('conv2d_tc: residual must be bf16 with the output shape %s' % (tuple(out.shape),))
+    c = _Conv2d(N, H, W, Cin, Cout, KH, KW, int(stride), int(pad), 1 if relu else 0, x.data_ptr(), w_packed.data_ptr(),
+                None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
+                None if residual is None else residual.data_ptr(), out.data_ptr())
+    with torch.cuda.device(x.device):
+        _check(lib().sdn_conv2d_forward(ctypes.byref(c), _stream()))
+    return out
+
+
+def im2col_nhwc(x, KH, KW, stride, pad, Kpad):
+    """x [N,H,W,Cin] bf16 -> [N,Ho,Wo,Kpad] bf16 patches (sdn_im2col_nhwc): turns a few-channel stem convolution into a
+    1x1 convolution over Kpad channels."""
+    _need_cuda(x)
+    x = x.contiguous()
+    N, H, W, Cin = x.shape
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    out = torch.empty(N, Ho, Wo, Kpad, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _check(lib().sdn_im2col_nhwc(_ptr(x), _ptr(out), N, H, W, Cin, KH, KW, int(stride), int(pad), int(Kpad), _stream()))
+    return out
 
 
 class MeshBank(object):

@@ -166,6 +166,36 @@ int sdn_objects_backward(const sdn_objects* o, const float* grad_vertices, float
                          float* grad_rotations, float* grad_translations, float* grad_ptrans, float* grad_zoom,
                          float* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- convolution on the tcgen05 tensor cores -------------------------------------------------------------------
+ * Replaces the cuDNN convolutions behind torch.nn.Conv2d in the image encoder's ResNet-18 trunk
+ * (geometric/derender3d/models/derenderer.py:25-27,35-43 -> torchvision resnet18) and in the textural generator
+ * (textural/models/networks.py:211-283).  Implicit GEMM, bf16 operands, fp32 accumulation in tensor memory:
+ *   output[n, ho, wo, co] = act( scale[co] * sum_{kh,kw,ci} input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci]
+ *                                                     * weight[co, kh, kw, ci]  + shift[co]  (+ residual[n, ho, wo, co]) )
+ * input  [N, H, W, Cin]   bf16 NHWC (channels-last), Cin a multiple of 64 (pad with zero channels);
+ * weight [Cout, KH, KW, Cin] bf16 (K contiguous),   Cout a multiple of 64;
+ * output [N, Ho, Wo, Cout] bf16 NHWC, Ho = (H + 2 pad - KH) / stride + 1; residual (optional) has the output's shape;
+ * scale / shift [Cout] fp32 (NULL = 1 / 0): a folded BatchNorm (eval mode) or a bias.  All pointers 16-byte aligned.
+ * Zero padding is done by the TMA unit (out-of-bounds box elements read as 0); other paddings (reflection) are the
+ * caller's (pad the input, pass pad = 0). */
+typedef struct sdn_conv2d {
+    int N, H, W, Cin, Cout, KH, KW, stride, pad, relu;
+    const void* input;
+    const void* weight;
+    const float* scale;
+    const float* shift;
+    const void* residual;
+    void* output;
+} sdn_conv2d;
+
+int sdn_conv2d_forward(const sdn_conv2d* c, void* stream);
+
+/* im2col for inputs with few channels (the 7x7 stem, Cin = 3): output [N, Ho, Wo, Kpad] bf16 with
+ * output[.., (kh*KW + kw)*Cin + ci] = input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci] (0 outside and beyond
+ * KH*KW*Cin); the stem then runs through sdn_conv2d_forward as a 1x1 convolution over Kpad channels. */
+int sdn_im2col_nhwc(const void* input, void* output, int N, int H, int W, int Cin, int KH, int KW, int stride, int pad,
+                    int Kpad, void* stream);
+
 /* ---- test-time scene compositor ------------------------------------------------------------------------------
  * Replaces the per-object loop of geometric/scripts/main.py:547-606 (to_pil_image -> resize -> PIL paste -> to_tensor
  * on the CPU, far to near) for the M drawn objects of one frame.  Bit-identical to Pillow's bilinear resize; the

@@ -1,0 +1,110 @@
+"""sdn_conv2d_forward (implicit GEMM: TMA tensor-map loads, tcgen05.mma, fp32 accumulation in tensor memory) against
+torch's fp32 convolution on the SAME bf16-rounded operands.  The output is stored as bf16 (relative rounding 2^-9), so the
+bar is rel-L2 <= 4e-3 on the result and <= 2e-2 against the unrounded fp32 convolution (operand rounding 2^-9 each)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    import sdn_b200
+    sdn_b200.lib()
+    return torch.device('cuda:0')
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _case(dev, N, H, W, Cin, Cout, K, stride, pad, seed, relu=False, residual=False, affine=False):
+    import sdn_b200
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
+    xb, wb = x.bfloat16().float(), w.bfloat16().float()
+    ref = F.conv2d(xb, wb, stride=stride, padding=pad)
+    scale = shift = res = None
+    if affine:
+        scale, shift = 0.5 + torch.rand(Cout, generator=g), torch.randn(Cout, generator=g)
+        ref = ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if residual:
+        res = torch.randn(ref.shape, generator=g).bfloat16()
+        ref = ref + res.float()
+    if relu:
+        ref = ref.clamp_min(0)
+    xn = x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous()
+    wp = sdn_b200.pack_conv_weight(w.to(dev))
+    if xn.shape[-1] % 64:
+        xn = F.pad(xn, (0, wp.shape[-1] - xn.shape[-1]))
+    out = sdn_b200.conv2d_tc(xn, wp, stride, pad, None if scale is None else scale.to(dev),
+                             None if shift is None else shift.to(dev),
+                             None if res is None else res.to(dev).permute(0, 2, 3, 1).contiguous(), relu)
+    got = out[..., :Cout].permute(0, 3, 1, 2).float().cpu()
+    assert got.shape == ref.shape
+    return _rel(got, ref), _rel(got, F.conv2d(x, w, stride=stride, padding=pad)) if not (affine or residual or relu) else 0.0
+
+
+RESNET18_B16 = [    # every distinct convolution shape of torchvision resnet18 at 224x224 after the stem (H = W)
+    (56, 64, 64, 3, 1, 1), (56, 64, 128, 3, 2, 1), (56, 64, 128, 1, 2, 0), (28, 128, 128, 3, 1, 1),
+    (28, 128, 256, 3, 2, 1), (28, 128, 256, 1, 2, 0), (14, 256, 256, 3, 1, 1), (14, 256, 512, 3, 2, 1),
+    (14, 256, 512, 1, 2, 0), (7, 512, 512, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize('HW,Cin,Cout,K,stride,pad', RESNET18_B16)
+def test_resnet18_layer_shapes_batch16(dev, HW, Cin, Cout, K, stride, pad):
+    e_same, e_fp32 = _case(dev, 16, HW, HW, Cin, Cout, K, stride, pad, seed=HW + Cout + K)
+    assert e_same <= 4e-3, e_same
+    assert e_fp32 <= 2e-2, e_fp32
+
+
+def test_stem_7x7_through_im2col(dev):
+    """conv1 of ResNet-18 (3 -> 64, 7x7, stride 2, pad 3): im2col to 192 channels, then a 1x1 convolution."""
+    import sdn_b200
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 3, 224, 224, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) / 12.0
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
+    cols = sdn_b200.im2col_nhwc(x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous(), 7, 7, 2, 3, 192)
+    assert cols.shape == (4, 112, 112, 192)
+    wk = torch.zeros(64, 1, 1, 192, device=dev, dtype=torch.bfloat16)
+    wk[:, 0, 0, :147] = w.to(dev).permute(0, 2, 3, 1).reshape(64, 147).bfloat16()        # (kh, kw, ci) order
+    out = sdn_b200.conv2d_tc(cols, wk, 1, 0)
+    assert _rel(out.permute(0, 3, 1, 2).float().cpu(), ref) <= 4e-3
+
+
+@pytest.mark.parametrize('relu,residual,affine', [(True, False, True), (True, True, True), (False, True, False)])
+def test_epilogue_scale_shift_residual_relu(dev, relu, residual, affine):
+    e, _ = _case(dev, 3, 20, 28, 128, 192, 3, 1, 1, seed=9, relu=relu, residual=residual, affine=affine)
+    assert e <= 4e-3, e
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,K,stride,pad', [
+    (1, 9, 13, 64, 64, 3, 1, 1),        # ragged: partial tiles in both directions
+    (5, 7, 7, 64, 128, 3, 1, 1),        # several images per 128-pixel tile, odd batch
+    (2, 33, 65, 64, 64, 3, 2, 1),       # stride 2 with odd sizes
+    (1, 16, 48, 128, 64, 7, 1, 0),      # 7x7 valid convolution (the generator's stem after reflection padding)
+    (2, 8, 8, 1024, 1024, 3, 1, 0),     # 1024 channels (the generator's residual blocks), valid
+    (1, 12, 20, 40, 48, 3, 1, 1),       # channel counts that need padding to 64
+])
+def test_shapes_and_edges(dev, N, H, W, Cin, Cout, K, stride, pad):
+    e, _ = _case(dev, N, H, W, Cin, Cout, K, stride, pad, seed=N + H + W)
+    assert e <= 4e-3, e
+
+
+def test_argument_errors(dev):
+    import sdn_b200
+    x = torch.zeros(1, 8, 8, 64, device=dev, dtype=torch.bfloat16)
+    w = torch.zeros(64, 3, 3, 64, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(sdn_b200.SdnError):
+        sdn_b200.conv2d_tc(x.float(), w)                           # not bf16
+    with pytest.raises(sdn_b200.SdnError):
+        sdn_b200.conv2d_tc(x[..., :32].contiguous(), w[..., :32].contiguous())     # channels not a multiple of 64
+    with pytest.raises(sdn_b200.SdnError):
+        sdn_b200.conv2d_tc(x.cpu(), w.cpu())                       # no CPU fallback
+    assert sdn_b200.conv2d_tc(x, w, 1, 1).abs().sum() == 0
