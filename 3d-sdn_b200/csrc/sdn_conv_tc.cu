@@ -47,7 +47,7 @@ struct ConvParams {
     const float* scale;                 // [Cout] or null (= 1)
     const float* shift;                 // [Cout] or null (= 0)
     const __nv_bfloat16* residual;      // [N, Ho, Wo, Cout] or null
-    int relu;
+    int relu;                           // activation: 0 none, 1 ReLU, 2 tanh
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
                         float a = y[g * 8 + h * 2], b = y[g * 8 + h * 2 + 1];
-                        if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        if (p.relu == 1) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                        else if (p.relu == 2) { a = tanhf(a); b = tanhf(b); }
                         const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
                         w4[h] = *reinterpret_cast<const uint32_t*>(&b2);
                     }
@@ -267,6 +268,50 @@ __global__ void __launch_bounds__(256) k_im2col_nhwc(const __nv_bfloat16* __rest
             if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = in[(((size_t)n * H + hi) * W + wi) * Cin + c];
         }
         out[i] = v;
+    }
+}
+
+// ---- instance normalisation of an NHWC bf16 tensor (textural/models/networks.py:23-29: InstanceNorm2d, affine=False) ----
+// stats: per (n, c) sum and sum of squares over H*W, fp32, one atomicAdd per (block, channel).  A block covers `rows`
+// pixels of one image; thread t owns channel pair (2t, 2t+1) of a 2*blockDim-wide channel slab (coalesced 4-byte reads).
+__global__ void __launch_bounds__(256) k_inorm_stats(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
+                                                     int HW, int C, int rows) {
+    const int n = blockIdx.z;
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 2;
+    if (c >= C) return;
+    const int r0 = blockIdx.x * rows, r1 = min(r0 + rows, HW);
+    const __nv_bfloat16* base = x + (size_t)n * HW * C + c;
+    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+    for (int r = r0; r < r1; r++) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + (size_t)r * C);
+        const float a = __low2float(v), b = __high2float(v);
+        s0 += a; s1 += b; q0 = __fmaf_rn(a, a, q0); q1 = __fmaf_rn(b, b, q1);
+    }
+    float* o = stats + ((size_t)n * C + c) * 2;
+    atomicAdd(o, s0); atomicAdd(o + 1, q0); atomicAdd(o + 2, s1); atomicAdd(o + 3, q1);
+}
+
+// apply: y = act((x - mean) * rsqrt(var + eps) (+ residual)); biased variance like torch.nn.InstanceNorm2d
+__global__ void __launch_bounds__(256) k_inorm_apply(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                                                     const __nv_bfloat16* __restrict__ residual,
+                                                     __nv_bfloat16* __restrict__ y, int HW, int C, float eps, int act,
+                                                     long total2) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long)gridDim.x * blockDim.x) {
+        const long e = i * 2;
+        const int c = (int)(e % C);
+        const long n = e / ((long)HW * C);
+        const float* st = stats + ((size_t)n * C + c) * 2;
+        const float inv = 1.0f / (float)HW;
+        const float m0 = st[0] * inv, m1 = st[2] * inv;
+        const float r0 = rsqrtf(fmaxf(st[1] * inv - m0 * m0, 0.0f) + eps), r1 = rsqrtf(fmaxf(st[3] * inv - m1 * m1, 0.0f) + eps);
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + e);
+        float a = (__low2float(v) - m0) * r0, b = (__high2float(v) - m1) * r1;
+        if (residual) {
+            const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(residual + e);
+            a += __low2float(rr); b += __high2float(rr);
+        }
+        if (act == 1) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+        *reinterpret_cast<__nv_bfloat162*>(y + e) = __floats2bfloat162_rn(a, b);
     }
 }
 
@@ -382,5 +427,28 @@ extern "C" int sdn_im2col_nhwc(const void* input, void* output, int N, int H, in
     sdn_internal::launch_begin("k_im2col_nhwc", (cudaStream_t)stream);
     k_im2col_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)input, (__nv_bfloat16*)output, N, H, W, Cin,
                                                             Ho, Wo, KH, KW, stride, pad, Kpad);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_instance_norm_nhwc(const void* x, const void* residual, void* y, float* stats, int N, int HW, int C,
+                                      float eps, int act, void* stream) {
+    if (!x || !y || !stats || N <= 0 || HW <= 0 || C <= 0 || (C & 1)) return SDN_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)N * C, st);
+    if (e != cudaSuccess) return (int)e;
+    const int threads = C / 2 < 256 ? ((C / 2 + 31) / 32 * 32) : 256;
+    const int slabs = (C / 2 + threads - 1) / threads;
+    int rows = 64;
+    while (rows < 4096 && (long)((HW + rows - 1) / rows) * slabs * N > 148L * 16) rows *= 2;
+    const dim3 grid((unsigned)((HW + rows - 1) / rows), (unsigned)slabs, (unsigned)N);
+    sdn_internal::launch_begin("k_inorm_stats", st);
+    k_inorm_stats<<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, stats, HW, C, rows);
+    int rc = sdn_internal::launch_end();
+    if (rc) return rc;
+    const long total2 = (long)N * HW * C / 2;
+    const unsigned blocks = (unsigned)((total2 + 255) / 256 > 148L * 16 ? 148L * 16 : (total2 + 255) / 256);
+    sdn_internal::launch_begin("k_inorm_apply", st);
+    k_inorm_apply<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y,
+                                         HW, C, eps, act, total2);
     return sdn_internal::launch_end();
 }

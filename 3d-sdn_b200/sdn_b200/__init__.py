@@ -89,6 +89,7 @@ def lib():
         L.sdn_linear_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
         L.sdn_conv2d_forward.argtypes = [ctypes.POINTER(_Conv2d), vp]
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_objects_forward.argtypes = [ctypes.POINTER(_Objects), vp]
         L.sdn_objects_backward.argtypes = [ctypes.POINTER(_Objects), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
@@ -405,12 +406,29 @@ def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=Non
         residual = residual.contiguous()
         if residual.shape != out.shape or residual.dtype != torch.bfloat16:
             raise SdnError('conv2d_tc: residual must be bf16 with the output shape %s' % (tuple(out.shape),))
-    c = _Conv2d(N, H, W, Cin, Cout, KH, KW, int(stride), int(pad), 1 if relu else 0, x.data_ptr(), w_packed.data_ptr(),
+    act = {False: 0, True: 1, None: 0, 'relu': 1, 'tanh': 2, 'none': 0}[relu]
+    c = _Conv2d(N, H, W, Cin, Cout, KH, KW, int(stride), int(pad), act, x.data_ptr(), w_packed.data_ptr(),
                 None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
                 None if residual is None else residual.data_ptr(), out.data_ptr())
     with torch.cuda.device(x.device):
         _check(lib().sdn_conv2d_forward(ctypes.byref(c), _stream()))
     return out
+
+
+def instance_norm_nhwc(x, residual=None, relu=False, eps=1e-5, out=None):
+    """x [N, H, W, C] bf16 NHWC -> relu?((x - mean) / sqrt(var + eps) (+ residual)) per (n, c) over H*W
+    (sdn_instance_norm_nhwc; torch.nn.InstanceNorm2d(affine=False) semantics)."""
+    _need_cuda(x, residual)
+    x = x.contiguous()
+    N, H, W, C = x.shape
+    y = torch.empty_like(x) if out is None else out
+    stats = torch.empty(N, C, 2, device=x.device, dtype=torch.float32)
+    if residual is not None:
+        residual = residual.contiguous()
+    with torch.cuda.device(x.device):
+        _check(lib().sdn_instance_norm_nhwc(_ptr(x), _ptr(residual), _ptr(y), _ptr(stats), N, H * W, C, float(eps),
+                                            1 if relu else 0, _stream()))
+    return y
 
 
 def im2col_nhwc(x, KH, KW, stride, pad, Kpad):

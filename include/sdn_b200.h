@@ -179,7 +179,8 @@ int sdn_objects_backward(const sdn_objects* o, const float* grad_vertices, float
  * Zero padding is done by the TMA unit (out-of-bounds box elements read as 0); other paddings (reflection) are the
  * caller's (pad the input, pass pad = 0). */
 typedef struct sdn_conv2d {
-    int N, H, W, Cin, Cout, KH, KW, stride, pad, relu;
+    int N, H, W, Cin, Cout, KH, KW, stride, pad;
+    int relu;               /* activation after scale / shift / residual: 0 none, 1 ReLU, 2 tanh */
     const void* input;
     const void* weight;
     const float* scale;
@@ -195,6 +196,12 @@ int sdn_conv2d_forward(const sdn_conv2d* c, void* stream);
  * KH*KW*Cin); the stem then runs through sdn_conv2d_forward as a 1x1 convolution over Kpad channels. */
 int sdn_im2col_nhwc(const void* input, void* output, int N, int H, int W, int Cin, int KH, int KW, int stride, int pad,
                     int Kpad, void* stream);
+
+/* Instance normalisation of an NHWC bf16 tensor [N, HW, C] (textural/models/networks.py:23-29: InstanceNorm2d with
+ * affine=False): y = act((x - mean_nc) / sqrt(var_nc + eps) (+ residual)), biased variance over HW, act 0 none / 1 ReLU.
+ * stats: fp32 scratch [N, C, 2] (sum, sum of squares), cleared by the call.  C even; y may alias x. */
+int sdn_instance_norm_nhwc(const void* x, const void* residual, void* y, float* stats, int N, int HW, int C, float eps,
+                           int act, void* stream);
 
 /* ---- test-time scene compositor ------------------------------------------------------------------------------
  * Replaces the per-object loop of geometric/scripts/main.py:547-606 (to_pil_image -> resize -> PIL paste -> to_tensor
