@@ -43,7 +43,8 @@ constexpr int NTHREADS = 192;
 struct ConvParams {
     int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad;
     int bw, bh, bn, tiles_w, tiles_h, tiles_n;
-    __nv_bfloat16* out;                 // [N, Ho, Wo, Cout]
+    __nv_bfloat16* out;                 // pixel (n, ho, wo) at out + n*osn + ho*osh + wo*osw (elements), Cout contiguous
+    long osn, osh, osw;
     const float* scale;                 // [Cout] or null (= 1)
     const float* shift;                 // [Cout] or null (= 0)
     const __nv_bfloat16* residual;      // [N, Ho, Wo, Cout] or null
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
     }
     if (warp == 1) {        // the MMA warp owns the accumulator columns in tensor memory
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"((uint32_t)TN));
+                     "r"((uint32_t)(TN < 32 ? 32 : TN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -185,28 +186,39 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         const int hl = rem / p.bw, wl = rem - hl * p.bw;
         const int n = n0 + nl, ho = ho0 + hl, wo = wo0 + wl;
         const bool valid = n < p.N && ho < p.Ho && wo < p.Wo;
-        const size_t pix = ((size_t)n * p.Ho + ho) * p.Wo + wo;
+        const size_t pix = ((size_t)n * p.Ho + ho) * p.Wo + wo;                 // residual: dense [N, Ho, Wo, Cout]
+        const size_t opix = (size_t)((long)n * p.osn + (long)ho * p.osh + (long)wo * p.osw);
         mbar_wait(&s_tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr int CW = TN >= 32 ? 32 : 16;          // accumulator columns per tcgen05.ld
 #pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
+        for (int c0 = 0; c0 < TN; c0 += CW) {
             uint32_t v[32];
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
+            if (CW == 32) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+            } else {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int c = co0 + c0;
             if (valid && c < p.Cout) {
-                float y[32];
+                float y[CW];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
+                for (int j = 0; j < CW; j++) {
                     const float sc = p.scale ? __ldg(p.scale + c + j) : 1.0f;
                     const float sh = p.shift ? __ldg(p.shift + c + j) : 0.0f;
                     y[j] = __fmaf_rn(__uint_as_float(v[j]), sc, sh);
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                 if (p.residual) {
                     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + c);
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
+                    for (int g = 0; g < CW / 8; g++) {
                         const uint4 r = __ldg(rp + g);
                         const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -225,9 +237,9 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                         }
                     }
                 }
-                uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c);
+                uint4* op = reinterpret_cast<uint4*>(p.out + opix + c);
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
+                for (int g = 0; g < CW / 8; g++) {
                     uint32_t w4[4];
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(TN < 32 ? 32 : TN)));
 }
 
 // im2col for convolutions whose input has too few channels for a 64-wide K block (the 7x7 stem of ResNet-18, Cin = 3):
@@ -272,46 +284,101 @@ __global__ void __launch_bounds__(256) k_im2col_nhwc(const __nv_bfloat16* __rest
 }
 
 // ---- instance normalisation of an NHWC bf16 tensor (textural/models/networks.py:23-29: InstanceNorm2d, affine=False) ----
-// stats: per (n, c) sum and sum of squares over H*W, fp32, one atomicAdd per (block, channel).  A block covers `rows`
-// pixels of one image; thread t owns channel pair (2t, 2t+1) of a 2*blockDim-wide channel slab (coalesced 4-byte reads).
+// stats: per (n, c) sum and sum of squares over H*W in fp32.  A block of 256 threads covers `rows` pixels of one image
+// and a slab of up to 512 channels: thread t owns channel pair t % (slab/2) and walks rows t / (slab/2), += 256/(slab/2)
+// (coalesced 4-byte reads along C, several rows in flight per block); partials are combined through shared memory and
+// leave the block as one atomicAdd per channel.
 __global__ void __launch_bounds__(256) k_inorm_stats(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats,
-                                                     int HW, int C, int rows) {
+                                                     int HW, int C, int rows, int pairs) {
+    __shared__ float s_part[256 * 4];
     const int n = blockIdx.z;
-    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 2;
-    if (c >= C) return;
+    const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs, nrl = 256 / pairs;
+    const int c = (blockIdx.y * pairs + cp) * 2;
     const int r0 = blockIdx.x * rows, r1 = min(r0 + rows, HW);
-    const __nv_bfloat16* base = x + (size_t)n * HW * C + c;
     float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
-    for (int r = r0; r < r1; r++) {
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + (size_t)r * C);
-        const float a = __low2float(v), b = __high2float(v);
-        s0 += a; s1 += b; q0 = __fmaf_rn(a, a, q0); q1 = __fmaf_rn(b, b, q1);
+    if (c < C && rl < nrl) {
+        const __nv_bfloat16* base = x + (size_t)n * HW * C + c;
+#pragma unroll 4
+        for (int r = r0 + rl; r < r1; r += nrl) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(base + (size_t)r * C);
+            const float a = __low2float(v), b = __high2float(v);
+            s0 += a; s1 += b; q0 = __fmaf_rn(a, a, q0); q1 = __fmaf_rn(b, b, q1);
+        }
     }
-    float* o = stats + ((size_t)n * C + c) * 2;
-    atomicAdd(o, s0); atomicAdd(o + 1, q0); atomicAdd(o + 2, s1); atomicAdd(o + 3, q1);
+    s_part[threadIdx.x * 4] = s0; s_part[threadIdx.x * 4 + 1] = q0; s_part[threadIdx.x * 4 + 2] = s1; s_part[threadIdx.x * 4 + 3] = q1;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        for (int k = 1; k < nrl; k++) {
+            const float* o = s_part + (k * pairs + cp) * 4;
+            s0 += o[0]; q0 += o[1]; s1 += o[2]; q1 += o[3];
+        }
+        float* o = stats + ((size_t)n * C + c) * 2;
+        atomicAdd(o, s0); atomicAdd(o + 1, q0); atomicAdd(o + 2, s1); atomicAdd(o + 3, q1);
+    }
 }
 
-// apply: y = act((x - mean) * rsqrt(var + eps) (+ residual)); biased variance like torch.nn.InstanceNorm2d
+// apply: y = act((x - mean) * rsqrt(var + eps) (+ residual)); biased variance like torch.nn.InstanceNorm2d.
+// grid.y = image; a thread handles 8 consecutive channels (16 bytes) of one pixel; 32-bit index arithmetic.
 __global__ void __launch_bounds__(256) k_inorm_apply(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
                                                      const __nv_bfloat16* __restrict__ residual,
-                                                     __nv_bfloat16* __restrict__ y, int HW, int C, float eps, int act,
-                                                     long total2) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (long)gridDim.x * blockDim.x) {
-        const long e = i * 2;
-        const int c = (int)(e % C);
-        const long n = e / ((long)HW * C);
-        const float* st = stats + ((size_t)n * C + c) * 2;
-        const float inv = 1.0f / (float)HW;
-        const float m0 = st[0] * inv, m1 = st[2] * inv;
-        const float r0 = rsqrtf(fmaxf(st[1] * inv - m0 * m0, 0.0f) + eps), r1 = rsqrtf(fmaxf(st[3] * inv - m1 * m1, 0.0f) + eps);
-        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + e);
-        float a = (__low2float(v) - m0) * r0, b = (__high2float(v) - m1) * r1;
-        if (residual) {
-            const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(residual + e);
-            a += __low2float(rr); b += __high2float(rr);
+                                                     __nv_bfloat16* __restrict__ y, int HW, int C, float eps, int act) {
+    const int n = blockIdx.y;
+    const int cg = C >> 3;                                      // 16-byte groups per pixel
+    const unsigned total = (unsigned)HW * (unsigned)cg;
+    const float inv = 1.0f / (float)HW;
+    const size_t img = (size_t)n * HW * C;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned g = i % (unsigned)cg;
+        const float* st = stats + ((size_t)n * C + g * 8) * 2;
+        const size_t e = img + (size_t)i * 8;
+        const uint4 xv = *reinterpret_cast<const uint4*>(x + e);
+        uint4 rv = make_uint4(0, 0, 0, 0);
+        if (residual) rv = *reinterpret_cast<const uint4*>(residual + e);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            const float4 s4 = *reinterpret_cast<const float4*>(st + h * 4);      // (sum, sumsq) of two channels
+            const float m0 = s4.x * inv, m1 = s4.z * inv;
+            const float r0 = rsqrtf(fmaxf(s4.y * inv - m0 * m0, 0.0f) + eps), r1 = rsqrtf(fmaxf(s4.w * inv - m1 * m1, 0.0f) + eps);
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&xw[h]);
+            float a = (__low2float(v) - m0) * r0, b = (__high2float(v) - m1) * r1;
+            if (residual) {
+                const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
+                a += __low2float(rr); b += __high2float(rr);
+            }
+            if (act == 1) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+            const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+            ow[h] = *reinterpret_cast<const uint32_t*>(&o2);
         }
-        if (act == 1) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-        *reinterpret_cast<__nv_bfloat162*>(y + e) = __floats2bfloat162_rn(a, b);
+        *reinterpret_cast<uint4*>(y + e) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// ---- C. reflection padding of an NHWC bf16 tensor (nn.ReflectionPad2d), with optional zero channels up to Cp ----
+__global__ void __launch_bounds__(256) k_reflect_pad_nhwc(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          int N, int H, int W, int C, int pad, int Cp) {
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad, cg = Cp >> 3;
+    const long total = (long)N * Hp * Wp * cg;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        long r = i / cg;
+        const int wp = (int)(r % Wp); r /= Wp;
+        const int hp = (int)(r % Hp);
+        const int n = (int)(r / Hp);
+        int h = hp - pad, w = wp - pad;
+        h = h < 0 ? -h : (h >= H ? 2 * (H - 1) - h : h);
+        w = w < 0 ? -w : (w >= W ? 2 * (W - 1) - w : w);
+        const __nv_bfloat16* src = x + (((size_t)n * H + h) * W + w) * C + g * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (g * 8 + 8 <= C && (C & 7) == 0) v = *reinterpret_cast<const uint4*>(src);
+        else if (g * 8 < C) {
+            __nv_bfloat16 t[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) t[k] = g * 8 + k < C ? src[k] : __float2bfloat16(0.0f);
+            v = *reinterpret_cast<const uint4*>(t);
+        }
+        *reinterpret_cast<uint4*>(y + (size_t)i * 8) = v;
     }
 }
 
@@ -354,12 +421,15 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
     if (c->N <= 0 || c->H <= 0 || c->W <= 0 || c->Cin <= 0 || c->Cout <= 0 || c->KH <= 0 || c->KW <= 0 || c->stride <= 0 ||
         c->pad < 0)
         return SDN_E_ARG;
-    if (c->Cin % TK != 0 || c->Cout % 64 != 0) return SDN_E_ARG;        // pad channels on the caller's side
+    if (c->Cin % TK != 0 || (c->Cout % 64 != 0 && c->Cout != 16)) return SDN_E_ARG;    // pad channels on the caller's side
     if ((reinterpret_cast<uintptr_t>(c->input) & 15) || (reinterpret_cast<uintptr_t>(c->weight) & 15) ||
         (reinterpret_cast<uintptr_t>(c->output) & 15) || (reinterpret_cast<uintptr_t>(c->residual) & 15))
         return SDN_E_ARG;
-    const int Ho = (c->H + 2 * c->pad - c->KH) / c->stride + 1, Wo = (c->W + 2 * c->pad - c->KW) / c->stride + 1;
+    // output extent: the convolution's own, or the caller's (reads beyond the input are zeros: asymmetric padding)
+    const int Ho = c->out_h > 0 ? c->out_h : (c->H + 2 * c->pad - c->KH) / c->stride + 1;
+    const int Wo = c->out_w > 0 ? c->out_w : (c->W + 2 * c->pad - c->KW) / c->stride + 1;
     if (Ho <= 0 || Wo <= 0) return SDN_E_ARG;
+    if (c->residual && (c->out_stride_w > 0)) return SDN_E_ARG;     // residual is read densely
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return (int)cudaErrorNotSupported;
 
@@ -370,9 +440,12 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
     if (rc) return rc;
     p.tiles_w = (Wo + p.bw - 1) / p.bw; p.tiles_h = (Ho + p.bh - 1) / p.bh; p.tiles_n = (c->N + p.bn - 1) / p.bn;
     p.out = (__nv_bfloat16*)c->output; p.scale = c->scale; p.shift = c->shift;
+    if (c->out_stride_w > 0) { p.osn = c->out_stride_n; p.osh = c->out_stride_h; p.osw = c->out_stride_w; }
+    else { p.osw = c->Cout; p.osh = (long)Wo * c->Cout; p.osn = (long)Ho * Wo * c->Cout; }
+    if ((p.osn | p.osh | p.osw) & 7) return SDN_E_ARG;              // 16-byte stores
     p.residual = (const __nv_bfloat16*)c->residual; p.relu = c->relu;
 
-    const int TN = (c->Cout % 128 == 0) ? 128 : 64;
+    const int TN = c->Cout == 16 ? 16 : ((c->Cout % 128 == 0) ? 128 : 64);
     alignas(64) CUtensorMap tmA, tmB;
     {   // activations: dims (fastest first) {C, W, H, N}
         const cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
@@ -406,11 +479,16 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         if (e) return (int)e;
         sdn_internal::launch_begin("k_conv_tc", st);
         k_conv_tc<128><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
-    } else {
+    } else if (TN == 64) {
         e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e) return (int)e;
         sdn_internal::launch_begin("k_conv_tc", st);
         k_conv_tc<64><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+    } else {
+        e = cudaFuncSetAttribute(k_conv_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return (int)e;
+        sdn_internal::launch_begin("k_conv_tc", st);
+        k_conv_tc<16><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
     }
     return sdn_internal::launch_end();
 }
@@ -432,23 +510,38 @@ extern "C" int sdn_im2col_nhwc(const void* input, void* output, int N, int H, in
 
 extern "C" int sdn_instance_norm_nhwc(const void* x, const void* residual, void* y, float* stats, int N, int HW, int C,
                                       float eps, int act, void* stream) {
-    if (!x || !y || !stats || N <= 0 || HW <= 0 || C <= 0 || (C & 1)) return SDN_E_ARG;
+    if (!x || !y || !stats || N <= 0 || HW <= 0 || C <= 0 || (C & 7)) return SDN_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)N * C, st);
     if (e != cudaSuccess) return (int)e;
-    const int threads = C / 2 < 256 ? ((C / 2 + 31) / 32 * 32) : 256;
-    const int slabs = (C / 2 + threads - 1) / threads;
-    int rows = 64;
-    while (rows < 4096 && (long)((HW + rows - 1) / rows) * slabs * N > 148L * 16) rows *= 2;
+    int pairs = C / 2;                      // channel pairs per block: a power-of-two divisor of 256 where possible
+    if (pairs > 256) pairs = 256;
+    while (256 % pairs) pairs--;
+    const int slabs = (C / 2 + pairs - 1) / pairs;
+    // rows per block: enough blocks to fill the machine (~8 per SM), at least one trip of the block's row lanes
+    const int nrl = 256 / pairs;
+    long want = ((long)HW * slabs * N + 148L * 8 - 1) / (148L * 8);
+    int rows = (int)(want < 4L * nrl ? 4L * nrl : (want > 8192 ? 8192 : want));
+    rows = (rows + nrl - 1) / nrl * nrl;
     const dim3 grid((unsigned)((HW + rows - 1) / rows), (unsigned)slabs, (unsigned)N);
     sdn_internal::launch_begin("k_inorm_stats", st);
-    k_inorm_stats<<<grid, threads, 0, st>>>((const __nv_bfloat16*)x, stats, HW, C, rows);
+    k_inorm_stats<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, stats, HW, C, rows, pairs);
     int rc = sdn_internal::launch_end();
     if (rc) return rc;
-    const long total2 = (long)N * HW * C / 2;
-    const unsigned blocks = (unsigned)((total2 + 255) / 256 > 148L * 16 ? 148L * 16 : (total2 + 255) / 256);
+    const long total = (long)HW * (C / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148L * 16 ? 148L * 16 : (total + 255) / 256);
     sdn_internal::launch_begin("k_inorm_apply", st);
-    k_inorm_apply<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y,
-                                         HW, C, eps, act, total2);
+    k_inorm_apply<<<dim3(blocks, (unsigned)N), 256, 0, st>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual,
+                                                            (__nv_bfloat16*)y, HW, C, eps, act);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_reflect_pad_nhwc(const void* x, void* y, int N, int H, int W, int C, int pad, int Cp, void* stream) {
+    if (!x || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || pad < 0 || pad >= H || pad >= W || Cp < C || (Cp & 7))
+        return SDN_E_ARG;
+    const long total = (long)N * (H + 2 * pad) * (W + 2 * pad) * (Cp / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148L * 32 ? 148L * 32 : (total + 255) / 256);
+    sdn_internal::launch_begin("k_reflect_pad_nhwc", (cudaStream_t)stream);
+    k_reflect_pad_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, pad, Cp);
     return sdn_internal::launch_end();
 }

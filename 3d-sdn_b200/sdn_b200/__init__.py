@@ -62,7 +62,9 @@ class _Conv2d(ctypes.Structure):
                 ('Cout', ctypes.c_int), ('KH', ctypes.c_int), ('KW', ctypes.c_int), ('stride', ctypes.c_int),
                 ('pad', ctypes.c_int), ('relu', ctypes.c_int), ('input', ctypes.c_void_p), ('weight', ctypes.c_void_p),
                 ('scale', ctypes.c_void_p), ('shift', ctypes.c_void_p), ('residual', ctypes.c_void_p),
-                ('output', ctypes.c_void_p)]
+                ('output', ctypes.c_void_p), ('out_h', ctypes.c_int), ('out_w', ctypes.c_int),
+                ('out_stride_n', ctypes.c_longlong), ('out_stride_h', ctypes.c_longlong),
+                ('out_stride_w', ctypes.c_longlong)]
 
 
 def lib():
@@ -90,6 +92,7 @@ def lib():
         L.sdn_conv2d_forward.argtypes = [ctypes.POINTER(_Conv2d), vp]
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
+        L.sdn_reflect_pad_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_objects_forward.argtypes = [ctypes.POINTER(_Objects), vp]
         L.sdn_objects_backward.argtypes = [ctypes.POINTER(_Objects), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
@@ -377,42 +380,68 @@ def linear_tc(x, weight, bias=None, relu=False):
 # --------------------------------------------------------------------------------------------------------------
 def pack_conv_weight(weight, cin_pad=None, cout_pad=None):
     """torch Conv2d weight [Cout, Cin, KH, KW] -> the kernel's K-major operand [Cout_pad, KH, KW, Cin_pad] bf16
-    (zero rows / channels for the padding; Cin_pad, Cout_pad multiples of 64)."""
+    (zero rows / channels for the padding; Cin_pad a multiple of 64; Cout_pad a multiple of 64, or 16 for <= 16 outputs)."""
     co, ci, kh, kw = weight.shape
     cin_pad = cin_pad or (ci + 63) // 64 * 64
-    cout_pad = cout_pad or (co + 63) // 64 * 64
+    cout_pad = cout_pad or (16 if co <= 16 else (co + 63) // 64 * 64)
     w = torch.zeros(cout_pad, kh, kw, cin_pad, device=weight.device, dtype=torch.bfloat16)
     w[:co, :, :, :ci] = weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
     return w.contiguous()
 
 
-def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False):
+def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False, out_hw=None, out=None):
     """x [N, H, W, Cin] bf16 NHWC (Cin a multiple of 64), w_packed [Cout, KH, KW, Cin] bf16 (pack_conv_weight) ->
-    [N, Ho, Wo, Cout] bf16:  act(scale * conv(x, w) + shift (+ residual)).  sdn_conv2d_forward: implicit GEMM, TMA
-    loads, tcgen05.mma with fp32 accumulation in tensor memory.  Inference-path operator (no autograd)."""
-    _need_cuda(x, w_packed, scale, shift, residual)
+    [N, Ho, Wo, Cout] bf16:  act(scale * conv(x, w) + shift (+ residual)), act = relu in (False, True / 'relu', 'tanh').
+    sdn_conv2d_forward: implicit GEMM, TMA loads, tcgen05.mma with fp32 accumulation in tensor memory.
+    out_hw = (Ho, Wo) overrides the output extent (reads beyond the input are zeros); out = a [N, Ho, Wo, Cout] bf16 VIEW
+    (channels contiguous, strides multiples of 8) to write into -- e.g. one parity phase of a transposed convolution.
+    Inference-path operator (no autograd)."""
+    _need_cuda(x, w_packed, scale, shift, residual, out)
     if x.dtype != torch.bfloat16 or w_packed.dtype != torch.bfloat16 or x.dim() != 4 or w_packed.dim() != 4:
         raise SdnError('conv2d_tc: x [N,H,W,Cin] and w [Cout,KH,KW,Cin] must be bf16')
     x, w_packed = x.contiguous(), w_packed.contiguous()
     N, H, W, Cin = x.shape
     Cout, KH, KW, Cw = w_packed.shape
-    if Cw != Cin or Cin % 64 or Cout % 64:
-        raise SdnError('conv2d_tc: channels must match and be multiples of 64 (got Cin %d / %d, Cout %d)' % (Cin, Cw, Cout))
-    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
-    out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=torch.bfloat16)
+    if Cw != Cin or Cin % 64 or (Cout % 64 and Cout != 16):
+        raise SdnError('conv2d_tc: channels must match; Cin a multiple of 64, Cout a multiple of 64 or 16 '
+                       '(got Cin %d / %d, Cout %d)' % (Cin, Cw, Cout))
+    if out_hw is None:
+        Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    else:
+        Ho, Wo = int(out_hw[0]), int(out_hw[1])
+    sn = sh = sw = 0
+    if out is None:
+        out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=torch.bfloat16)
+    else:
+        if tuple(out.shape) != (N, Ho, Wo, Cout) or out.dtype != torch.bfloat16 or out.stride(3) != 1:
+            raise SdnError('conv2d_tc: out must be a bf16 [%d,%d,%d,%d] view with contiguous channels' % (N, Ho, Wo, Cout))
+        sn, sh, sw = out.stride(0), out.stride(1), out.stride(2)
     f32 = lambda t: None if t is None else t.detach().float().contiguous()      # noqa: E731
     scale, shift = f32(scale), f32(shift)
     if residual is not None:
         residual = residual.contiguous()
-        if residual.shape != out.shape or residual.dtype != torch.bfloat16:
-            raise SdnError('conv2d_tc: residual must be bf16 with the output shape %s' % (tuple(out.shape),))
+        if tuple(residual.shape) != (N, Ho, Wo, Cout) or residual.dtype != torch.bfloat16:
+            raise SdnError('conv2d_tc: residual must be bf16 with the output shape %s' % ((N, Ho, Wo, Cout),))
     act = {False: 0, True: 1, None: 0, 'relu': 1, 'tanh': 2, 'none': 0}[relu]
     c = _Conv2d(N, H, W, Cin, Cout, KH, KW, int(stride), int(pad), act, x.data_ptr(), w_packed.data_ptr(),
                 None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
-                None if residual is None else residual.data_ptr(), out.data_ptr())
+                None if residual is None else residual.data_ptr(), out.data_ptr(),
+                0 if out_hw is None else Ho, 0 if out_hw is None else Wo, sn, sh, sw)
     with torch.cuda.device(x.device):
         _check(lib().sdn_conv2d_forward(ctypes.byref(c), _stream()))
     return out
+
+
+def reflect_pad_nhwc(x, pad, cpad=None):
+    """nn.ReflectionPad2d(pad) on x [N,H,W,C] bf16 NHWC, channels zero-padded to cpad (sdn_reflect_pad_nhwc)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    N, H, W, C = x.shape
+    cp = C if cpad is None else int(cpad)
+    y = torch.empty(N, H + 2 * pad, W + 2 * pad, cp, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _check(lib().sdn_reflect_pad_nhwc(_ptr(x), _ptr(y), N, H, W, C, int(pad), cp, _stream()))
+    return y
 
 
 def instance_norm_nhwc(x, residual=None, relu=False, eps=1e-5, out=None):

@@ -47,7 +47,11 @@ def _reflect_index(n, p, device):
 
 
 def reflect_pad_nhwc(x, p, cpad=None):
-    """nn.ReflectionPad2d(p) on an NHWC tensor (two gathers); optionally zero-pads the channels to `cpad`."""
+    """nn.ReflectionPad2d(p) on an NHWC tensor; optionally zero-pads the channels to `cpad`.  One native pass on CUDA
+    bf16 tensors (sdn_reflect_pad_nhwc), two torch gathers otherwise."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and (x.shape[-1] if cpad is None else cpad) % 8 == 0:
+        import sdn_b200
+        return sdn_b200.reflect_pad_nhwc(x, p, cpad)
     N, H, W, C = x.shape
     x = x.index_select(1, _reflect_index(H, p, x.device)).index_select(2, _reflect_index(W, p, x.device))
     if cpad is not None and cpad > C:
@@ -85,9 +89,9 @@ class GlobalGenerator(nn.Module):
         import sdn_b200
         key = id(conv)
         if key not in self._packed:
-            self._packed[key] = (sdn_b200.pack_conv_weight(conv.weight),
-                                 None if conv.bias is None else F.pad(conv.bias.detach().float(),
-                                                                      (0, (-conv.out_channels) % 64)))
+            w = sdn_b200.pack_conv_weight(conv.weight)
+            self._packed[key] = (w, None if conv.bias is None else F.pad(conv.bias.detach().float(),
+                                                                         (0, w.shape[0] - conv.out_channels)))
         return self._packed[key]
 
     def _deconv_w(self, m):
@@ -132,16 +136,16 @@ class GlobalGenerator(nn.Module):
         return sdn_b200.conv2d_tc(x, w, conv.stride[0], pad, None, b, None, act)
 
     def _deconv(self, x, m):
+        """Four parity phases, each written straight into its interleaved positions of the [N, 2H, 2W, Co] output (strided
+        store in the kernel's epilogue); phase taps that reach one pixel beyond the input read TMA's zeros."""
         import sdn_b200
         phases, b = self._deconv_w(m)
         N, H, W, C = x.shape
-        xp = F.pad(x, (0, 0, 0, 1, 0, 1))                            # one zero column / row after the last (offset +1)
         Co = phases[(0, 0)].shape[0]
-        out = torch.empty(N, H, 2, W, 2, Co, device=x.device, dtype=torch.bfloat16)
+        out = torch.empty(N, 2 * H, 2 * W, Co, device=x.device, dtype=torch.bfloat16)
         for (ph, pw), w in phases.items():
-            xin = xp[:, :H + ph, :W + pw].contiguous() if (ph, pw) != (1, 1) else xp
-            out[:, :, ph, :, pw] = sdn_b200.conv2d_tc(xin, w, 1, 0, None, b, None, None)
-        return out.view(N, 2 * H, 2 * W, Co)
+            sdn_b200.conv2d_tc(x, w, 1, 0, None, b, None, None, out_hw=(H, W), out=out[:, ph::2, pw::2])
+        return out
 
     def forward_tc(self, input):
         """input [N, input_nc, H, W] float (CUDA) -> [N, output_nc, H, W] float32."""
@@ -185,7 +189,7 @@ class GlobalGenerator(nn.Module):
             else:
                 raise NotImplementedError('GlobalGenerator tcgen05 path: layer %r' % (m,))
         C = layers[-2].out_channels if isinstance(layers[-1], nn.Tanh) else x.shape[-1]
-        return x[..., :C].permute(0, 3, 1, 2).float().contiguous()
+        return x[..., :C].permute(0, 3, 1, 2).float().contiguous()      # NCHW fp32 like the reference module
 
     def forward(self, input):
         if input.is_cuda and not torch.is_grad_enabled():

@@ -173,7 +173,7 @@ int sdn_objects_backward(const sdn_objects* o, const float* grad_vertices, float
  *   output[n, ho, wo, co] = act( scale[co] * sum_{kh,kw,ci} input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci]
  *                                                     * weight[co, kh, kw, ci]  + shift[co]  (+ residual[n, ho, wo, co]) )
  * input  [N, H, W, Cin]   bf16 NHWC (channels-last), Cin a multiple of 64 (pad with zero channels);
- * weight [Cout, KH, KW, Cin] bf16 (K contiguous),   Cout a multiple of 64;
+ * weight [Cout, KH, KW, Cin] bf16 (K contiguous),   Cout a multiple of 64, or exactly 16 (few-channel heads);
  * output [N, Ho, Wo, Cout] bf16 NHWC, Ho = (H + 2 pad - KH) / stride + 1; residual (optional) has the output's shape;
  * scale / shift [Cout] fp32 (NULL = 1 / 0): a folded BatchNorm (eval mode) or a bias.  All pointers 16-byte aligned.
  * Zero padding is done by the TMA unit (out-of-bounds box elements read as 0); other paddings (reflection) are the
@@ -187,6 +187,10 @@ typedef struct sdn_conv2d {
     const float* shift;
     const void* residual;
     void* output;
+    int out_h, out_w;       /* 0 = the convolution's own extent; else that many output rows / columns (input reads
+                               beyond the tensor are zeros: one-sided padding, used by the transposed-convolution phases) */
+    long long out_stride_n, out_stride_h, out_stride_w;   /* element strides of an output pixel; all 0 = dense NHWC.
+                               Multiples of 8.  Lets four parity phases interleave into one [N, 2H, 2W, C] tensor. */
 } sdn_conv2d;
 
 int sdn_conv2d_forward(const sdn_conv2d* c, void* stream);
@@ -199,9 +203,13 @@ int sdn_im2col_nhwc(const void* input, void* output, int N, int H, int W, int Ci
 
 /* Instance normalisation of an NHWC bf16 tensor [N, HW, C] (textural/models/networks.py:23-29: InstanceNorm2d with
  * affine=False): y = act((x - mean_nc) / sqrt(var_nc + eps) (+ residual)), biased variance over HW, act 0 none / 1 ReLU.
- * stats: fp32 scratch [N, C, 2] (sum, sum of squares), cleared by the call.  C even; y may alias x. */
+ * stats: fp32 scratch [N, C, 2] (sum, sum of squares), cleared by the call.  C a multiple of 8; y may alias x. */
 int sdn_instance_norm_nhwc(const void* x, const void* residual, void* y, float* stats, int N, int HW, int C, float eps,
                            int act, void* stream);
+
+/* nn.ReflectionPad2d(pad) on an NHWC bf16 tensor, channels zero-padded from C to Cp (a multiple of 8):
+ * y [N, H + 2 pad, W + 2 pad, Cp] (textural/models/networks.py:218,238,250-269). */
+int sdn_reflect_pad_nhwc(const void* x, void* y, int N, int H, int W, int C, int pad, int Cp, void* stream);
 
 /* ---- test-time scene compositor ------------------------------------------------------------------------------
  * Replaces the per-object loop of geometric/scripts/main.py:547-606 (to_pil_image -> resize -> PIL paste -> to_tensor

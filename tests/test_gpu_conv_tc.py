@@ -97,6 +97,37 @@ def test_shapes_and_edges(dev, N, H, W, Cin, Cout, K, stride, pad):
     assert e <= 4e-3, e
 
 
+def test_few_output_channels_strided_output_and_extent_override(dev):
+    import sdn_b200
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 64, 10, 14, generator=g)
+    w = torch.randn(3, 64, 7, 7, generator=g) / 56.0
+    ref = torch.tanh(F.conv2d(x.bfloat16().float(), w.bfloat16().float(), padding=3))
+    wp = sdn_b200.pack_conv_weight(w.to(dev))
+    assert wp.shape[0] == 16                                   # 3 outputs -> the 16-column tile, not 64
+    out = sdn_b200.conv2d_tc(x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous(), wp, 1, 3, relu='tanh')
+    assert _rel(out[..., :3].permute(0, 3, 1, 2).float().cpu(), ref) <= 4e-3
+    # extent override + strided destination: a 2x2-tap kernel evaluated at H x W outputs (one-sided zero padding),
+    # written into the odd / odd positions of a twice-as-large tensor
+    w2 = torch.randn(64, 64, 2, 2, generator=g) / 16.0
+    xr = x.bfloat16().float()
+    ref2 = F.conv2d(F.pad(xr, (0, 1, 0, 1)), w2.bfloat16().float())
+    big = torch.zeros(2, 20, 28, 64, device=dev, dtype=torch.bfloat16)
+    sdn_b200.conv2d_tc(x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous(), sdn_b200.pack_conv_weight(w2.to(dev)), 1, 0,
+                       out_hw=(10, 14), out=big[:, 1::2, 1::2])
+    assert _rel(big[:, 1::2, 1::2].permute(0, 3, 1, 2).float().cpu(), ref2) <= 4e-3
+    assert float(big[:, 0::2].abs().sum()) == 0 and float(big[:, :, 0::2].abs().sum()) == 0
+
+
+def test_reflect_pad_kernel(dev):
+    import sdn_b200
+    x = torch.randn(2, 9, 11, 48, generator=torch.Generator().manual_seed(3)).to(dev).bfloat16()
+    got = sdn_b200.reflect_pad_nhwc(x, 3, 64)
+    want = F.pad(x.permute(0, 3, 1, 2).float(), (3, 3, 3, 3), mode='reflect').permute(0, 2, 3, 1)
+    assert got.shape == (2, 15, 17, 64)
+    assert torch.equal(got[..., :48].float(), want) and float(got[..., 48:].abs().sum()) == 0
+
+
 def test_argument_errors(dev):
     import sdn_b200
     x = torch.zeros(1, 8, 8, 64, device=dev, dtype=torch.bfloat16)
