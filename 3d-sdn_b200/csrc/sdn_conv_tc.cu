@@ -521,7 +521,8 @@ extern "C" int sdn_instance_norm_nhwc(const void* x, const void* residual, void*
     // rows per block: enough blocks to fill the machine (~8 per SM), at least one trip of the block's row lanes
     const int nrl = 256 / pairs;
     long want = ((long)HW * slabs * N + 148L * 8 - 1) / (148L * 8);
-    int rows = (int)(want < 4L * nrl ? 4L * nrl : (want > 8192 ? 8192 : want));
+    // (every block ends with one atomicAdd per channel: at least 32 rows per row lane keep that traffic negligible)
+    int rows = (int)(want < 32L * nrl ? 32L * nrl : (want > 8192 ? 8192 : want));
     rows = (rows + nrl - 1) / nrl * nrl;
     const dim3 grid((unsigned)((HW + rows - 1) / rows), (unsigned)slabs, (unsigned)N);
     sdn_internal::launch_begin("k_inorm_stats", st);

@@ -41,16 +41,27 @@ class Derenderer(Module):
         self.fc2 = torch.nn.Linear(self.hidden_size, self.hidden_size)
         self._fc3 = torch.nn.Linear(self.hidden_size, sum(self.out_sizes.values()))
         self.tensor_core_head = os.environ.get('SDN_TC_HEAD', '0') == '1'
+        # eval-mode trunk on the hand-written tcgen05 convolution (encoder_tc.ResNet18TC: bf16 operands, BatchNorm folded
+        # into the epilogue).  Opt-in like the head (SDN_TC_TRUNK=1 or `tensor_core_trunk = True`): the reference is fp32.
+        self.tensor_core_trunk = os.environ.get('SDN_TC_TRUNK', '0') == '1'
+        self._trunk_tc = None
 
     def _trunk(self, images):
         """torchvision ResNet._forward_impl without its last Linear."""
+        if self.tensor_core_trunk and images.is_cuda and not self.training:
+            from derender3d.models.encoder_tc import ResNet18TC
+            if self._trunk_tc is None or self._trunk_tc.signature != ResNet18TC.weights_signature(self.net) or \
+                    self._trunk_tc.device != images.device:
+                self._trunk_tc = ResNet18TC(self.net)
+            return self._trunk_tc(images)
         n = self.net
         x = n.maxpool(n.relu(n.bn1(n.conv1(images))))
         x = n.layer4(n.layer3(n.layer2(n.layer1(x))))
         return torch.flatten(n.avgpool(x), 1)
 
     def forward(self, images, mroi_norms, droi_norms):
-        if images.is_cuda and (self.tensor_core_head or torch.is_autocast_enabled()):
+        if images.is_cuda and (self.tensor_core_head or torch.is_autocast_enabled() or
+                               (self.tensor_core_trunk and not self.training)):
             from sdn_b200 import linear_tc
             x = linear_tc(self._trunk(images), self.net.fc.weight, self.net.fc.bias, relu=True)
             x = torch.cat([x, mroi_norms.float(), droi_norms.float()], dim=1)

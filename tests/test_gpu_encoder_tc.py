@@ -1,0 +1,73 @@
+"""The encoder's ResNet-18 trunk on the tcgen05 convolution path (eval mode, BatchNorm folded into the epilogue) against
+torchvision's fp32 module with the same weights (derender3d/models/derenderer.py:25-43)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    import sdn_b200
+    sdn_b200.lib()
+    return torch.device('cuda:0')
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _encoder(dev):
+    from derender3d.models.derenderer import Derenderer
+    torch.manual_seed(0)
+    enc = Derenderer().to(dev).eval()
+    with torch.no_grad():       # non-trivial BatchNorm statistics, as after training
+        for m in enc.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0.0, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0.0, 0.2)
+    return enc
+
+
+def test_trunk_features_match_fp32_torchvision(dev):
+    enc = _encoder(dev)
+    x = torch.randn(16, 3, 224, 224, generator=torch.Generator().manual_seed(1)).to(dev)
+    with torch.no_grad():
+        want = enc._trunk(x)                                  # torchvision / cuDNN fp32
+        enc.tensor_core_trunk = True
+        import sdn_b200
+        n0 = sdn_b200.launch_count()
+        got = enc._trunk(x)
+        assert sdn_b200.launch_count() - n0 >= 21             # stem im2col + 20 convolutions (+ 3 downsample) went native
+    assert got.shape == want.shape == (16, 512)
+    assert _rel(got, want) <= 3e-2, _rel(got, want)
+
+
+def test_encoder_outputs_and_weight_refresh(dev):
+    enc = _encoder(dev)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(5, 3, 224, 224, generator=g).to(dev)
+    m, d = torch.randn(5, 2, generator=g).to(dev) * 0.1, (0.2 + torch.rand(5, 2, generator=g)).to(dev)
+    with torch.no_grad():
+        want = enc(x, m, d)
+        enc.tensor_core_trunk = True
+        got = enc(x, m, d)
+        for k in want:
+            assert got[k].shape == want[k].shape
+            assert _rel(got[k], want[k]) <= 6e-2, (k, _rel(got[k], want[k]))
+        # in-place weight update -> the packed / folded copy is rebuilt
+        first = enc._trunk_tc
+        enc.net.layer4[1].conv2.weight.mul_(0.5)
+        got2 = enc(x, m, d)
+        assert enc._trunk_tc is not first
+        enc.tensor_core_trunk = False
+        want2 = enc(x, m, d)
+        assert _rel(got2['_log_scales'], want2['_log_scales']) <= 6e-2
+    enc.train()
+    enc.tensor_core_trunk = True
+    out = enc(x, m, d)                                        # training mode: the autograd (cuDNN) path
+    assert out['_theta_deltas'].requires_grad
