@@ -498,14 +498,11 @@ def test_analysis_by_synthesis_reduces_silhouette_error(dev):
     assert refined['_masks'].shape == target.shape
 
 
-def test_analysis_by_synthesis_as_cuda_graph_matches_eager(dev):
-    """refine(graph=True): iteration 0 eager, the rest replays of one captured iteration; same loss trajectory."""
+def _refine_setup(dev, seed=3, S=64, B=4):
     from derender3d import TargetType
     from derender3d.models import Derenderer3d
-    from derender3d.optimise import refine
-    S, B = 64, 4
     model = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=_synthetic_objs()).to(dev)
-    blob, _ = _synthetic_blob(B, dev, seed=3)
+    blob, _ = _synthetic_blob(B, dev, seed=seed)
     model.train()
     model._force_no_sample = True
     with torch.no_grad():
@@ -513,10 +510,65 @@ def test_analysis_by_synthesis_as_cuda_graph_matches_eager(dev):
     start = dict(blob)
     start['_translation2ds'] = blob['_translation2ds'] + 0.08
     start['_log_scales'] = blob['_log_scales'] + 0.15
+    return model, start, target
+
+
+def test_analysis_by_synthesis_equals_the_reference_loop(dev):
+    """optimise.refine against a literal restatement of geometric/scripts/main.py:405-459 on fixed latents: train mode
+    with _force_no_sample, detached clones of the encoder outputs, Adam(lr 3e-2) over theta / translation2d / log-scale /
+    FFD coefficients, loss = mean((mse(_masks, pad_like(masks), reduce=False) + 100 * mean(ffd^2)) * (1 - pad_like(ignores,
+    replicate))).  Same renderer underneath, so the loss trajectories agree to float-sum reordering (the vertex scatter
+    of sdn_faces_backward uses float atomics)."""
+    from derender3d.optimise import refine
+    from derender3d.train_step import pad_like
+    model, start, target = _refine_setup(dev)
+    g = torch.Generator().manual_seed(4)
+    masks = torch.nn.functional.avg_pool2d(target, 2).round()             # GT masks arrive smaller than the render
+    ignores = (torch.rand(masks.shape, generator=g) > 0.9).float().to(dev)
+    n = 8
+    # ---- the reference loop, restated (main.py:424-456) ----
+    model.train()
+    model._force_no_sample = True
+    _blob = {k: (v.clone().detach() if isinstance(v, torch.Tensor) else v) for k, v in start.items()}
+    opt_vars = [_blob[k].requires_grad_() for k in ('_theta_deltas', '_translation2ds', '_log_scales', '_ffd_coeffs')]
+    optimizer = torch.optim.Adam(opt_vars, lr=3e-2)
+    ref_hist = []
+    for _ in range(n):
+        optimizer.zero_grad()
+        _blob.update(model.render(_blob))
+        _masks = _blob['_masks']
+        loss = torch.nn.functional.mse_loss(_masks, pad_like(masks, _masks), reduction='none') + \
+            100 * torch.mean(_blob['_ffd_coeffs'] ** 2)
+        loss = loss * (1 - pad_like(ignores, _masks, mode='replicate'))
+        loss = torch.mean(loss)
+        loss.backward()
+        optimizer.step()
+        ref_hist.append(float(loss))
+    out_blob, hist = refine(model, start, masks, ignores, num_opts=n)
+    hist = hist.cpu().tolist()
+    assert abs(hist[0] - ref_hist[0]) <= 1e-6 * abs(ref_hist[0])          # identical arithmetic before any update
+    assert rel_l2(torch.tensor(hist[:3]), torch.tensor(ref_hist[:3])) <= 1e-4
+    assert rel_l2(torch.tensor(hist), torch.tensor(ref_hist)) <= 2e-2
+    assert hist[-1] < hist[0]
+    for k in ('_translation2ds', '_log_scales', '_theta_deltas'):
+        assert rel_l2(out_blob[k], _blob[k].detach()) <= 2e-2, k
+
+
+def test_analysis_by_synthesis_as_cuda_graph_matches_eager(dev):
+    """refine(graph=True): iteration 0 eager, the rest replays of one captured iteration; same loss trajectory.
+
+    Why the trajectory bound is loose while the first steps are tight: forward and the per-face backward are
+    deterministic, but the face -> vertex scatter (sdn_faces_backward) and the per-object reductions of
+    sdn_objects_backward add floats with atomics, so two runs differ by ~1e-7 in the latent gradients.  Adam divides by
+    sqrt(v): components whose gradient is ~0 amplify that noise into the update, and a silhouette is a step function of
+    the latents -- once a boundary sample lands on the other side of an edge the loss moves by O(1 / pixels).  The first
+    iterations (no such flip yet) agree to 1e-4; 12 iterations to 5e-2."""
+    from derender3d.optimise import refine
+    model, start, target = _refine_setup(dev)
     ref_blob, ref_hist = refine(model, start, target, num_opts=12)
     out_blob, out_hist = refine(model, start, target, num_opts=12, graph=True)
     assert out_hist.shape == ref_hist.shape == (12,)
-    # float atomics reorder sums run to run; a sample that flips moves the trajectory slightly: 5e-2 on 12 iterations
+    assert rel_l2(out_hist[:3].cpu().numpy(), ref_hist[:3].cpu().numpy()) <= 1e-4, (out_hist.tolist(), ref_hist.tolist())
     assert rel_l2(out_hist.cpu().numpy(), ref_hist.cpu().numpy()) <= 5e-2, (out_hist.tolist(), ref_hist.tolist())
     assert float(out_hist[-1]) < float(out_hist[0])
     for k in ('_translation2ds', '_log_scales'):
