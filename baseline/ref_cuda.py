@@ -114,10 +114,11 @@ class Module(object):
 
 def faces_ndc(vertices, faces, angle_deg):
     """derender3d renderer glue in torch (renderer.py:243-262 + look / perspective / vertices_to_faces / fill_back)."""
-    v = vertices * torch.tensor([-1.0, 1.0, 1.0], device=vertices.device)
-    f = torch.cat([faces, faces.flip(-1)], dim=0)
-    z = -v[..., 2] * 0.99999
-    x, y = v[..., 0] * 0.99999, v[..., 1] * 0.99999
+    v = vertices * torch.tensor([-1.0, 1.0, 1.0], device=vertices.device)         # renderer.py:243
+    f = torch.cat([faces, faces.flip(-1)], dim=0)                                # fill_back, neural_renderer/renderer.py:41
+    # look(eye 0, direction (0,0,-1), up (0,1,0)): rows x = (-1,0,0), y = (0,1,0), z = (0,0,-1), each 0.99999 long
+    # (cf.normalize adds 1e-5 to the norm)
+    x, y, z = -v[..., 0] * 0.99999, v[..., 1] * 0.99999, -v[..., 2] * 0.99999
     w = math.tan(angle_deg * 3.1416 / 180.0)
     ndc = torch.stack([x / z / w, y / z / w, z], dim=-1)
     return ndc[f.long()].contiguous().float()               # [F, 3, 3]
