@@ -49,6 +49,7 @@ struct ConvParams {
     const float* shift;                 // [Cout] or null (= 0)
     const __nv_bfloat16* residual;      // [N, Ho, Wo, Cout] or null
     int relu;                           // activation: 0 none, 1 ReLU, 2 tanh
+    float* stats;                       // [N, Cout, 2] or null: per (image, channel) sum / sum of squares of the result
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         const size_t opix = (size_t)((long)n * p.osn + (long)ho * p.osh + (long)wo * p.osw);
         mbar_wait(&s_tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* sT = reinterpret_cast<float*>(smem) + q * (32 * 33);           // 32 x (CW + 1) floats per epilogue warp
         constexpr int CW = TN >= 32 ? 32 : 16;          // accumulator columns per tcgen05.ld
 #pragma unroll 1
         for (int c0 = 0; c0 < TN; c0 += CW) {
@@ -237,6 +239,10 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                         }
                     }
                 }
+                if (p.stats) {
+#pragma unroll
+                    for (int j = 0; j < CW; j++) sT[lane * (CW + 1) + j] = y[j];
+                }
                 uint4* op = reinterpret_cast<uint4*>(p.out + opix + c);
 #pragma unroll
                 for (int g = 0; g < CW / 8; g++) {
@@ -251,6 +257,25 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                     }
                     op[g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 }
+            } else if (p.stats) {
+#pragma unroll
+                for (int j = 0; j < CW; j++) sT[lane * (CW + 1) + j] = 0.0f;       // rows outside the image add nothing
+            }
+            if (p.stats && c < p.Cout) {
+                // column sums of this warp's 32 rows x CW channels through shared memory (the operand ring is idle now):
+                // lane j owns channel c + j; all 32 rows of a warp lie in ONE image (128 / bn >= 32 rows per image)
+                __syncwarp();
+                if (lane < CW) {
+                    float sm = 0.0f, sq = 0.0f;
+#pragma unroll 8
+                    for (int r = 0; r < 32; r++) { const float v1 = sT[r * (CW + 1) + lane]; sm += v1; sq = __fmaf_rn(v1, v1, sq); }
+                    const int nimg = n0 + (q * 32) / per_img;
+                    if (nimg < p.N) {
+                        float* o = p.stats + ((size_t)nimg * p.Cout + c + lane) * 2;
+                        atomicAdd(o, sm); atomicAdd(o + 1, sq);
+                    }
+                }
+                __syncwarp();
             }
         }
     }
@@ -444,6 +469,14 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
     else { p.osw = c->Cout; p.osh = (long)Wo * c->Cout; p.osn = (long)Ho * Wo * c->Cout; }
     if ((p.osn | p.osh | p.osw) & 7) return SDN_E_ARG;              // 16-byte stores
     p.residual = (const __nv_bfloat16*)c->residual; p.relu = c->relu;
+    p.stats = c->stats;
+    if (p.stats) {
+        if ((p.bh * p.bw) % 32) return SDN_E_ARG;                   // a warp's 32 rows must lie in one image
+        if (!c->stats_keep) {
+            const cudaError_t em = cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * (size_t)c->N * c->Cout, (cudaStream_t)stream);
+            if (em != cudaSuccess) return (int)em;
+        }
+    }
 
     const int TN = c->Cout == 16 ? 16 : ((c->Cout % 128 == 0) ? 128 : 64);
     alignas(64) CUtensorMap tmA, tmB;
@@ -534,6 +567,17 @@ extern "C" int sdn_instance_norm_nhwc(const void* x, const void* residual, void*
     sdn_internal::launch_begin("k_inorm_apply", st);
     k_inorm_apply<<<dim3(blocks, (unsigned)N), 256, 0, st>>>((const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual,
                                                             (__nv_bfloat16*)y, HW, C, eps, act);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_instance_norm_apply_nhwc(const void* x, const void* residual, void* y, const float* stats, int N, int HW,
+                                            int C, float eps, int act, void* stream) {
+    if (!x || !y || !stats || N <= 0 || HW <= 0 || C <= 0 || (C & 7)) return SDN_E_ARG;
+    const long total = (long)HW * (C / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148L * 16 ? 148L * 16 : (total + 255) / 256);
+    sdn_internal::launch_begin("k_inorm_apply", (cudaStream_t)stream);
+    k_inorm_apply<<<dim3(blocks, (unsigned)N), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, HW, C, eps, act);
     return sdn_internal::launch_end();
 }
 

@@ -64,7 +64,7 @@ class _Conv2d(ctypes.Structure):
                 ('scale', ctypes.c_void_p), ('shift', ctypes.c_void_p), ('residual', ctypes.c_void_p),
                 ('output', ctypes.c_void_p), ('out_h', ctypes.c_int), ('out_w', ctypes.c_int),
                 ('out_stride_n', ctypes.c_longlong), ('out_stride_h', ctypes.c_longlong),
-                ('out_stride_w', ctypes.c_longlong)]
+                ('out_stride_w', ctypes.c_longlong), ('stats', ctypes.c_void_p), ('stats_keep', ctypes.c_int)]
 
 
 def lib():
@@ -93,6 +93,7 @@ def lib():
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_reflect_pad_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
+        L.sdn_instance_norm_apply_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_objects_forward.argtypes = [ctypes.POINTER(_Objects), vp]
         L.sdn_objects_backward.argtypes = [ctypes.POINTER(_Objects), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
@@ -389,14 +390,17 @@ def pack_conv_weight(weight, cin_pad=None, cout_pad=None):
     return w.contiguous()
 
 
-def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False, out_hw=None, out=None):
+def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=None, relu=False, out_hw=None, out=None,
+              stats=None, stats_keep=False):
     """x [N, H, W, Cin] bf16 NHWC (Cin a multiple of 64), w_packed [Cout, KH, KW, Cin] bf16 (pack_conv_weight) ->
     [N, Ho, Wo, Cout] bf16:  act(scale * conv(x, w) + shift (+ residual)), act = relu in (False, True / 'relu', 'tanh').
     sdn_conv2d_forward: implicit GEMM, TMA loads, tcgen05.mma with fp32 accumulation in tensor memory.
     out_hw = (Ho, Wo) overrides the output extent (reads beyond the input are zeros); out = a [N, Ho, Wo, Cout] bf16 VIEW
     (channels contiguous, strides multiples of 8) to write into -- e.g. one parity phase of a transposed convolution.
+    stats = fp32 [N, Cout, 2]: receives per (image, channel) sum / sum of squares of the result before the activation
+    (cleared first unless stats_keep) -- the statistics of a following InstanceNorm2d, straight from the accumulators.
     Inference-path operator (no autograd)."""
-    _need_cuda(x, w_packed, scale, shift, residual, out)
+    _need_cuda(x, w_packed, scale, shift, residual, out, stats)
     if x.dtype != torch.bfloat16 or w_packed.dtype != torch.bfloat16 or x.dim() != 4 or w_packed.dim() != 4:
         raise SdnError('conv2d_tc: x [N,H,W,Cin] and w [Cout,KH,KW,Cin] must be bf16')
     x, w_packed = x.contiguous(), w_packed.contiguous()
@@ -426,7 +430,10 @@ def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=Non
     c = _Conv2d(N, H, W, Cin, Cout, KH, KW, int(stride), int(pad), act, x.data_ptr(), w_packed.data_ptr(),
                 None if scale is None else scale.data_ptr(), None if shift is None else shift.data_ptr(),
                 None if residual is None else residual.data_ptr(), out.data_ptr(),
-                0 if out_hw is None else Ho, 0 if out_hw is None else Wo, sn, sh, sw)
+                0 if out_hw is None else Ho, 0 if out_hw is None else Wo, sn, sh, sw,
+                None if stats is None else stats.data_ptr(), 1 if stats_keep else 0)
+    if stats is not None and (stats.dtype != torch.float32 or stats.numel() != N * Cout * 2 or not stats.is_contiguous()):
+        raise SdnError('conv2d_tc: stats must be a contiguous fp32 [N, Cout, 2] tensor')
     with torch.cuda.device(x.device):
         _check(lib().sdn_conv2d_forward(ctypes.byref(c), _stream()))
     return out
@@ -444,19 +451,24 @@ def reflect_pad_nhwc(x, pad, cpad=None):
     return y
 
 
-def instance_norm_nhwc(x, residual=None, relu=False, eps=1e-5, out=None):
+def instance_norm_nhwc(x, residual=None, relu=False, eps=1e-5, out=None, stats=None):
     """x [N, H, W, C] bf16 NHWC -> relu?((x - mean) / sqrt(var + eps) (+ residual)) per (n, c) over H*W
-    (sdn_instance_norm_nhwc; torch.nn.InstanceNorm2d(affine=False) semantics)."""
-    _need_cuda(x, residual)
+    (sdn_instance_norm_nhwc; torch.nn.InstanceNorm2d(affine=False) semantics).  stats = the fp32 [N, C, 2] sums a
+    convolution already produced (conv2d_tc(stats=...)): then only the normalising pass runs."""
+    _need_cuda(x, residual, stats)
     x = x.contiguous()
     N, H, W, C = x.shape
     y = torch.empty_like(x) if out is None else out
-    stats = torch.empty(N, C, 2, device=x.device, dtype=torch.float32)
     if residual is not None:
         residual = residual.contiguous()
     with torch.cuda.device(x.device):
-        _check(lib().sdn_instance_norm_nhwc(_ptr(x), _ptr(residual), _ptr(y), _ptr(stats), N, H * W, C, float(eps),
-                                            1 if relu else 0, _stream()))
+        if stats is None:
+            scratch = torch.empty(N, C, 2, device=x.device, dtype=torch.float32)
+            _check(lib().sdn_instance_norm_nhwc(_ptr(x), _ptr(residual), _ptr(y), _ptr(scratch), N, H * W, C, float(eps),
+                                                1 if relu else 0, _stream()))
+        else:
+            _check(lib().sdn_instance_norm_apply_nhwc(_ptr(x), _ptr(residual), _ptr(y), _ptr(stats), N, H * W, C,
+                                                      float(eps), 1 if relu else 0, _stream()))
     return y
 
 

@@ -111,14 +111,20 @@ class GlobalGenerator(nn.Module):
             self._packed[key] = (phases, bias)
         return self._packed[key]
 
-    def _norm(self, x, m, relu, residual=None):
+    @staticmethod
+    def _wants_stats(m):
+        """The following norm layer takes per-instance statistics: let the convolution's epilogue produce them."""
+        return isinstance(m, nn.InstanceNorm2d) and not ((not m.training) and m.track_running_stats and
+                                                         m.running_mean is not None)
+
+    def _norm(self, x, m, relu, residual=None, stats=None):
         """InstanceNorm2d(affine=False, track_running_stats=True): instance statistics in train mode, the running
         statistics in eval mode (torch semantics); BatchNorm2d in eval mode likewise folds to scale / shift."""
         import sdn_b200
         C = m.num_features
         use_running = (not m.training) and getattr(m, 'track_running_stats', False) and m.running_mean is not None
         if isinstance(m, nn.InstanceNorm2d) and not use_running:
-            return sdn_b200.instance_norm_nhwc(x, residual, relu, m.eps)
+            return sdn_b200.instance_norm_nhwc(x, residual, relu, m.eps, stats=stats)
         if not use_running:
             raise NotImplementedError('GlobalGenerator tcgen05 path: BatchNorm2d in training mode')
         rstd = torch.rsqrt(m.running_var.float() + m.eps)
@@ -130,12 +136,16 @@ class GlobalGenerator(nn.Module):
         y = y.clamp_min(0) if relu else y
         return F.pad(y.to(torch.bfloat16), (0, x.shape[-1] - C))
 
-    def _conv(self, x, conv, pad, act=None):
+    def _conv(self, x, conv, pad, act=None, stats=None):
         import sdn_b200
         w, b = self._conv_w(conv)
-        return sdn_b200.conv2d_tc(x, w, conv.stride[0], pad, None, b, None, act)
+        return sdn_b200.conv2d_tc(x, w, conv.stride[0], pad, None, b, None, act, stats=stats)
 
-    def _deconv(self, x, m):
+    @staticmethod
+    def _new_stats(x, channels):
+        return torch.empty(x.shape[0], channels, 2, device=x.device, dtype=torch.float32)
+
+    def _deconv(self, x, m, stats=None):
         """Four parity phases, each written straight into its interleaved positions of the [N, 2H, 2W, Co] output (strided
         store in the kernel's epilogue); phase taps that reach one pixel beyond the input read TMA's zeros."""
         import sdn_b200
@@ -143,15 +153,16 @@ class GlobalGenerator(nn.Module):
         N, H, W, C = x.shape
         Co = phases[(0, 0)].shape[0]
         out = torch.empty(N, 2 * H, 2 * W, Co, device=x.device, dtype=torch.bfloat16)
-        for (ph, pw), w in phases.items():
-            sdn_b200.conv2d_tc(x, w, 1, 0, None, b, None, None, out_hw=(H, W), out=out[:, ph::2, pw::2])
+        for k, ((ph, pw), w) in enumerate(phases.items()):
+            sdn_b200.conv2d_tc(x, w, 1, 0, None, b, None, None, out_hw=(H, W), out=out[:, ph::2, pw::2], stats=stats,
+                               stats_keep=k > 0)
         return out
 
     def forward_tc(self, input):
         """input [N, input_nc, H, W] float (CUDA) -> [N, output_nc, H, W] float32."""
         layers = list(self.model)
         x = input.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
-        i, pending_pad = 0, 0
+        i, pending_pad, pending_stats = 0, 0, None
         while i < len(layers):
             m = layers[i]
             if isinstance(m, nn.ReflectionPad2d):
@@ -166,25 +177,33 @@ class GlobalGenerator(nn.Module):
                     if x.shape[-1] % 64:
                         x = F.pad(x, (0, (-x.shape[-1]) % 64))
                 nxt = layers[i + 1] if i + 1 < len(layers) else None
+                pending_stats = None
                 if isinstance(nxt, nn.Tanh):
                     x = self._conv(x, m, pad, 'tanh')
                     i += 2
                 else:
-                    x = self._conv(x, m, pad)
+                    if self._wants_stats(nxt):
+                        pending_stats = self._new_stats(x, self._conv_w(m)[0].shape[0])
+                    x = self._conv(x, m, pad, stats=pending_stats)
                     i += 1
             elif isinstance(m, nn.ConvTranspose2d):
-                x = self._deconv(x, m)
+                nxt = layers[i + 1] if i + 1 < len(layers) else None
+                pending_stats = self._new_stats(x, self._deconv_w(m)[0][(0, 0)].shape[0]) if self._wants_stats(nxt) else None
+                x = self._deconv(x, m, pending_stats)
                 i += 1
             elif isinstance(m, (nn.InstanceNorm2d, nn.BatchNorm2d)):
                 relu = i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU)
-                x = self._norm(x, m, relu)
+                x = self._norm(x, m, relu, stats=pending_stats)
+                pending_stats = None
                 i += 2 if relu else 1
             elif isinstance(m, ResnetBlock):
                 cb = list(m.conv_block)     # pad, conv, norm, relu, pad, conv, norm
-                y = self._conv(reflect_pad_nhwc(x, 1), cb[1], 0)
-                y = self._norm(y, cb[2], True)
-                y = self._conv(reflect_pad_nhwc(y, 1), cb[5], 0)
-                x = self._norm(y, cb[6], False, residual=x)
+                st1 = self._new_stats(x, x.shape[-1]) if self._wants_stats(cb[2]) else None
+                y = self._conv(reflect_pad_nhwc(x, 1), cb[1], 0, stats=st1)
+                y = self._norm(y, cb[2], True, stats=st1)
+                st2 = self._new_stats(x, x.shape[-1]) if self._wants_stats(cb[6]) else None
+                y = self._conv(reflect_pad_nhwc(y, 1), cb[5], 0, stats=st2)
+                x = self._norm(y, cb[6], False, residual=x, stats=st2)
                 i += 1
             else:
                 raise NotImplementedError('GlobalGenerator tcgen05 path: layer %r' % (m,))

@@ -206,6 +206,32 @@ def main():
     out['coverage'] = round(float((img > 0).float().mean()), 3)
     if args.check:
         from derender3d.models.renderer import Renderer, RenderType
+        # this repo on the same scenes: ONE batched call (ragged topologies padded with degenerate triangles)
+        nvm, nfm = max(v.shape[0] for v, _, _ in scenes), max(f.shape[0] for _, f, _ in scenes)
+        vb = torch.zeros(len(scenes), nvm, 3, device=dev)
+        fb = torch.zeros(len(scenes), nfm, 3, device=dev, dtype=torch.int32)
+        for i, (v, f, g) in enumerate(scenes):
+            vb[i, :v.shape[0]] = v
+            vb[i, v.shape[0]:] = v[0]
+            fb[i, :f.shape[0]] = f
+        gb = torch.stack([g for _, _, g in scenes]).to(dev)[:, None]
+        rr = Renderer(image_size=args.render_size, viewing_angle=angle)
+        vbg = vb.requires_grad_(True)
+
+        def ours():
+            o = rr(vbg, fb, render_type=RenderType.Silhouette)
+            o.backward(gb)
+            vbg.grad = None
+        for _ in range(3):
+            ours()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ours()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 5
+        out['this_repo_same_scenes'] = {'objects_per_s': round(len(scenes) / dt, 1), 'ms_per_object': round(dt / len(scenes) * 1e3, 3),
+                                        'how': 'one batched Renderer call, silhouette fwd+bwd, eager'}
         v, f, g = scenes[0]
         vg = v.clone().requires_grad_(True)
         mine = Renderer(image_size=args.render_size, viewing_angle=angle)(vg[None], f[None].int(), render_type=RenderType.Silhouette)

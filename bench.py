@@ -366,6 +366,8 @@ def run_ours(args):
                             'whole_step_frac': round(value / world * sum(algorithmic_bytes()) / 1e9 / peak, 4)}
         if world == 1 and not args.no_cpu:
             line['cpu_baseline'] = cpu_baseline()
+        if world == 1 and not args.no_extra:
+            line['reference_cuda'] = reference_cuda_arm()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -456,6 +458,24 @@ def other_configs(renderer, dev, world, rank, fast, args):
     torch.cuda.empty_cache()
     out['config3'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph)
     return out
+
+
+def reference_cuda_arm(timeout=240):
+    """The reference's own CUDA kernels re-hosted on this GPU (baseline/ref_cuda.py: rasterize.py's kernel strings through
+    NVRTC, driven per object like derender3d/models/__init__.py:161-224), in a subprocess under a timeout (its visibility
+    kernel spins on per-pixel locks).  Needs the git-ignored copy baseline/_ref staged by __graft_entry__.build()."""
+    script = os.path.join(ROOT, 'baseline', 'ref_cuda.py')
+    try:
+        r = subprocess.run([sys.executable, script, '--objects', '16', '--check'], capture_output=True, text=True,
+                           timeout=timeout)
+        last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith('{')]
+        if r.returncode == 0 and last:
+            return json.loads(last[-1])
+        return {'unavailable': 'baseline/ref_cuda.py exited %d: %s' % (r.returncode, (r.stderr or '')[-200:])}
+    except subprocess.TimeoutExpired:
+        return {'unavailable': 'baseline/ref_cuda.py did not finish in %d s' % timeout}
+    except Exception as e:      # noqa: BLE001
+        return {'unavailable': repr(e)[:200]}
 
 
 def segment_times(renderer, v_dev, f_dev, g_dev, fast, steps):

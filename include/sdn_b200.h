@@ -191,6 +191,10 @@ typedef struct sdn_conv2d {
                                beyond the tensor are zeros: one-sided padding, used by the transposed-convolution phases) */
     long long out_stride_n, out_stride_h, out_stride_w;   /* element strides of an output pixel; all 0 = dense NHWC.
                                Multiples of 8.  Lets four parity phases interleave into one [N, 2H, 2W, C] tensor. */
+    float* stats;           /* NULL, or fp32 [N, Cout, 2]: the call clears it and adds, per (image, channel), the sum and
+                               the sum of squares of the result before the activation -- the statistics the following
+                               InstanceNorm2d needs, taken from the accumulators instead of a second pass */
+    int stats_keep;         /* 1: add into `stats` without clearing it first (later phases of a transposed convolution) */
 } sdn_conv2d;
 
 int sdn_conv2d_forward(const sdn_conv2d* c, void* stream);
@@ -206,6 +210,11 @@ int sdn_im2col_nhwc(const void* input, void* output, int N, int H, int W, int Ci
  * stats: fp32 scratch [N, C, 2] (sum, sum of squares), cleared by the call.  C a multiple of 8; y may alias x. */
 int sdn_instance_norm_nhwc(const void* x, const void* residual, void* y, float* stats, int N, int HW, int C, float eps,
                            int act, void* stream);
+
+/* The normalisation alone, with statistics [N, C, 2] produced elsewhere (sdn_conv2d.stats; several convolutions may have
+ * added into one buffer, e.g. the four phases of a transposed convolution). */
+int sdn_instance_norm_apply_nhwc(const void* x, const void* residual, void* y, const float* stats, int N, int HW, int C,
+                                 float eps, int act, void* stream);
 
 /* nn.ReflectionPad2d(pad) on an NHWC bf16 tensor, channels zero-padded from C to Cp (a multiple of 8):
  * y [N, H + 2 pad, W + 2 pad, Cp] (textural/models/networks.py:218,238,250-269). */

@@ -33,3 +33,6 @@ for path in sys.argv[1:]:
         for w in WANT:
             if w in hdr:
                 print('  %-82s %s %s' % (w, r[hdr.index(w)], rows[1][hdr.index(w)]))
+        for i, h in enumerate(hdr):         # every tensor-pipe / TMA metric the capture holds
+            if ('tensor' in h or 'tma' in h.lower()) and h not in WANT and r[i] not in ('', 'n/a'):
+                print('  %-82s %s %s' % (h, r[i], rows[1][i]))

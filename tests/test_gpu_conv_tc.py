@@ -119,6 +119,29 @@ def test_few_output_channels_strided_output_and_extent_override(dev):
     assert float(big[:, 0::2].abs().sum()) == 0 and float(big[:, :, 0::2].abs().sum()) == 0
 
 
+def test_epilogue_statistics_feed_instance_norm(dev):
+    """conv2d_tc(stats=...) leaves per (image, channel) sum / sum of squares of its fp32 result; the normalising pass alone
+    then equals InstanceNorm2d of the convolution."""
+    import sdn_b200
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 64, 24, 40, generator=g)
+    w = torch.randn(128, 64, 3, 3, generator=g) / 24.0
+    b = torch.randn(128, generator=g)
+    y = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)
+    stats = torch.full((2, 128, 2), 7.0, device=dev)          # garbage: the call clears it
+    out = sdn_b200.conv2d_tc(x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous(), sdn_b200.pack_conv_weight(w.to(dev)), 1, 1,
+                             None, b.to(dev), stats=stats)
+    want = torch.stack([y.sum(dim=(2, 3)), (y * y).sum(dim=(2, 3))], dim=-1)
+    assert _rel(stats.cpu(), want) <= 1e-3
+    normed = sdn_b200.instance_norm_nhwc(out, None, True, stats=stats)
+    ref = F.instance_norm(y).clamp_min(0)
+    assert _rel(normed.permute(0, 3, 1, 2).float().cpu(), ref) <= 6e-3
+    # two launches adding into one buffer (the phases of a transposed convolution do this)
+    sdn_b200.conv2d_tc(x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous(), sdn_b200.pack_conv_weight(w.to(dev)), 1, 1,
+                       None, b.to(dev), stats=stats, stats_keep=True)
+    assert _rel(stats.cpu(), 2 * want) <= 1e-3
+
+
 def test_reflect_pad_kernel(dev):
     import sdn_b200
     x = torch.randn(2, 9, 11, 48, generator=torch.Generator().manual_seed(3)).to(dev).bfloat16()
