@@ -32,7 +32,8 @@ import torch  # noqa: E402
 
 H, W, SS = 375, 1242, 2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {'k_line_sweep': 195101696}      # profiles/r1_prof_line_v4.txt
+NCU_TRAFFIC = {'k_line_sweep': 195101696,      # profiles/r1_prof_line_v4.txt
+               'k_line_split': 186921984 + 14710016}      # profiles/r2_raster_kernels.md (dram read + write per launch)
 NF_EFF = 2 * 1984
 C_OUT = 5
 
