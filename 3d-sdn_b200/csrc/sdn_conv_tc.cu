@@ -291,20 +291,29 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
 __global__ void __launch_bounds__(256) k_im2col_nhwc(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                      int N, int H, int W, int Cin, int Ho, int Wo, int KH, int KW,
                                                      int stride, int pad, int Kpad) {
-    const long total = (long)N * Ho * Wo * Kpad;
+    // one thread per 8 consecutive output columns (one 16-byte store); Kpad is a multiple of 64
+    const int groups = Kpad >> 3, K = KH * KW * Cin;
+    const long total = (long)N * Ho * Wo * groups;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % Kpad);
-        long r = i / Kpad;
+        const int g = (int)(i % groups);
+        long r = i / groups;
         const int wo = (int)(r % Wo); r /= Wo;
         const int ho = (int)(r % Ho);
         const int n = (int)(r / Ho);
-        __nv_bfloat16 v = __float2bfloat16(0.0f);
-        if (k < KH * KW * Cin) {
-            const int c = k % Cin, tap = k / Cin, kw = tap % KW, kh = tap / KW;
-            const int hi = ho * stride + kh - pad, wi = wo * stride + kw - pad;
-            if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = in[(((size_t)n * H + hi) * W + wi) * Cin + c];
+        const __nv_bfloat16* img = in + (size_t)n * H * W * Cin;
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = g * 8 + j;
+            __nv_bfloat16 x = __float2bfloat16(0.0f);
+            if (k < K) {
+                const int c = k % Cin, tap = k / Cin, kw = tap % KW, kh = tap / KW;
+                const int hi = ho * stride + kh - pad, wi = wo * stride + kw - pad;
+                if (hi >= 0 && hi < H && wi >= 0 && wi < W) x = img[((size_t)hi * W + wi) * Cin + c];
+            }
+            v[j] = x;
         }
-        out[i] = v;
+        *reinterpret_cast<uint4*>(out + (size_t)i * 8) = *reinterpret_cast<const uint4*>(v);
     }
 }
 
@@ -533,7 +542,8 @@ extern "C" int sdn_im2col_nhwc(const void* input, void* output, int N, int H, in
         return SDN_E_ARG;
     const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
     if (Ho <= 0 || Wo <= 0) return SDN_E_ARG;
-    const long total = (long)N * Ho * Wo * Kpad;
+    if (Kpad & 7) return SDN_E_ARG;
+    const long total = (long)N * Ho * Wo * (Kpad / 8);
     const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
     sdn_internal::launch_begin("k_im2col_nhwc", (cudaStream_t)stream);
     k_im2col_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)input, (__nv_bfloat16*)output, N, H, W, Cin,

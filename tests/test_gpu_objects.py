@@ -185,7 +185,8 @@ def test_derenderer3d_fused_front_end_equals_class_grouped_path(dev, training):
 
 def test_whole_train_step_as_cuda_graph_matches_eager(dev):
     """GraphedTrainStep: encoder -> pose -> fused front end -> render -> losses -> backward -> Adam in ONE graph launch;
-    same trajectory as the eager step (float atomics reorder sums: 1e-3 on the loss after 6 steps)."""
+    same trajectory as the eager step: the warm-up steps the capture needs are undone (parameters, BatchNorm buffers
+    and Adam state are restored), so graph replay k equals eager step k (float atomics reorder sums: 1e-3 on the loss)."""
     import copy
     from derender3d import TargetType
     from derender3d.models import Derenderer3d, ShapenetObj
@@ -220,14 +221,19 @@ def test_whole_train_step_as_cuda_graph_matches_eager(dev):
              'ignores': torch.zeros(B, 1, 40, 40, device=dev)}
     opt_a = torch.optim.Adam(model_a.parameters(), lr=1e-4, weight_decay=1e-3, capturable=True)
     opt_b = torch.optim.Adam(model_b.parameters(), lr=1e-4, weight_decay=1e-3, capturable=True)
-    for _ in range(6):
-        loss_a, _, blob_a = train_step(model_a, opt_a, batch, TargetType.full)
+    w0 = model_b.derenderer._fc3.weight.detach().clone()
     gs = GraphedTrainStep(model_b, opt_b, batch, TargetType.full, warmup=3)
-    for _ in range(3):
+    assert torch.equal(w0, model_b.derenderer._fc3.weight.detach()), 'building the graph must not train the model'
+    assert int(model_b.derenderer.net.bn1.num_batches_tracked) == 0
+    for _ in range(4):
+        loss_a, _, blob_a = train_step(model_a, opt_a, batch, TargetType.full)
         loss_b = gs.step(batch)
     torch.cuda.synchronize()
     assert torch.isfinite(loss_b)
     assert abs(float(loss_a) - float(loss_b)) <= 1e-3 * abs(float(loss_a))
+    wa, wb = model_a.derenderer._fc3.weight.detach(), model_b.derenderer._fc3.weight.detach()
+    assert float((wa - wb).norm() / wa.norm()) <= 1e-3
+    assert int(model_b.derenderer.net.bn1.num_batches_tracked) == 4
     assert float((gs.blob['_masks'] > 0).float().mean()) > 0.01
     assert _rel(gs.blob['_masks'].float(), blob_a['_masks'].float()) <= 5e-2
     wa, wb = model_a.derenderer._fc3.weight, model_b.derenderer._fc3.weight
