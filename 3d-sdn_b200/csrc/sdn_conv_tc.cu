@@ -18,8 +18,10 @@
 //     with r mod 8) that the UMMA shared-memory descriptor names with layout_type = SWIZZLE_128B, SBO = 1024 B; a
 //     K = 16 slice is selected by advancing the descriptor's start address by 32 bytes.
 //   * Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; also owns the TMEM
-//     allocation), warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = tile rows).  A 4-stage ring of
+//     allocation), warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = tile rows).  A 6- or 8-stage ring of
 //     (A | B) tiles is handed back and forth with mbarriers: `full` (TMA complete_tx) and `empty` (tcgen05.commit).
+//   * PERSISTENT CTAs (one per SM) walk the (m tile, channel block) work list; the accumulator is double-buffered in
+//     tensor memory (2 x TN columns) so the epilogue of one item overlaps the main loop of the next.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -36,7 +38,9 @@ namespace {
 
 constexpr int TM = 128;                 // output pixels per tile (= TMEM lanes)
 constexpr int TK = 64;                  // K block: 64 bf16 = 128 bytes = one swizzle row
-constexpr int STAGES = 4;
+// operand ring depth: 128-wide tiles run one persistent CTA per SM with ~190 KB of operands in flight; narrower tiles
+// (N = 64 halves the work per tcgen05.mma, so one issuing thread cannot keep the tensor pipe busy) run two CTAs per SM
+template <int TN> struct Ring { static constexpr int STAGES = TN >= 128 ? 6 : 4; };      // TN <= 64: two CTAs per SM (two MMA issuers)
 constexpr int A_BYTES = TM * TK * 2;    // 16 KB
 constexpr int NTHREADS = 192;
 
@@ -105,30 +109,31 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
     extern __shared__ unsigned char smem_raw[];
     // the swizzle pattern is a function of the address bits [4,10): tiles must start on 1024-byte boundaries
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int STAGES = Ring<TN>::STAGES;
     constexpr int B_BYTES = TN * TK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full;
+    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full[2], s_tmem_empty[2];
     __shared__ uint32_t s_tmem;
+    __shared__ float s_stat[2 * 128];                   // per-CTA (sum, sum of squares) of the current (image, channel block)
+    constexpr uint32_t TNA = TN < 32 ? 32 : TN;         // accumulator columns per buffer (TMEM allocations are >= 32)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // tile coordinates: blockIdx.x -> (tile_n, tile_h, tile_w); blockIdx.y -> output-channel block
-    int t = blockIdx.x;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h; t /= p.tiles_h;
-    const int tn = t;
-    const int wo0 = tw * p.bw, ho0 = th * p.bh, n0 = tn * p.bn;
-    const int co0 = blockIdx.y * TN;
+    // PERSISTENT CTAs: work item w -> (m tile, output-channel block), m fastest, so the CTAs that run together share one
+    // weight block and neighbouring input patches in L2.  The accumulator is double-buffered in tensor memory: the
+    // epilogue of item i drains buffer i & 1 while the MMA warp already fills the other one for item i + 1.
+    const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int total_work = tiles_m * (p.Cout / TN);
     const int cblocks = p.Cin / TK;
     const int kblocks = p.KH * p.KW * cblocks;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        mbar_init(&s_tmem_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&s_tmem_full[s], 1); mbar_init(&s_tmem_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {        // the MMA warp owns the accumulator columns in tensor memory
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"((uint32_t)(TN < 32 ? 32 : TN)));
+                     "r"(2u * TNA));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -141,42 +146,59 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
-            for (int kb = 0; kb < kblocks; kb++) {
-                const int st = kb % STAGES;
-                if (kb >= STAGES) mbar_wait(&s_empty[st], (uint32_t)(((kb / STAGES) - 1) & 1));
-                const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                const int kh = tap / p.KW, kw = tap - kh * p.KW;
-                unsigned char* sA = smem + st * STAGE_BYTES;
-                unsigned char* sB = sA + A_BYTES;
-                mbar_expect_tx(&s_full[st], (uint32_t)STAGE_BYTES);
-                tma_load_4d(sA, &tmA, &s_full[st], cb * TK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, n0);
-                tma_load_2d(sB, &tmB, &s_full[st], kb * TK, co0);
+            int kbg = 0;                                     // K blocks issued by this CTA so far (ring position)
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                int t = w % tiles_m;
+                const int co0 = (w / tiles_m) * TN;
+                const int tw = t % p.tiles_w; t /= p.tiles_w;
+                const int th = t % p.tiles_h; t /= p.tiles_h;
+                const int wo0 = tw * p.bw, ho0 = th * p.bh, n0 = t * p.bn;
+                for (int kb = 0; kb < kblocks; kb++, kbg++) {
+                    const int st = kbg % STAGES;
+                    if (kbg >= STAGES) mbar_wait(&s_empty[st], (uint32_t)(((kbg / STAGES) - 1) & 1));
+                    const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    unsigned char* sA = smem + st * STAGE_BYTES;
+                    unsigned char* sB = sA + A_BYTES;
+                    mbar_expect_tx(&s_full[st], (uint32_t)STAGE_BYTES);
+                    tma_load_4d(sA, &tmA, &s_full[st], cb * TK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, n0);
+                    tma_load_2d(sB, &tmB, &s_full[st], kb * TK, co0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            for (int kb = 0; kb < kblocks; kb++) {
-                const int st = kb % STAGES;
-                mbar_wait(&s_full[st], (uint32_t)((kb / STAGES) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_BYTES;
-#pragma unroll
-                for (int j = 0; j < TK / 16; j++) {     // K = 16 per UMMA = 32 bytes along the swizzled row
-                    const uint64_t da = make_desc_sw128(a0 + j * 32), db = make_desc_sw128(b0 + j * 32);
-                    const uint32_t accumulate = (kb > 0 || j > 0) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\t"
-                        "setp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem), "l"(da), "l"(db), "r"(idesc<TN>()), "r"(accumulate) : "memory");
+            int kbg = 0, it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+                const int ab = it & 1;
+                if (it >= 2) {      // the epilogue must have drained this accumulator buffer (two items ago)
+                    mbar_wait(&s_tmem_empty[ab], (uint32_t)(((it >> 1) - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                // frees the stage when every UMMA issued so far has completed (implies fence::before_thread_sync)
+                const uint32_t acc = tmem + (uint32_t)ab * TNA;
+                for (int kb = 0; kb < kblocks; kb++, kbg++) {
+                    const int st = kbg % STAGES;
+                    mbar_wait(&s_full[st], (uint32_t)((kbg / STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < TK / 16; j++) {     // K = 16 per UMMA = 32 bytes along the swizzled row
+                        const uint64_t da = make_desc_sw128(a0 + j * 32), db = make_desc_sw128(b0 + j * 32);
+                        const uint32_t accumulate = (kb > 0 || j > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(acc), "l"(da), "l"(db), "r"(idesc<TN>()), "r"(accumulate) : "memory");
+                    }
+                    // frees the stage when every UMMA issued so far has completed (implies fence::before_thread_sync)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 ::"r"(smem_u32(&s_empty[st])) : "memory");
+                }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             ::"r"(smem_u32(&s_empty[st])) : "memory");
+                             ::"r"(smem_u32(&s_tmem_full[ab])) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                         ::"r"(smem_u32(&s_tmem_full)) : "memory");
         }
     } else {
         // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31; lane = tile row = one output pixel =====
@@ -185,18 +207,44 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         const int per_img = p.bh * p.bw;
         const int nl = row / per_img, rem = row - nl * per_img;
         const int hl = rem / p.bw, wl = rem - hl * p.bw;
+        // statistics scratch: 32 x 33 floats per epilogue warp, behind the operand ring (which is busy with the next item)
+        float* sT = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + q * (32 * 17);
+        // statistics are accumulated per CTA across its work items and leave as ONE atomic per channel when the
+        // (image, channel block) changes or the CTA is done (tiles that span several images use direct atomics)
+        const bool cta_stats = p.stats && p.bn == 1;
+        const int et = tid - 64;                            // 0..127 within the four epilogue warps
+        int key_n = -1, key_c = -1;
+        if (cta_stats) { s_stat[et] = 0.0f; s_stat[et + 128] = 0.0f; asm volatile("bar.sync 1, 128;" ::: "memory"); }
+        int it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+        const int ab = it & 1;
+        int t = w % tiles_m;
+        const int co0 = (w / tiles_m) * TN;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int wo0 = tw * p.bw, ho0 = th * p.bh, n0 = t * p.bn;
         const int n = n0 + nl, ho = ho0 + hl, wo = wo0 + wl;
         const bool valid = n < p.N && ho < p.Ho && wo < p.Wo;
         const size_t pix = ((size_t)n * p.Ho + ho) * p.Wo + wo;                 // residual: dense [N, Ho, Wo, Cout]
         const size_t opix = (size_t)((long)n * p.osn + (long)ho * p.osh + (long)wo * p.osw);
-        mbar_wait(&s_tmem_full, 0);
+        if (cta_stats && (n0 != key_n || co0 != key_c)) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // every warp has finished adding the previous item
+            if (key_n >= 0 && et < TN && key_c + et < p.Cout) {
+                float* o = p.stats + ((size_t)key_n * p.Cout + key_c + et) * 2;
+                atomicAdd(o, s_stat[et]); atomicAdd(o + 1, s_stat[et + 128]);
+            }
+            s_stat[et] = 0.0f; s_stat[et + 128] = 0.0f;
+            key_n = n0; key_c = co0;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        mbar_wait(&s_tmem_full[ab], (uint32_t)((it >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* sT = reinterpret_cast<float*>(smem) + q * (32 * 33);           // 32 x (CW + 1) floats per epilogue warp
+        const uint32_t acc = tmem + (uint32_t)ab * TNA;
         constexpr int CW = TN >= 32 ? 32 : 16;          // accumulator columns per tcgen05.ld
 #pragma unroll 1
         for (int c0 = 0; c0 < TN; c0 += CW) {
             uint32_t v[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
             if (CW == 32) {
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -217,14 +265,58 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int c = co0 + c0;
-            if (valid && c < p.Cout) {
-                float y[CW];
+            // scale * acc + shift for this lane's pixel, CW channels (vector loads of the per-channel constants; the
+            // null checks are hoisted: per-element `p.scale ? .. : ..` costs a branch per channel)
+            float y[CW];
+            if (c < p.Cout) {
+                if (p.scale) {
+                    const float4* s4 = reinterpret_cast<const float4*>(p.scale + c);
 #pragma unroll
-                for (int j = 0; j < CW; j++) {
-                    const float sc = p.scale ? __ldg(p.scale + c + j) : 1.0f;
-                    const float sh = p.shift ? __ldg(p.shift + c + j) : 0.0f;
-                    y[j] = __fmaf_rn(__uint_as_float(v[j]), sc, sh);
+                    for (int g = 0; g < CW / 4; g++) {
+                        const float4 t4 = __ldg(s4 + g);
+                        y[4 * g] = __uint_as_float(v[4 * g]) * t4.x; y[4 * g + 1] = __uint_as_float(v[4 * g + 1]) * t4.y;
+                        y[4 * g + 2] = __uint_as_float(v[4 * g + 2]) * t4.z; y[4 * g + 3] = __uint_as_float(v[4 * g + 3]) * t4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CW; j++) y[j] = __uint_as_float(v[j]);
                 }
+                if (p.shift) {
+                    const float4* s4 = reinterpret_cast<const float4*>(p.shift + c);
+#pragma unroll
+                    for (int g = 0; g < CW / 4; g++) {
+                        const float4 t4 = __ldg(s4 + g);
+                        y[4 * g] += t4.x; y[4 * g + 1] += t4.y; y[4 * g + 2] += t4.z; y[4 * g + 3] += t4.w;
+                    }
+                }
+            }
+            if (p.stats && c < p.Cout) {
+                // column sums of this warp's 32 rows, 16 channels at a time, through a 32 x 17 shared-memory transpose
+                // (lane j < 16 then owns channel c + h + j); all 32 rows of a warp lie in ONE image (128 / bn >= 32 rows);
+                // rows outside the image add nothing
+#pragma unroll
+                for (int h = 0; h < CW; h += 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) sT[lane * 17 + j] = valid ? y[h + j] : 0.0f;
+                    __syncwarp();
+                    if (lane < 16) {
+                        float sm = 0.0f, sq = 0.0f;
+#pragma unroll
+                        for (int r = 0; r < 32; r++) { const float v1 = sT[r * 17 + lane]; sm += v1; sq = __fmaf_rn(v1, v1, sq); }
+                        if (cta_stats) {
+                            atomicAdd(&s_stat[c0 + h + lane], sm); atomicAdd(&s_stat[c0 + h + lane + 128], sq);
+                        } else {
+                            const int nimg = n0 + (q * 32) / per_img;
+                            if (nimg < p.N) {
+                                float* o = p.stats + ((size_t)nimg * p.Cout + c + h + lane) * 2;
+                                atomicAdd(o, sm); atomicAdd(o + 1, sq);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (valid && c < p.Cout) {
                 if (p.residual) {
                     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + c);
 #pragma unroll
@@ -238,10 +330,6 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                             y[g * 8 + h * 2 + 1] += __high2float(b2);
                         }
                     }
-                }
-                if (p.stats) {
-#pragma unroll
-                    for (int j = 0; j < CW; j++) sT[lane * (CW + 1) + j] = y[j];
                 }
                 uint4* op = reinterpret_cast<uint4*>(p.out + opix + c);
 #pragma unroll
@@ -257,32 +345,25 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                     }
                     op[g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 }
-            } else if (p.stats) {
-#pragma unroll
-                for (int j = 0; j < CW; j++) sT[lane * (CW + 1) + j] = 0.0f;       // rows outside the image add nothing
             }
-            if (p.stats && c < p.Cout) {
-                // column sums of this warp's 32 rows x CW channels through shared memory (the operand ring is idle now):
-                // lane j owns channel c + j; all 32 rows of a warp lie in ONE image (128 / bn >= 32 rows per image)
-                __syncwarp();
-                if (lane < CW) {
-                    float sm = 0.0f, sq = 0.0f;
-#pragma unroll 8
-                    for (int r = 0; r < 32; r++) { const float v1 = sT[r * (CW + 1) + lane]; sm += v1; sq = __fmaf_rn(v1, v1, sq); }
-                    const int nimg = n0 + (q * 32) / per_img;
-                    if (nimg < p.N) {
-                        float* o = p.stats + ((size_t)nimg * p.Cout + c + lane) * 2;
-                        atomicAdd(o, sm); atomicAdd(o + 1, sq);
-                    }
-                }
-                __syncwarp();
+        }
+        // this accumulator buffer is drained: hand it back to the MMA warp (one arrival per epilogue warp)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tmem_empty[ab])) : "memory");
+        }
+        if (cta_stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (key_n >= 0 && et < TN && key_c + et < p.Cout) {
+                float* o = p.stats + ((size_t)key_n * p.Cout + key_c + et) * 2;
+                atomicAdd(o, s_stat[et]); atomicAdd(o + 1, s_stat[et + 128]);
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(TN < 32 ? 32 : TN)));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * TNA));
 }
 
 // im2col for convolutions whose input has too few channels for a 64-wide K block (the 7x7 stem of ResNet-18, Cin = 3):
@@ -457,7 +538,8 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         return SDN_E_ARG;
     if (c->Cin % TK != 0 || (c->Cout % 64 != 0 && c->Cout != 16)) return SDN_E_ARG;    // pad channels on the caller's side
     if ((reinterpret_cast<uintptr_t>(c->input) & 15) || (reinterpret_cast<uintptr_t>(c->weight) & 15) ||
-        (reinterpret_cast<uintptr_t>(c->output) & 15) || (reinterpret_cast<uintptr_t>(c->residual) & 15))
+        (reinterpret_cast<uintptr_t>(c->output) & 15) || (reinterpret_cast<uintptr_t>(c->residual) & 15) ||
+        (reinterpret_cast<uintptr_t>(c->scale) & 15) || (reinterpret_cast<uintptr_t>(c->shift) & 15))
         return SDN_E_ARG;
     // output extent: the convolution's own, or the caller's (reads beyond the input are zeros: asymmetric padding)
     const int Ho = c->out_h > 0 ? c->out_h : (c->H + 2 * c->pad - c->KH) / c->stride + 1;
@@ -480,6 +562,7 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
     p.residual = (const __nv_bfloat16*)c->residual; p.relu = c->relu;
     p.stats = c->stats;
     if (p.stats) {
+        if (c->residual) return SDN_E_ARG;                          // statistics are of scale * conv + shift
         if ((p.bh * p.bw) % 32) return SDN_E_ARG;                   // a warp's 32 rows must lie in one image
         if (!c->stats_keep) {
             const cudaError_t em = cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * (size_t)c->N * c->Cout, (cudaStream_t)stream);
@@ -513,8 +596,13 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         if (r != CUDA_SUCCESS) return SDN_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_n), (unsigned)(c->Cout / TN));
-    const size_t smem = (size_t)STAGES * (A_BYTES + TN * TK * 2) + 1024;
+    const long total_work = (long)p.tiles_w * p.tiles_h * p.tiles_n * (c->Cout / TN);
+    const int stages = TN >= 128 ? Ring<128>::STAGES : Ring<64>::STAGES;
+    const size_t smem = (size_t)stages * (A_BYTES + TN * TK * 2) + 4 * 32 * 17 * sizeof(float) + 1024;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;      // CTAs that fit one SM's shared memory
+    const dim3 grid((unsigned)(total_work < (long)sms * per_sm ? total_work : (long)sms * per_sm), 1);
     cudaError_t e;
     if (TN == 128) {
         e = cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -2366,7 +2366,7 @@ __device__ __forceinline__ void line_rgb_role(const BwdParams& P, const Workspac
             // queries of the chunk that reach into this pass: lane k looks at query k, the warp walks the set bits.
             // A range that ends at a border of the LINE is treated as unbounded on that side: samples beyond the line
             // carry g = D = 0 and contribute exactly 0, so the last pass needs no masking.
-            static_assert(LQ == 32, "one ballot bit per staged query");
+            static_assert(LQ <= 32, "one ballot bit per staged query");
             unsigned active;
             {
                 int qlo = 0x7fffffff, qhi = -1;
@@ -2466,8 +2466,8 @@ __device__ __forceinline__ void line_rgb_role(const BwdParams& P, const Workspac
     }
 }
 
-template <int OP, int LQ>
-__global__ void __launch_bounds__(LW * 32, 2) k_line_rgb(BwdParams P, Workspace ws, int accumulate) {
+template <int OP, int LQ, int MINB>
+__global__ void __launch_bounds__(LW * 32, MINB) k_line_rgb(BwdParams P, Workspace ws, int accumulate) {
     extern __shared__ __align__(16) unsigned char s_rgb_dyn[];
     line_rgb_role<OP, LQ>(P, ws, (int)blockIdx.x, accumulate, ws.qres, s_rgb_dyn);
 }
@@ -2868,11 +2868,19 @@ int backward_impl(const sdn_raster* r, const sdn_raster_grad* g, int split, doub
                     if (rgb_pairs) {
                         timing_begin("k_line_rgb", st);
                         if (op == 4) {
-                            allow_smem_once(k_line_rgb<4, 32>, lsmem);
-                            k_line_rgb<4, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                            allow_smem_once(k_line_rgb<4, 32, 2>, lsmem);
+                            k_line_rgb<4, 32, 2><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                        } else if (op == 3) {       // three CTAs per SM: 24 staged queries, <= 85 registers
+                            const size_t lsmem3 = sizeof(float2) * LW * 24 * 33;
+                            allow_smem_once(k_line_rgb<4, 24, 3>, lsmem3);
+                            k_line_rgb<4, 24, 3><<<lgrid, LW * 32, lsmem3, st>>>(P, ws, alpha_moments ? 1 : 0);
+                        } else if (op == 5) {
+                            const size_t lsmem3 = sizeof(float2) * LW * 24 * 33;
+                            allow_smem_once(k_line_rgb<8, 24, 3>, lsmem3);
+                            k_line_rgb<8, 24, 3><<<lgrid, LW * 32, lsmem3, st>>>(P, ws, alpha_moments ? 1 : 0);
                         } else {
-                            allow_smem_once(k_line_rgb<8, 32>, lsmem);
-                            k_line_rgb<8, 32><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
+                            allow_smem_once(k_line_rgb<8, 32, 2>, lsmem);
+                            k_line_rgb<8, 32, 2><<<lgrid, LW * 32, lsmem, st>>>(P, ws, alpha_moments ? 1 : 0);
                         }
                     }
                 }

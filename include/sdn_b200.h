@@ -192,7 +192,7 @@ typedef struct sdn_conv2d {
     long long out_stride_n, out_stride_h, out_stride_w;   /* element strides of an output pixel; all 0 = dense NHWC.
                                Multiples of 8.  Lets four parity phases interleave into one [N, 2H, 2W, C] tensor. */
     float* stats;           /* NULL, or fp32 [N, Cout, 2]: the call clears it and adds, per (image, channel), the sum and
-                               the sum of squares of the result before the activation -- the statistics the following
+                               the sum of squares of scale * conv + shift (no residual allowed) -- the statistics the following
                                InstanceNorm2d needs, taken from the accumulators instead of a second pass */
     int stats_keep;         /* 1: add into `stats` without clearing it first (later phases of a transposed convolution) */
 } sdn_conv2d;
