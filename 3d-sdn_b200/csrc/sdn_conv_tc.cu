@@ -470,6 +470,50 @@ __global__ void __launch_bounds__(256) k_inorm_apply(const __nv_bfloat16* __rest
     }
 }
 
+// apply + nn.ReflectionPad2d(pad) in one pass: y [N, H + 2 pad, W + 2 pad, C] = reflect_pad(act(norm(x) (+ residual))).
+// The next 3x3 / 7x7 convolution of the generator reads exactly this tensor, so the normalised activation is never
+// written unpadded (one read + one write instead of two of each).
+__global__ void __launch_bounds__(256) k_inorm_apply_pad(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                                                         const __nv_bfloat16* __restrict__ residual,
+                                                         __nv_bfloat16* __restrict__ y, int H, int W, int C, float eps,
+                                                         int act, int pad) {
+    const int n = blockIdx.y;
+    const int cg = C >> 3, Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const unsigned total = (unsigned)Hp * (unsigned)Wp * (unsigned)cg;
+    const float inv = 1.0f / (float)(H * W);
+    const size_t img = (size_t)n * H * W * C, imgp = (size_t)n * Hp * Wp * C;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned g = i % (unsigned)cg;
+        const unsigned pp = i / (unsigned)cg;
+        int h = (int)(pp / (unsigned)Wp) - pad, w = (int)(pp % (unsigned)Wp) - pad;
+        h = h < 0 ? -h : (h >= H ? 2 * (H - 1) - h : h);
+        w = w < 0 ? -w : (w >= W ? 2 * (W - 1) - w : w);
+        const float* st = stats + ((size_t)n * C + g * 8) * 2;
+        const size_t e = img + ((size_t)h * W + w) * C + g * 8;
+        const uint4 xv = *reinterpret_cast<const uint4*>(x + e);
+        uint4 rv = make_uint4(0, 0, 0, 0);
+        if (residual) rv = *reinterpret_cast<const uint4*>(residual + e);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 s4 = *reinterpret_cast<const float4*>(st + k * 4);
+            const float m0 = s4.x * inv, m1 = s4.z * inv;
+            const float r0 = rsqrtf(fmaxf(s4.y * inv - m0 * m0, 0.0f) + eps), r1 = rsqrtf(fmaxf(s4.w * inv - m1 * m1, 0.0f) + eps);
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&xw[k]);
+            float a = (__low2float(v) - m0) * r0, b = (__high2float(v) - m1) * r1;
+            if (residual) {
+                const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(&rw[k]);
+                a += __low2float(rr); b += __high2float(rr);
+            }
+            if (act == 1) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+            const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+            ow[k] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+        *reinterpret_cast<uint4*>(y + imgp + (size_t)i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
 // ---- C. reflection padding of an NHWC bf16 tensor (nn.ReflectionPad2d), with optional zero channels up to Cp ----
 __global__ void __launch_bounds__(256) k_reflect_pad_nhwc(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                           int N, int H, int W, int C, int pad, int Cp) {
@@ -676,6 +720,17 @@ extern "C" int sdn_instance_norm_apply_nhwc(const void* x, const void* residual,
     sdn_internal::launch_begin("k_inorm_apply", (cudaStream_t)stream);
     k_inorm_apply<<<dim3(blocks, (unsigned)N), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, HW, C, eps, act);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_instance_norm_apply_pad_nhwc(const void* x, const void* residual, void* y, const float* stats, int N, int H,
+                                                int W, int C, float eps, int act, int pad, void* stream) {
+    if (!x || !y || !stats || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || pad < 0 || pad >= H || pad >= W) return SDN_E_ARG;
+    const long total = (long)(H + 2 * pad) * (W + 2 * pad) * (C / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148L * 16 ? 148L * 16 : (total + 255) / 256);
+    sdn_internal::launch_begin("k_inorm_apply_pad", (cudaStream_t)stream);
+    k_inorm_apply_pad<<<dim3(blocks, (unsigned)N), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, stats, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, H, W, C, eps, act, pad);
     return sdn_internal::launch_end();
 }
 

@@ -94,6 +94,7 @@ def lib():
         L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_reflect_pad_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_instance_norm_apply_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
+        L.sdn_instance_norm_apply_pad_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ctypes.c_float, ci, ci, vp]
         L.sdn_objects_forward.argtypes = [ctypes.POINTER(_Objects), vp]
         L.sdn_objects_backward.argtypes = [ctypes.POINTER(_Objects), vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.sdn_rasterize_backward.argtypes = [ctypes.POINTER(_Raster), ctypes.POINTER(_RasterGrad), vp]
@@ -448,6 +449,21 @@ def reflect_pad_nhwc(x, pad, cpad=None):
     y = torch.empty(N, H + 2 * pad, W + 2 * pad, cp, device=x.device, dtype=torch.bfloat16)
     with torch.cuda.device(x.device):
         _check(lib().sdn_reflect_pad_nhwc(_ptr(x), _ptr(y), N, H, W, C, int(pad), cp, _stream()))
+    return y
+
+
+def instance_norm_pad_nhwc(x, stats, pad, residual=None, relu=False, eps=1e-5):
+    """reflect_pad(relu?(instance_norm(x) (+ residual)), pad) in ONE pass, from statistics a convolution produced
+    (sdn_instance_norm_apply_pad_nhwc): [N, H, W, C] -> [N, H + 2 pad, W + 2 pad, C] bf16."""
+    _need_cuda(x, residual, stats)
+    x = x.contiguous()
+    N, H, W, C = x.shape
+    y = torch.empty(N, H + 2 * pad, W + 2 * pad, C, device=x.device, dtype=torch.bfloat16)
+    if residual is not None:
+        residual = residual.contiguous()
+    with torch.cuda.device(x.device):
+        _check(lib().sdn_instance_norm_apply_pad_nhwc(_ptr(x), _ptr(residual), _ptr(y), _ptr(stats), N, H, W, C, float(eps),
+                                                      1 if relu else 0, int(pad), _stream()))
     return y
 
 

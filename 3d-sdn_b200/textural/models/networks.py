@@ -162,14 +162,18 @@ class GlobalGenerator(nn.Module):
         """input [N, input_nc, H, W] float (CUDA) -> [N, output_nc, H, W] float32."""
         layers = list(self.model)
         x = input.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
-        i, pending_pad, pending_stats = 0, 0, None
+        i, pending_pad, pending_stats, prepadded = 0, 0, None, False
         while i < len(layers):
             m = layers[i]
             if isinstance(m, nn.ReflectionPad2d):
                 pending_pad = int(m.padding[0])
                 i += 1
             elif isinstance(m, nn.Conv2d):
-                if pending_pad:
+                if prepadded:                   # the producer already wrote the reflection-padded tensor
+                    pad, prepadded = 0, False
+                    if x.shape[-1] % 64:
+                        x = F.pad(x, (0, (-x.shape[-1]) % 64))
+                elif pending_pad:
                     x = reflect_pad_nhwc(x, pending_pad, (x.shape[-1] + 63) // 64 * 64)
                     pad, pending_pad = 0, 0
                 else:
@@ -193,6 +197,14 @@ class GlobalGenerator(nn.Module):
                 i += 1
             elif isinstance(m, (nn.InstanceNorm2d, nn.BatchNorm2d)):
                 relu = i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU)
+                after = layers[i + (2 if relu else 1)] if i + (2 if relu else 1) < len(layers) else None
+                if pending_stats is not None and isinstance(after, nn.ReflectionPad2d):
+                    # norm (+ReLU) and the reflection padding of the next convolution in one pass
+                    import sdn_b200
+                    x = sdn_b200.instance_norm_pad_nhwc(x, pending_stats, int(after.padding[0]), None, relu, m.eps)
+                    pending_stats, prepadded = None, True
+                    i += 3 if relu else 2
+                    continue
                 x = self._norm(x, m, relu, stats=pending_stats)
                 pending_stats = None
                 i += 2 if relu else 1
@@ -200,9 +212,13 @@ class GlobalGenerator(nn.Module):
                 cb = list(m.conv_block)     # pad, conv, norm, relu, pad, conv, norm
                 st1 = self._new_stats(x, x.shape[-1]) if self._wants_stats(cb[2]) else None
                 y = self._conv(reflect_pad_nhwc(x, 1), cb[1], 0, stats=st1)
-                y = self._norm(y, cb[2], True, stats=st1)
+                if st1 is not None:             # norm + ReLU + the second convolution's reflection padding in one pass
+                    import sdn_b200
+                    y = sdn_b200.instance_norm_pad_nhwc(y, st1, 1, None, True, cb[2].eps)
+                else:
+                    y = reflect_pad_nhwc(self._norm(y, cb[2], True), 1)
                 st2 = self._new_stats(x, x.shape[-1]) if self._wants_stats(cb[6]) else None
-                y = self._conv(reflect_pad_nhwc(y, 1), cb[5], 0, stats=st2)
+                y = self._conv(y, cb[5], 0, stats=st2)
                 x = self._norm(y, cb[6], False, residual=x, stats=st2)
                 i += 1
             else:

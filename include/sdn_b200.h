@@ -216,6 +216,11 @@ int sdn_instance_norm_nhwc(const void* x, const void* residual, void* y, float* 
 int sdn_instance_norm_apply_nhwc(const void* x, const void* residual, void* y, const float* stats, int N, int HW, int C,
                                  float eps, int act, void* stream);
 
+/* Normalisation + nn.ReflectionPad2d(pad) in one pass: y [N, H + 2 pad, W + 2 pad, C] = reflect_pad(act(norm(x) (+ residual)))
+ * -- what the generator's next 3x3 / 7x7 convolution reads (networks.py:250-269). */
+int sdn_instance_norm_apply_pad_nhwc(const void* x, const void* residual, void* y, const float* stats, int N, int H, int W,
+                                     int C, float eps, int act, int pad, void* stream);
+
 /* nn.ReflectionPad2d(pad) on an NHWC bf16 tensor, channels zero-padded from C to Cp (a multiple of 8):
  * y [N, H + 2 pad, W + 2 pad, Cp] (textural/models/networks.py:218,238,250-269). */
 int sdn_reflect_pad_nhwc(const void* x, void* y, int N, int H, int W, int C, int pad, int Cp, void* stream);
