@@ -141,7 +141,7 @@ Workspace make_ws(void* base, int B, int F, int Hs, int Ws) {
     w.active_ids = (int*)(p + off); off = align_up(off + (size_t)B * w.Fp * 4, 256);
     w.active_bbox = (short*)(p + off); off = align_up(off + (size_t)B * w.Fp * 8, 256);
     w.tile_prefix = (int*)(p + off); off = align_up(off + (size_t)(B + 1) * 4, 256);
-    const size_t bc = BF * 3 + 262144;
+    const size_t bc = BF * 3 + 262144 + (size_t)w.num_tiles * 3;       // + padding of every tile's slice to 4 ids
     w.bin_cap = (int)(bc > 64000000 ? 64000000 : bc);
     w.bin_ids = (int*)(p + off); off = align_up(off + (size_t)w.bin_cap * 4, 256);
     w.bin_sums = (int*)(p + off); off = align_up(off + ((size_t)w.num_tiles / 2048 + 2) * 4, 256);
@@ -545,6 +545,14 @@ __global__ void __launch_bounds__(256) k_bin_faces(int B, int tiles_x, int tiles
         }
 }
 
+// Rounds every tile's face count up to a multiple of 4 before the scan: each tile's slice of bin_ids then starts on a
+// 16-byte boundary and can be staged into shared memory with ONE 1-D TMA bulk copy (k_raster_tiles).  The real counts
+// are what k_bin_faces<true> leaves in tile_cursor.
+__global__ void __launch_bounds__(256) k_pad_tile_counts(Workspace ws) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ws.num_tiles) ws.tile_off[t] = (ws.tile_off[t] + 3) & ~3;
+}
+
 // tiles that intersect each image's face bounding box: prefix[b] .. prefix[b+1]
 __device__ __forceinline__ void image_tile_range(const Workspace& ws, int b, int& tx0, int& ty0, int& nx, int& ny) {
     nx = 0; ny = 0; tx0 = 0; ty0 = 0;
@@ -600,7 +608,7 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
     __shared__ __align__(128) short4 s_bb[2][BCH];
     __shared__ __align__(128) int s_ids[2][BCH];
     __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ int s_queue[QCAP];
+    __shared__ __align__(16) int s_queue[QCAP];
     __shared__ int s_big[QCAP];
     __shared__ float s_xp[TW], s_yp[TH];
     __shared__ int s_qn, s_tile, s_nbig;
@@ -689,17 +697,32 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
 
         const bool binned = ws.tile_off[ws.num_tiles] <= ws.bin_cap;
         if (binned) {
-            // the faces of this tile were binned by k_bin_faces: every entry is a hit
+            // the faces of this tile were binned by k_bin_faces: every entry is a hit.  The tile's slice of bin_ids
+            // (16-byte aligned, see k_pad_tile_counts) is staged into shared memory in chunks of QCAP ids, each ONE
+            // 1-D TMA bulk copy (cp.async.bulk + mbarrier); the first one flies while the z-buffer is initialised.
             const int tg = (b * P.tiles_y + ty) * P.tiles_x + tx;
-            const int off = ws.tile_off[tg], cnt = ws.tile_off[tg + 1] - off;
+            const int off = ws.tile_off[tg], cnt = ws.tile_cursor[tg];
+            if (tid == 0 && cnt > 0) {
+                const uint32_t bytes = (uint32_t)(((min(QCAP, cnt) + 3) / 4) * 16);
+                mbar_expect_tx(&s_bar[0], bytes);
+                bulk_g2s(&s_queue[0], ws.bin_ids + off, bytes, &s_bar[0]);
+            }
             for (int k = tid; k < TH * TW; k += NT) s_key[k] = ~0ull;
             if (tid < TW) s_xp[tid] = xp_of(sx0 + tid, P.Ws);
             if (tid < TH) s_yp[tid] = xp_of(sy0 + tid, P.Hs);
             for (int base = 0; base < cnt; base += QCAP) {
                 const int n = min(QCAP, cnt - base);
-                __syncthreads();
-                for (int k = tid; k < n; k += NT) s_queue[k] = ws.bin_ids[off + base + k];
-                __syncthreads();
+                if (base > 0) {
+                    __syncthreads();                    // the previous chunk has been consumed
+                    if (tid == 0) {
+                        const uint32_t bytes = (uint32_t)(((n + 3) / 4) * 16);
+                        mbar_expect_tx(&s_bar[0], bytes);
+                        bulk_g2s(&s_queue[0], ws.bin_ids + off + base, bytes, &s_bar[0]);
+                    }
+                }
+                mbar_wait(&s_bar[0], phase[0]);
+                phase[0] ^= 1u;
+                __syncthreads();                        // + the shared-memory initialisation above
                 rasterise_queue(n);
             }
         } else {
@@ -3058,6 +3081,9 @@ int sdn_rasterize_forward(const sdn_raster* r, void* stream_) {
         const int tn = ws.num_tiles + 1, tblocks = (tn + SCAN_ELEMS - 1) / SCAN_ELEMS;
         timing_begin("k_bin_faces", st);
         k_bin_faces<false><<<bgrid, 256, 0, st>>>(r->B, P.tiles_x, P.tiles_y, ws);
+        if ((rc = check_launch())) return rc;
+        timing_begin("k_pad_tile_counts", st);
+        k_pad_tile_counts<<<(unsigned)((ws.num_tiles + 255) / 256), 256, 0, st>>>(ws);
         if ((rc = check_launch())) return rc;
         timing_begin("k_scan_reduce", st);
         k_scan_reduce<<<tblocks, 256, 0, st>>>(ws, ws.tile_off, ws.bin_sums, tn);

@@ -71,8 +71,11 @@ def main():
             ref = g(x)
             graph.replay()
             torch.cuda.synchronize()
-            err = float((ref - y_static).norm() / ref.norm())      # statistics are summed with float atomics: not bit-stable
-            assert err < 1e-3, 'graph replay differs from the eager forward: %g' % err
+            # Two runs are not bit-identical: the instance-norm statistics are summed with float atomics, and after 27
+            # layers of bf16 activations a last-bit difference decorrelates the rounding noise (two eager runs differ by
+            # ~2e-2 rel-L2, each is ~3e-2 from the fp32 module).  The check guards against a broken capture, not rounding.
+            err = float((ref - y_static).norm() / ref.norm())
+            assert err < 6e-2, 'graph replay differs from the eager forward: %g' % err
             ms = time_ms(graph.replay, args.steps)
             launch = 'cuda graph replay'
         except Exception as e:      # noqa: BLE001
@@ -91,7 +94,7 @@ def main():
     fl = conv_flops(g.model, args.H, args.W)
     out = {'workload': 'config5: GlobalGenerator(48->3, ngf 64, 4 down, %d blocks, instance norm) forward [1,48,%d,%d], bf16 '
                        'tcgen05 convolutions, fp32 accumulate' % (args.blocks, args.H, args.W),
-           'ms_per_image': round(ms, 3), 'launch': launch, 'ms_per_image_eager': round(ms_eager, 3), 'conv_tflop': round(fl / 1e12, 3), 'tflops': round(fl / ms / 1e9, 1),
+           'ms_per_image': round(ms, 3), 'launch': launch, 'graph_vs_eager_rel_l2': round(err, 4) if launch.startswith('cuda') else None, 'ms_per_image_eager': round(ms_eager, 3), 'conv_tflop': round(fl / 1e12, 3), 'tflops': round(fl / ms / 1e9, 1),
            'bf16_peak_sustained_tflops': peaks.get('bf16_tflops_sustained'),
            'frac_of_sustained_peak': round(fl / ms / 1e9 / peaks['bf16_tflops_sustained'], 4) if peaks else None,
            'kernels_ms': kern}
