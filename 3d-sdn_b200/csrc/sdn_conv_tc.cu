@@ -366,6 +366,179 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * TNA));
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Weight gradient of the convolution (training path of the encoder trunk):
+//     dW[co, kh, kw, ci] = sum_{n, ho, wo} g[n, ho, wo, co] * x[n, ho*s + kh - p, wo*s + kw - p, ci]
+// as a GEMM whose REDUCTION runs over pixels:  D[co, ci] (+)= G^T[co, pix] . X_tap[pix, ci], one (tap, channel blocks,
+// pixel range) per work item.  Both operands are "MN-major" for the tensor core: in memory a pixel is a row of
+// contiguous channels, i.e. the M (co) and N (ci) indices are the contiguous ones and K (pixels) strides by a row.  A
+// K block = a patch of 64 pixels: TMA box {64 channels, bw, bh, bn} of g, and the box of x shifted by the tap (traversal
+// stride = convolution stride, out-of-bounds = zero padding) -- 64 rows of 128 bytes, 128-byte swizzle, exactly the
+// canonical MN-major SWIZZLE_128B operand ((8 x 16 B, n), (8, k)) : ((1, LBO), (8 x 16 B, SBO)): SBO = 1024 B between
+// 8-pixel groups, LBO = 8192 B between 64-channel blocks (a second box), K = 16 pixels per tcgen05.mma = +2048 B.
+// The pixel range is split over several work items (the layers have 9 taps x 1..16 channel-block pairs only), partial
+// results are added into the fp32 gradient with atomics.  Same warp roles / mbarrier ring / persistent loop as above.
+// ------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+    int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad;
+    int bw, bh, bn, tiles_w, tiles_h, tiles_n;      // 64-pixel patches of the OUTPUT grid
+    int splits, patches_per_split;
+    float* dw;                                      // [Cout, KH, KW, Cin] fp32, accumulated into
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t addr_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr_bytes & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(8192u >> 4) << 16;              // LBO: next 64-channel block (a second 64 x 128 B box)
+    d |= (uint64_t)(1024u >> 4) << 32;              // SBO: next group of 8 pixels
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int TNW>
+__global__ void __launch_bounds__(NTHREADS) k_conv_wgrad(const __grid_constant__ CUtensorMap tmG,
+                                                         const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int STAGES = 6;
+    constexpr int A_B = 2 * 8192, B_B = (TNW / 64) * 8192, STAGE_BYTES = A_B + B_B;
+    __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full[2], s_tmem_empty[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cobs = (p.Cout + 127) / 128, cibs = (p.Cin + TNW - 1) / TNW, taps = p.KH * p.KW;
+    const int total_work = cobs * cibs * taps * p.splits;
+    const int patches = p.tiles_w * p.tiles_h * p.tiles_n;
+    // instruction descriptor: F32 accumulate, BF16 x BF16, A and B MN-major (bits 15, 16), N = TNW, M = 128
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TNW >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&s_tmem_full[s], 1); mbar_init(&s_tmem_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(2u * TNW));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    // work item -> (split, tap, ci block, co block); split fastest so that concurrent CTAs hit different pixels
+    auto decode = [&](int w, int& split, int& tap, int& cib, int& cob) {
+        split = w % p.splits; w /= p.splits;
+        tap = w % taps; w /= taps;
+        cib = w % cibs; cob = w / cibs;
+    };
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmG) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmX) : "memory");
+            int kbg = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                int split, tap, cib, cob;
+                decode(w, split, tap, cib, cob);
+                const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                const int p0 = split * p.patches_per_split, p1 = min(p0 + p.patches_per_split, patches);
+                for (int pt = p0; pt < p1; pt++, kbg++) {
+                    int t = pt;
+                    const int tw = t % p.tiles_w; t /= p.tiles_w;
+                    const int th = t % p.tiles_h; t /= p.tiles_h;
+                    const int wo0 = tw * p.bw, ho0 = th * p.bh, n0 = t * p.bn;
+                    const int st = kbg % STAGES;
+                    if (kbg >= STAGES) mbar_wait(&s_empty[st], (uint32_t)(((kbg / STAGES) - 1) & 1));
+                    unsigned char* sA = smem + st * STAGE_BYTES;
+                    unsigned char* sB = sA + A_B;
+                    mbar_expect_tx(&s_full[st], (uint32_t)STAGE_BYTES);
+                    tma_load_4d(sA, &tmG, &s_full[st], cob * 128, wo0, ho0, n0);
+                    tma_load_4d(sA + 8192, &tmG, &s_full[st], cob * 128 + 64, wo0, ho0, n0);
+                    const int xw = wo0 * p.stride + kw - p.pad, xh = ho0 * p.stride + kh - p.pad;
+#pragma unroll
+                    for (int h = 0; h < TNW / 64; h++) tma_load_4d(sB + h * 8192, &tmX, &s_full[st], cib * TNW + h * 64, xw, xh, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int kbg = 0, it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+                int split, tap, cib, cob;
+                decode(w, split, tap, cib, cob);
+                const int p0 = split * p.patches_per_split, p1 = min(p0 + p.patches_per_split, patches);
+                const int ab = it & 1;
+                if (it >= 2) {
+                    mbar_wait(&s_tmem_empty[ab], (uint32_t)(((it >> 1) - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t acc = tmem + (uint32_t)ab * TNW;
+                for (int pt = p0; pt < p1; pt++, kbg++) {
+                    const int st = kbg % STAGES;
+                    mbar_wait(&s_full[st], (uint32_t)((kbg / STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a0 = smem_u32(smem + st * STAGE_BYTES), b0 = a0 + A_B;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {           // 16 pixels per UMMA = two 8-pixel groups = 2048 bytes
+                        const uint64_t da = make_desc_mn_sw128(a0 + j * 2048), db = make_desc_mn_sw128(b0 + j * 2048);
+                        const uint32_t accumulate = (pt > p0 || j > 0) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(acc), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 ::"r"(smem_u32(&s_empty[st])) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             ::"r"(smem_u32(&s_tmem_full[ab])) : "memory");
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+            int split, tap, cib, cob;
+            decode(w, split, tap, cib, cob);
+            const int ab = it & 1;
+            const int co = cob * 128 + q * 32 + lane;
+            mbar_wait(&s_tmem_full[ab], (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + (uint32_t)ab * TNW;
+            const bool empty = split * p.patches_per_split >= patches;     // a trailing split without patches
+#pragma unroll 1
+            for (int c0 = 0; c0 < TNW; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int ci = cib * TNW + c0;
+                if (!empty && co < p.Cout && ci < p.Cin) {
+                    float* o = p.dw + ((size_t)co * taps + tap) * p.Cin + ci;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (ci + j < p.Cin) atomicAdd(o + j, __uint_as_float(v[j]));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tmem_empty[ab])) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * TNW));
+}
+
 // im2col for convolutions whose input has too few channels for a 64-wide K block (the 7x7 stem of ResNet-18, Cin = 3):
 // out[n, ho, wo, (kh*KW + kw)*Cin + c] = in[n, ho*s + kh - p, wo*s + kw - p, c] (zero outside, zero beyond KH*KW*Cin up
 // to Kpad); the stem then runs as a 1x1 convolution over Kpad channels.
@@ -557,15 +730,15 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-int pick_patch(int Ho, int Wo, int N, int stride, int* bw, int* bh, int* bn) {
-    // 128 output pixels per tile as bn x bh x bw; choose the shape that wastes the fewest rows.  TMA boxes are at most 256
-    // elements per dimension before the traversal stride: bw * stride <= 256.
+int pick_patch(int Ho, int Wo, int N, int stride, int* bw, int* bh, int* bn, int rows = 128) {
+    // `rows` output pixels per tile as bn x bh x bw; choose the shape that wastes the fewest rows.  TMA boxes are at most
+    // 256 elements per dimension before the traversal stride: bw * stride <= 256.
     long best = -1;
-    for (int w = 128; w >= 1; w >>= 1) {
+    for (int w = rows; w >= 1; w >>= 1) {
         if (w * stride > 256) continue;
-        for (int h = 128 / w; h >= 1; h >>= 1) {
+        for (int h = rows / w; h >= 1; h >>= 1) {
             if (h * stride > 256) continue;
-            const int n = 128 / (w * h);
+            const int n = rows / (w * h);
             const long tiles = (long)((Wo + w - 1) / w) * ((Ho + h - 1) / h) * ((N + n - 1) / n);
             if (best < 0 || tiles < best) { best = tiles; *bw = w; *bh = h; *bn = n; }
         }
@@ -741,5 +914,73 @@ extern "C" int sdn_reflect_pad_nhwc(const void* x, void* y, int N, int H, int W,
     const unsigned blocks = (unsigned)((total + 255) / 256 > 148L * 32 ? 148L * 32 : (total + 255) / 256);
     sdn_internal::launch_begin("k_reflect_pad_nhwc", (cudaStream_t)stream);
     k_reflect_pad_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, pad, Cp);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* grad_weight, int N, int H, int W, int Cin,
+                                int Cout, int KH, int KW, int stride, int pad, void* stream) {
+    if (!grad_out || !input || !grad_weight || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 ||
+        stride <= 0 || pad < 0)
+        return SDN_E_ARG;
+    if (Cin % 64 != 0 || Cout % 64 != 0) return SDN_E_ARG;
+    if ((reinterpret_cast<uintptr_t>(grad_out) & 15) || (reinterpret_cast<uintptr_t>(input) & 15)) return SDN_E_ARG;
+    const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return SDN_E_ARG;
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_weight, 0, sizeof(float) * (size_t)Cout * KH * KW * Cin, st);
+    if (e != cudaSuccess) return (int)e;
+
+    WgradParams p;
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+    int rc = pick_patch(Ho, Wo, N, stride, &p.bw, &p.bh, &p.bn, 64);
+    if (rc) return rc;
+    p.tiles_w = (Wo + p.bw - 1) / p.bw; p.tiles_h = (Ho + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
+    p.dw = grad_weight;
+    const int TNW = Cin >= 128 ? 128 : 64;
+    const int patches = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int base_items = ((Cout + 127) / 128) * ((Cin + TNW - 1) / TNW) * KH * KW;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int splits = (3 * sms + base_items - 1) / base_items;           // ~3 work items per SM
+    if (splits < 1) splits = 1;
+    if (splits > patches) splits = patches;
+    p.patches_per_split = (patches + splits - 1) / splits;
+    p.splits = (patches + p.patches_per_split - 1) / p.patches_per_split;     // no empty split
+
+    alignas(64) CUtensorMap tmG, tmX;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+        const cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2};
+        const cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bn};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&tmG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)grad_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SDN_E_ARG;
+    }
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        const cuuint32_t box[4] = {64, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)p.bn};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)input, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SDN_E_ARG;
+    }
+    const long total_work = (long)base_items * p.splits;
+    const size_t smem = (size_t)6 * (16384 + (TNW / 64) * 8192) + 1024;
+    const dim3 grid((unsigned)(total_work < sms ? total_work : sms), 1);
+    if (TNW == 128) {
+        e = cudaFuncSetAttribute(k_conv_wgrad<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return (int)e;
+        sdn_internal::launch_begin("k_conv_wgrad", st);
+        k_conv_wgrad<128><<<grid, NTHREADS, smem, st>>>(tmG, tmX, p);
+    } else {
+        e = cudaFuncSetAttribute(k_conv_wgrad<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return (int)e;
+        sdn_internal::launch_begin("k_conv_wgrad", st);
+        k_conv_wgrad<64><<<grid, NTHREADS, smem, st>>>(tmG, tmX, p);
+    }
     return sdn_internal::launch_end();
 }

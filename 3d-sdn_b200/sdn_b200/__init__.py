@@ -91,6 +91,7 @@ def lib():
         L.sdn_linear_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
         L.sdn_conv2d_forward.argtypes = [ctypes.POINTER(_Conv2d), vp]
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.sdn_conv2d_wgrad.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_reflect_pad_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_instance_norm_apply_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
@@ -437,6 +438,61 @@ def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=Non
         raise SdnError('conv2d_tc: stats must be a contiguous fp32 [N, Cout, 2] tensor')
     with torch.cuda.device(x.device):
         _check(lib().sdn_conv2d_forward(ctypes.byref(c), _stream()))
+    return out
+
+
+def conv2d_wgrad_tc(grad_out, x, KH, KW, stride=1, pad=0):
+    """Weight gradient of conv2d_tc: grad_out [N,Ho,Wo,Cout] bf16, x [N,H,W,Cin] bf16 -> fp32 [Cout,KH,KW,Cin]
+    (sdn_conv2d_wgrad: tcgen05 GEMM over pixels, MN-major operands straight from the NHWC tensors, split over pixel
+    ranges with fp32 atomics)."""
+    _need_cuda(grad_out, x)
+    if grad_out.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        raise SdnError('conv2d_wgrad_tc: bf16 NHWC tensors expected')
+    grad_out, x = grad_out.contiguous(), x.contiguous()
+    N, H, W, Cin = x.shape
+    Cout = grad_out.shape[-1]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    if tuple(grad_out.shape) != (N, Ho, Wo, Cout) or Cin % 64 or Cout % 64:
+        raise SdnError('conv2d_wgrad_tc: grad_out %s does not match x %s (channels must be multiples of 64)'
+                       % (tuple(grad_out.shape), tuple(x.shape)))
+    gw = torch.empty(Cout, KH, KW, Cin, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _check(lib().sdn_conv2d_wgrad(_ptr(grad_out), _ptr(x), _ptr(gw), N, H, W, Cin, Cout, KH, KW, int(stride), int(pad),
+                                      _stream()))
+    return gw
+
+
+def conv2d_dgrad_tc(grad_out, weight, in_hw, stride=1, pad=0, residual=None):
+    """Data gradient of a convolution with `weight` [Cout, Cin, KH, KW] (fp32 / bf16 torch layout): grad_out
+    [N,Ho,Wo,Cout] bf16 -> [N,H,W,Cin] bf16, on the SAME tcgen05 kernel as the forward: stride 1 = a convolution with the
+    spatially flipped, channel-transposed weights and padding K-1-pad; stride 2 (3x3 pad 1, or 1x1) = the parity phases
+    of the transposed convolution, each written into its interleaved positions.  `residual` (dense [N,H,W,Cin] bf16) is
+    added in the epilogue (the skip connection's gradient)."""
+    Cout, Cin, KH, KW = weight.shape
+    H, W = in_hw
+    N = grad_out.shape[0]
+    if stride == 1:
+        wt = pack_conv_weight(weight.detach().flip(2, 3).transpose(0, 1))
+        return conv2d_tc(grad_out, wt, 1, KH - 1 - pad, None, None, residual, False, out_hw=(H, W))
+    if stride != 2 or H % 2 or W % 2:
+        raise SdnError('conv2d_dgrad_tc: stride %d with input %dx%d is not supported' % (stride, H, W))
+    out = torch.empty(N, H, W, Cin, device=grad_out.device, dtype=torch.bfloat16)
+    wT = weight.detach().transpose(0, 1)                    # [Cin(out of the transposed conv), Cout(in), KH, KW]
+    if KH == 3 and pad == 1:
+        taps = {0: [1], 1: [2, 0]}
+        for ph in (0, 1):
+            for pw in (0, 1):
+                wk = wT[:, :, taps[ph], :][:, :, :, taps[pw]]
+                conv2d_tc(grad_out, pack_conv_weight(wk.contiguous()), 1, 0, None, None, None, False,
+                          out_hw=(H // 2, W // 2), out=out[:, ph::2, pw::2])
+    elif KH == 1 and pad == 0:
+        out.zero_()
+        conv2d_tc(grad_out, pack_conv_weight(wT.contiguous()), 1, 0, None, None, None, False, out_hw=(H // 2, W // 2),
+                  out=out[:, 0::2, 0::2])
+    else:
+        raise SdnError('conv2d_dgrad_tc: stride-2 kernel %dx%d pad %d is not supported' % (KH, KW, pad))
+    if residual is not None:
+        out = out + residual
     return out
 
 

@@ -199,6 +199,15 @@ typedef struct sdn_conv2d {
 
 int sdn_conv2d_forward(const sdn_conv2d* c, void* stream);
 
+/* Weight gradient of the convolution above (training path of the encoder trunk; replaces cuDNN's backward-filter behind
+ * torch.autograd for the convolutions of derenderer.py:25-27):
+ *   grad_weight[co, kh, kw, ci] = sum_{n,ho,wo} grad_out[n,ho,wo,co] * input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci]
+ * grad_out [N,Ho,Wo,Cout] bf16, input [N,H,W,Cin] bf16 (Cin, Cout multiples of 64), grad_weight fp32 [Cout,KH,KW,Cin]
+ * (overwritten).  The data gradient needs no entry point of its own: it is sdn_conv2d_forward of grad_out with the
+ * spatially flipped, channel-transposed weights (stride 1) or, for stride 2, its four output-parity phases. */
+int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* grad_weight, int N, int H, int W, int Cin, int Cout,
+                     int KH, int KW, int stride, int pad, void* stream);
+
 /* im2col for inputs with few channels (the 7x7 stem, Cin = 3): output [N, Ho, Wo, Kpad] bf16 with
  * output[.., (kh*KW + kw)*Cin + ci] = input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci] (0 outside and beyond
  * KH*KW*Cin); the stem then runs through sdn_conv2d_forward as a 1x1 convolution over Kpad channels. */

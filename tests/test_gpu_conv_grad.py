@@ -1,0 +1,57 @@
+"""Backward of the tcgen05 convolution: weight gradient (sdn_conv2d_wgrad: GEMM over pixels with MN-major operands) and data
+gradient (the forward kernel on flipped / transposed weights, parity phases for stride 2) against torch autograd in fp32 on
+the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    import sdn_b200
+    sdn_b200.lib()
+    return torch.device('cuda:0')
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+CASES = [   # N, H, W, Cin, Cout, K, stride, pad: the ResNet-18 layer shapes (smaller batch) + ragged ones
+    (4, 56, 56, 64, 64, 3, 1, 1), (4, 56, 56, 64, 128, 3, 2, 1), (4, 56, 56, 64, 128, 1, 2, 0), (4, 28, 28, 128, 128, 3, 1, 1),
+    (4, 28, 28, 128, 256, 3, 2, 1), (4, 14, 14, 256, 256, 3, 1, 1), (4, 14, 14, 256, 512, 3, 2, 1), (4, 14, 14, 256, 512, 1, 2, 0),
+    (6, 7, 7, 512, 512, 3, 1, 1), (3, 10, 18, 64, 192, 3, 1, 1), (1, 112, 112, 192, 64, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,K,stride,pad', CASES)
+def test_weight_and_data_gradients(dev, N, H, W, Cin, Cout, K, stride, pad):
+    import sdn_b200
+    g_ = torch.Generator().manual_seed(N + H + Cin + Cout + K + stride)
+    x = torch.randn(N, Cin, H, W, generator=g_).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, K, K, generator=g_) / (Cin * K * K) ** 0.5).bfloat16().float().requires_grad_(True)
+    y = F.conv2d(x, w, stride=stride, padding=pad)
+    go = torch.randn(y.shape, generator=g_).bfloat16().float()
+    y.backward(go)
+    xn = x.detach().to(dev).bfloat16().permute(0, 2, 3, 1).contiguous()
+    gn = go.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous()
+    gw = sdn_b200.conv2d_wgrad_tc(gn, xn, K, K, stride, pad)                   # [Cout, K, K, Cin] fp32
+    assert _rel(gw.permute(0, 3, 1, 2), w.grad) <= 2e-3, _rel(gw.permute(0, 3, 1, 2), w.grad)
+    gx = sdn_b200.conv2d_dgrad_tc(gn, w.detach().to(dev), (H, W), stride, pad)  # [N, H, W, Cin] bf16
+    assert _rel(gx.permute(0, 3, 1, 2).float(), x.grad) <= 4e-3, _rel(gx.permute(0, 3, 1, 2).float(), x.grad)
+
+
+def test_data_gradient_adds_the_skip_gradient(dev):
+    import sdn_b200
+    g_ = torch.Generator().manual_seed(5)
+    w = (torch.randn(64, 64, 3, 3, generator=g_) / 24.0).bfloat16().float()
+    go = torch.randn(2, 64, 12, 20, generator=g_).bfloat16().float()
+    skip = torch.randn(2, 64, 12, 20, generator=g_).bfloat16()
+    want = F.conv_transpose2d(go, w, padding=1) + skip.float()
+    got = sdn_b200.conv2d_dgrad_tc(go.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous(), w.to(dev), (12, 20), 1, 1,
+                                   residual=skip.to(dev).permute(0, 2, 3, 1).contiguous())
+    assert _rel(got.permute(0, 3, 1, 2).float(), want) <= 4e-3
