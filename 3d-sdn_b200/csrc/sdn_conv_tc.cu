@@ -687,6 +687,117 @@ __global__ void __launch_bounds__(256) k_inorm_apply_pad(const __nv_bfloat16* __
     }
 }
 
+// ---- BatchNorm2d in training mode around the convolutions of the encoder trunk (torchvision BasicBlock: conv -> bn -> relu,
+// conv -> bn -> (+ identity) -> relu).  Forward: the convolution's epilogue already produced the per-channel sums; the
+// normalisation is y = act(z * scale[c] + shift[c] (+ residual)) with scale = gamma * rstd, shift = beta - mean * scale.
+__global__ void __launch_bounds__(256) k_affine_act(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
+                                                    __nv_bfloat16* __restrict__ y, long groups, int C, int act) {
+    const int cg = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cg) * 8;
+        const uint4 zv = *reinterpret_cast<const uint4*>(z + i * 8);
+        uint4 rv = make_uint4(0, 0, 0, 0);
+        if (residual) rv = *reinterpret_cast<const uint4*>(residual + i * 8);
+        const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&zw[k]);
+            float a = __fmaf_rn(__low2float(v), __ldg(scale + c + 2 * k), __ldg(shift + c + 2 * k));
+            float b = __fmaf_rn(__high2float(v), __ldg(scale + c + 2 * k + 1), __ldg(shift + c + 2 * k + 1));
+            if (residual) {
+                const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(&rw[k]);
+                a += __low2float(rr); b += __high2float(rr);
+            }
+            if (act == 1) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+            const __nv_bfloat162 o2 = __floats2bfloat162_rn(a, b);
+            ow[k] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+        *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// Backward, pass 1: per channel  s1 = sum g^,  s2 = sum g^ * zhat,  g^ = gy * [y > 0] (when the unit ends in a ReLU),
+// zhat = (z - mean) * rstd.  Same block shape as k_inorm_stats (rows of one slab of channels, smem combine, one atomic
+// per channel per block).
+__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
+                                                       const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, float* __restrict__ sums, long M, int C,
+                                                       int rows, int pairs, int relu) {
+    __shared__ float s_part[256 * 4];
+    const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs, nrl = 256 / pairs;
+    const int c = (blockIdx.y * pairs + cp) * 2;
+    const long r0 = (long)blockIdx.x * rows, r1 = r0 + rows < M ? r0 + rows : M;
+    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
+    if (c < C && rl < nrl) {
+        const float m0 = mean[c], m1 = mean[c + 1], i0 = rstd[c], i1 = rstd[c + 1];
+#pragma unroll 4
+        for (long r = r0 + rl; r < r1; r += nrl) {
+            const size_t e = (size_t)r * C + c;
+            const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(gy + e);
+            const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(z + e);
+            float g0 = __low2float(g2), g1 = __high2float(g2);
+            if (relu) {
+                const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(y + e);
+                if (!(__low2float(y2) > 0.0f)) g0 = 0.0f;
+                if (!(__high2float(y2) > 0.0f)) g1 = 0.0f;
+            }
+            a0 += g0; a1 += g1;
+            b0 = __fmaf_rn(g0, (__low2float(z2) - m0) * i0, b0);
+            b1 = __fmaf_rn(g1, (__high2float(z2) - m1) * i1, b1);
+        }
+    }
+    s_part[threadIdx.x * 4] = a0; s_part[threadIdx.x * 4 + 1] = b0; s_part[threadIdx.x * 4 + 2] = a1; s_part[threadIdx.x * 4 + 3] = b1;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        for (int k = 1; k < nrl; k++) {
+            const float* o = s_part + (k * pairs + cp) * 4;
+            a0 += o[0]; b0 += o[1]; a1 += o[2]; b1 += o[3];
+        }
+        float* o = sums + (size_t)c * 2;
+        atomicAdd(o, a0); atomicAdd(o + 1, b0); atomicAdd(o + 2, a1); atomicAdd(o + 3, b1);
+    }
+}
+
+// Backward, pass 2: gz = gamma * rstd * (g^ - s1 / M - zhat * s2 / M); optionally also writes g^ (the gradient that flows
+// into the skip connection of a BasicBlock).
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
+                                                      const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                      const float* __restrict__ sums, __nv_bfloat16* __restrict__ gz,
+                                                      __nv_bfloat16* __restrict__ gres, long groups, int C, float inv_m, int relu) {
+    const int cg = C >> 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cg) * 8;
+        const uint4 gv = *reinterpret_cast<const uint4*>(gy + i * 8), zv = *reinterpret_cast<const uint4*>(z + i * 8);
+        uint4 yv = make_uint4(0, 0, 0, 0);
+        if (relu) yv = *reinterpret_cast<const uint4*>(y + i * 8);
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, zw[4] = {zv.x, zv.y, zv.z, zv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        uint32_t ow[4], rw[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[k]);
+            const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&zw[k]);
+            float g0 = __low2float(g2), g1 = __high2float(g2);
+            if (relu) {
+                const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yw[k]);
+                if (!(__low2float(y2) > 0.0f)) g0 = 0.0f;
+                if (!(__high2float(y2) > 0.0f)) g1 = 0.0f;
+            }
+            const int c0 = c + 2 * k, c1 = c0 + 1;
+            const float zh0 = (__low2float(z2) - mean[c0]) * rstd[c0], zh1 = (__high2float(z2) - mean[c1]) * rstd[c1];
+            const float o0 = gamma[c0] * rstd[c0] * (g0 - sums[2 * c0] * inv_m - zh0 * sums[2 * c0 + 1] * inv_m);
+            const float o1 = gamma[c1] * rstd[c1] * (g1 - sums[2 * c1] * inv_m - zh1 * sums[2 * c1 + 1] * inv_m);
+            const __nv_bfloat162 o2 = __floats2bfloat162_rn(o0, o1), r2 = __floats2bfloat162_rn(g0, g1);
+            ow[k] = *reinterpret_cast<const uint32_t*>(&o2);
+            rw[k] = *reinterpret_cast<const uint32_t*>(&r2);
+        }
+        *reinterpret_cast<uint4*>(gz + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (gres) *reinterpret_cast<uint4*>(gres + i * 8) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+    }
+}
+
 // ---- C. reflection padding of an NHWC bf16 tensor (nn.ReflectionPad2d), with optional zero channels up to Cp ----
 __global__ void __launch_bounds__(256) k_reflect_pad_nhwc(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                           int N, int H, int W, int C, int pad, int Cp) {
@@ -982,5 +1093,46 @@ extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* 
         sdn_internal::launch_begin("k_conv_wgrad", st);
         k_conv_wgrad<64><<<grid, NTHREADS, smem, st>>>(tmG, tmX, p);
     }
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_affine_act_nhwc(const void* z, const float* scale, const float* shift, const void* residual, void* y,
+                                   long long pixels, int C, int act, void* stream) {
+    if (!z || !scale || !shift || !y || pixels <= 0 || C <= 0 || (C & 7)) return SDN_E_ARG;
+    const long groups = (long)pixels * (C / 8);
+    const unsigned blocks = (unsigned)((groups + 255) / 256 > 148L * 16 ? 148L * 16 : (groups + 255) / 256);
+    sdn_internal::launch_begin("k_affine_act", (cudaStream_t)stream);
+    k_affine_act<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, scale, shift, (const __nv_bfloat16*)residual,
+                                                           (__nv_bfloat16*)y, groups, C, act);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, const void* z, const float* mean, const float* rstd,
+                                            const float* gamma, float* sums, void* grad_z, void* grad_skip, long long pixels,
+                                            int C, int relu, void* stream) {
+    if (!grad_y || !z || !mean || !rstd || !gamma || !sums || !grad_z || pixels <= 0 || C <= 0 || (C & 7) || (relu && !y))
+        return SDN_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)C, st);
+    if (e != cudaSuccess) return (int)e;
+    int pairs = C / 2;
+    if (pairs > 256) pairs = 256;
+    while (256 % pairs) pairs--;
+    const int slabs = (C / 2 + pairs - 1) / pairs, nrl = 256 / pairs;
+    long want = ((long)pixels * slabs + 148L * 8 - 1) / (148L * 8);
+    int rows = (int)(want < 32L * nrl ? 32L * nrl : (want > 8192 ? 8192 : want));
+    rows = (rows + nrl - 1) / nrl * nrl;
+    sdn_internal::launch_begin("k_bn_bwd_reduce", st);
+    k_bn_bwd_reduce<<<dim3((unsigned)((pixels + rows - 1) / rows), (unsigned)slabs), 256, 0, st>>>(
+        (const __nv_bfloat16*)grad_y, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, rstd, sums, (long)pixels, C, rows,
+        pairs, relu);
+    int rc = sdn_internal::launch_end();
+    if (rc) return rc;
+    const long groups = (long)pixels * (C / 8);
+    const unsigned blocks = (unsigned)((groups + 255) / 256 > 148L * 16 ? 148L * 16 : (groups + 255) / 256);
+    sdn_internal::launch_begin("k_bn_bwd_apply", st);
+    k_bn_bwd_apply<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)grad_y, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, rstd,
+                                           gamma, sums, (__nv_bfloat16*)grad_z, (__nv_bfloat16*)grad_skip, groups, C,
+                                           1.0f / (float)pixels, relu);
     return sdn_internal::launch_end();
 }

@@ -54,6 +54,11 @@ class Derenderer(Module):
                     self._trunk_tc.device != images.device:
                 self._trunk_tc = ResNet18TC(self.net)
             return self._trunk_tc(images)
+        if self.tensor_core_trunk and images.is_cuda and self.training:
+            # training form: forward, data and weight gradients of every convolution on the tcgen05 kernels, BatchNorm
+            # in batch-statistics mode on native kernels (encoder_tc.resnet18_trunk_train)
+            from derender3d.models.encoder_tc import resnet18_trunk_train
+            return resnet18_trunk_train(self.net, images)
         n = self.net
         x = n.maxpool(n.relu(n.bn1(n.conv1(images))))
         x = n.layer4(n.layer3(n.layer2(n.layer1(x))))

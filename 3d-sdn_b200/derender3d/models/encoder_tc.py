@@ -68,3 +68,144 @@ class ResNet18TC(object):
             y = sdn_b200.conv2d_tc(x, w1, s1, 1, bn1[0], bn1[1], None, True)
             x = sdn_b200.conv2d_tc(y, w2, 1, 1, bn2[0], bn2[1], identity, True)
         return x.float().mean(dim=(1, 2))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Training form: forward AND backward of the trunk on the hand-written kernels (BatchNorm in batch-statistics mode).
+# ----------------------------------------------------------------------------------------------------------------------
+def _bn_train(z, stats, bn, relu, residual=None):
+    """BatchNorm2d (training) of a convolution result z [N,H,W,C] bf16 whose per-(image, channel) sums the convolution's
+    epilogue left in `stats` [N,C,2]: batch mean / biased variance, running-statistics update (momentum, unbiased variance,
+    as torch.nn.BatchNorm2d does), y = relu?(z * scale + shift (+ residual)).  -> (y, mean [C], rstd [C])."""
+    M = z.numel() // z.shape[-1]
+    tot = stats.sum(dim=0)                                  # [C, 2]
+    mean = tot[:, 0] / M
+    var = (tot[:, 1] / M - mean * mean).clamp_min(0.0)
+    rstd = torch.rsqrt(var + bn.eps)
+    if bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            m = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (M / max(M - 1, 1)), alpha=m)
+            bn.num_batches_tracked.add_(1)
+    scale = bn.weight.detach().float() * rstd
+    shift = bn.bias.detach().float() - mean * scale
+    return sdn_b200.affine_act_nhwc(z, scale, shift, residual, relu), mean, rstd
+
+
+class _TrunkTrainFunction(torch.autograd.Function):
+    """features = ResNet18(images) in training mode; every convolution (forward, data gradient, weight gradient) on the
+    tcgen05 kernels of csrc/sdn_conv_tc.cu, BatchNorm forward / backward on sdn_affine_act_nhwc /
+    sdn_batch_norm_backward_nhwc, max-pool / average-pool through torch.  Activations and activation gradients are bf16
+    NHWC, parameter gradients fp32."""
+
+    @staticmethod
+    def forward(ctx, images, net, *params):
+        x = images.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
+        N = x.shape[0]
+        dev = x.device
+        saved = {}
+
+        def conv_bn(xin, conv, bn, relu, residual=None, stem=False):
+            if stem:
+                k, s, p = int(conv.kernel_size[0]), int(conv.stride[0]), int(conv.padding[0])
+                cols_n = conv.in_channels * k * k
+                kpad = (cols_n + 63) // 64 * 64
+                xin = sdn_b200.im2col_nhwc(xin, k, k, s, p, kpad)
+                w = torch.zeros(conv.out_channels, 1, 1, kpad, device=dev, dtype=torch.bfloat16)
+                w[:, 0, 0, :cols_n] = conv.weight.detach().permute(0, 2, 3, 1).reshape(conv.out_channels, cols_n).to(torch.bfloat16)
+                stride, pad = 1, 0
+            else:
+                w = sdn_b200.pack_conv_weight(conv.weight)
+                stride, pad = int(conv.stride[0]), int(conv.padding[0])
+            stats = torch.empty(N, conv.out_channels, 2, device=dev, dtype=torch.float32)
+            z = sdn_b200.conv2d_tc(xin, w, stride, pad, stats=stats)
+            y, mean, rstd = _bn_train(z, stats, bn, relu, residual)
+            return xin, z, y, mean, rstd
+
+        units = []          # (name, conv, bn, relu, input, z, y, mean, rstd)
+        xin, z, y, mean, rstd = conv_bn(x, net.conv1, net.bn1, True, stem=True)
+        units.append(('stem', net.conv1, net.bn1, True, xin, z, y, mean, rstd))
+        pool_in = y.permute(0, 3, 1, 2)
+        pooled, pool_idx = F.max_pool2d(pool_in, net.maxpool.kernel_size, net.maxpool.stride, net.maxpool.padding,
+                                        return_indices=True)
+        x = pooled.permute(0, 2, 3, 1).contiguous()
+        saved['pool'] = (pool_in.shape, pool_idx)
+        blocks = []
+        for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+            for blk in layer:
+                xb = x
+                ds = None
+                identity = xb
+                if blk.downsample is not None:
+                    dxin, dz, dy, dmean, drstd = conv_bn(xb, blk.downsample[0], blk.downsample[1], False)
+                    ds = (blk.downsample[0], blk.downsample[1], dz, dmean, drstd)
+                    identity = dy
+                _, z1, y1, m1, r1 = conv_bn(xb, blk.conv1, blk.bn1, True)
+                _, z2, out, m2, r2 = conv_bn(y1, blk.conv2, blk.bn2, True, residual=identity)
+                blocks.append((blk, xb, z1, y1, m1, r1, z2, out, m2, r2, ds))
+                x = out
+        feat = x.float().mean(dim=(1, 2))
+        ctx.net, ctx.units, ctx.blocks, ctx.saved, ctx.last_shape = net, units, blocks, saved, x.shape
+        ctx.param_ids = [id(p) for p in params]
+        return feat
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        net = ctx.net
+        grads = {}
+        N, H, W, C = ctx.last_shape
+        g = (g_feat.detach().float() / (H * W)).to(torch.bfloat16)[:, None, None, :].expand(N, H, W, C).contiguous()
+
+        def bn_conv_backward(gy, y, z, mean, rstd, conv, bn, relu, xin, want_skip=False, need_dx=True, skip_add=None, stem=False):
+            gz, g_gamma, g_beta, g_skip = sdn_b200.batch_norm_backward_nhwc(gy, y if relu else None, z, mean, rstd, bn.weight, relu,
+                                                                              want_skip)
+            grads[id(bn.weight)], grads[id(bn.bias)] = g_gamma, g_beta
+            if stem:
+                k = int(conv.kernel_size[0])
+                gw = sdn_b200.conv2d_wgrad_tc(gz, xin, 1, 1, 1, 0)              # [64, 1, 1, Kpad] over the im2col columns
+                cols_n = conv.in_channels * k * k
+                grads[id(conv.weight)] = gw[:, 0, 0, :cols_n].reshape(conv.out_channels, k, k, conv.in_channels).permute(0, 3, 1, 2)
+                return None, g_skip
+            k, s, p = int(conv.kernel_size[0]), int(conv.stride[0]), int(conv.padding[0])
+            grads[id(conv.weight)] = sdn_b200.conv2d_wgrad_tc(gz, xin, k, k, s, p).permute(0, 3, 1, 2)
+            dx = None
+            if need_dx:
+                dx = sdn_b200.conv2d_dgrad_tc(gz, conv.weight, (xin.shape[1], xin.shape[2]), s, p, residual=skip_add)
+            return dx, g_skip
+
+        for blk, xb, z1, y1, m1, r1, z2, out, m2, r2, ds in reversed(ctx.blocks):
+            # out = relu(bn2(conv2(y1)) + identity)
+            g_y1, g_id = bn_conv_backward(g, out, z2, m2, r2, blk.conv2, blk.bn2, True, y1, want_skip=True)
+            if ds is None:
+                g, _ = bn_conv_backward(g_y1, y1, z1, m1, r1, blk.conv1, blk.bn1, True, xb, skip_add=g_id if int(blk.conv1.stride[0]) == 1 else None)
+                if int(blk.conv1.stride[0]) != 1:
+                    g = g + g_id
+            else:
+                dconv, dbn, dz, dmean, drstd = ds
+                g_main, _ = bn_conv_backward(g_y1, y1, z1, m1, r1, blk.conv1, blk.bn1, True, xb)
+                g_ds, _ = bn_conv_backward(g_id, None, dz, dmean, drstd, dconv, dbn, False, xb)
+                g = g_main + g_ds
+        # max-pool backward (torch), then the stem
+        in_shape, idx = ctx.saved['pool']
+        g_pool = torch.ops.aten.max_pool2d_with_indices_backward(
+            g.permute(0, 3, 1, 2), ctx.units[0][6].permute(0, 3, 1, 2), list(_pair(net.maxpool.kernel_size)),
+            list(_pair(net.maxpool.stride)), list(_pair(net.maxpool.padding)), [1, 1], False, idx)
+        _, conv, bn, relu, xin, z, y, mean, rstd = ctx.units[0]
+        bn_conv_backward(g_pool.permute(0, 2, 3, 1).contiguous(), y, z, mean, rstd, conv, bn, True, xin, stem=True)
+        out = [None, None]
+        for pid in ctx.param_ids:
+            gp = grads.get(pid)
+            out.append(None if gp is None else gp.float())
+        return tuple(out)
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def resnet18_trunk_train(net, images):
+    """Training-mode trunk: features [N, 512] fp32 with autograd through the hand-written kernels.  Gradients flow to the
+    convolution weights and BatchNorm affine parameters of `net` (not to `images`: the encoder's input is data)."""
+    params = [p for n, p in net.named_parameters() if not n.startswith('fc.')]
+    return _TrunkTrainFunction.apply(images, net, *params)

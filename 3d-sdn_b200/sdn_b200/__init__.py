@@ -92,6 +92,8 @@ def lib():
         L.sdn_conv2d_forward.argtypes = [ctypes.POINTER(_Conv2d), vp]
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_conv2d_wgrad.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.sdn_affine_act_nhwc.argtypes = [vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
+        L.sdn_batch_norm_backward_nhwc.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
         L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_reflect_pad_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_instance_norm_apply_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
@@ -494,6 +496,38 @@ def conv2d_dgrad_tc(grad_out, weight, in_hw, stride=1, pad=0, residual=None):
     if residual is not None:
         out = out + residual
     return out
+
+
+def affine_act_nhwc(z, scale, shift, residual=None, relu=False):
+    """y = relu?(z * scale[c] + shift[c] (+ residual)) on NHWC bf16 (sdn_affine_act_nhwc): BatchNorm's normalising pass."""
+    _need_cuda(z, scale, shift, residual)
+    z = z.contiguous()
+    C = z.shape[-1]
+    y = torch.empty_like(z)
+    scale, shift = scale.detach().float().contiguous(), shift.detach().float().contiguous()
+    if residual is not None:
+        residual = residual.contiguous()
+    with torch.cuda.device(z.device):
+        _check(lib().sdn_affine_act_nhwc(_ptr(z), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(y), z.numel() // C, C,
+                                         1 if relu else 0, _stream()))
+    return y
+
+
+def batch_norm_backward_nhwc(grad_y, y, z, mean, rstd, gamma, relu, want_skip=False):
+    """-> (grad_z bf16, grad_gamma [C], grad_beta [C], grad_skip bf16 | None); see include/sdn_b200.h."""
+    _need_cuda(grad_y, y, z, mean, rstd, gamma)
+    grad_y, z = grad_y.contiguous(), z.contiguous()
+    y = None if y is None else y.contiguous()
+    C = z.shape[-1]
+    sums = torch.empty(C, 2, device=z.device, dtype=torch.float32)
+    gz = torch.empty_like(z)
+    gs = torch.empty_like(z) if want_skip else None
+    mean, rstd, gamma = mean.float().contiguous(), rstd.float().contiguous(), gamma.detach().float().contiguous()
+    with torch.cuda.device(z.device):
+        _check(lib().sdn_batch_norm_backward_nhwc(_ptr(grad_y), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma),
+                                                  _ptr(sums), _ptr(gz), _ptr(gs), z.numel() // C, C, 1 if relu else 0,
+                                                  _stream()))
+    return gz, sums[:, 1], sums[:, 0], gs
 
 
 def reflect_pad_nhwc(x, pad, cpad=None):

@@ -208,6 +208,18 @@ int sdn_conv2d_forward(const sdn_conv2d* c, void* stream);
 int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* grad_weight, int N, int H, int W, int Cin, int Cout,
                      int KH, int KW, int stride, int pad, void* stream);
 
+/* BatchNorm2d in training mode around those convolutions (torchvision BasicBlock), NHWC bf16, `pixels` = N*H*W:
+ *   forward : y = act(z * scale[c] + shift[c] (+ residual)), scale = gamma * rstd, shift = beta - mean * scale (the batch
+ *             statistics come from sdn_conv2d.stats); act 0 none / 1 ReLU;
+ *   backward: g^ = grad_y * [y > 0] (relu = 1), sums[c] = (sum g^, sum g^ * zhat) -- i.e. (grad_beta, grad_gamma) --,
+ *             grad_z = gamma * rstd * (g^ - sums[c,0] / pixels - zhat * sums[c,1] / pixels); grad_skip (optional) = g^,
+ *             the gradient entering the block's skip connection.  sums: fp32 [C, 2], cleared by the call. */
+int sdn_affine_act_nhwc(const void* z, const float* scale, const float* shift, const void* residual, void* y,
+                        long long pixels, int C, int act, void* stream);
+int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, const void* z, const float* mean, const float* rstd,
+                                 const float* gamma, float* sums, void* grad_z, void* grad_skip, long long pixels, int C,
+                                 int relu, void* stream);
+
 /* im2col for inputs with few channels (the 7x7 stem, Cin = 3): output [N, Ho, Wo, Kpad] bf16 with
  * output[.., (kh*KW + kw)*Cin + ci] = input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci] (0 outside and beyond
  * KH*KW*Cin); the stem then runs through sdn_conv2d_forward as a 1x1 convolution over Kpad channels. */

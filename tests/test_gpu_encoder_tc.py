@@ -71,3 +71,50 @@ def test_encoder_outputs_and_weight_refresh(dev):
     enc.tensor_core_trunk = True
     out = enc(x, m, d)                                        # training mode: the autograd (cuDNN) path
     assert out['_theta_deltas'].requires_grad
+
+
+def test_training_trunk_forward_backward_matches_torchvision(dev):
+    """resnet18_trunk_train: features, BatchNorm running statistics and every parameter gradient against torchvision's fp32
+    module in train mode with the same weights (bf16 operands and activations: a few 1e-2 on the deepest gradients)."""
+    import copy
+    from derender3d.models.derenderer import Derenderer
+    from derender3d.models.encoder_tc import resnet18_trunk_train
+    torch.manual_seed(0)
+    ref = Derenderer().to(dev).train()
+    mine = copy.deepcopy(ref)
+    x = torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(3)).to(dev)
+    t = torch.randn(8, 512, generator=torch.Generator().manual_seed(4)).to(dev)
+    f_ref = ref._trunk(x)
+    (f_ref * t).sum().backward()
+    f_mine = resnet18_trunk_train(mine.net, x)
+    (f_mine * t).sum().backward()
+    assert _rel(f_mine, f_ref) <= 3e-2, _rel(f_mine, f_ref)
+    assert _rel(mine.net.bn1.running_mean, ref.net.bn1.running_mean) <= 2e-2
+    assert _rel(mine.net.layer4[1].bn2.running_var, ref.net.layer4[1].bn2.running_var) <= 5e-2
+    assert int(mine.net.bn1.num_batches_tracked) == 1
+    worst = 0.0
+    for (n, p), (_, q) in zip(mine.net.named_parameters(), ref.net.named_parameters()):
+        if n.startswith('fc.'):
+            continue
+        assert p.grad is not None, n
+        e = _rel(p.grad, q.grad)
+        worst = max(worst, e)
+        assert e <= 0.12, (n, e)
+    assert worst > 0
+
+
+def test_derenderer_trains_through_the_native_trunk(dev):
+    from derender3d.models.derenderer import Derenderer
+    torch.manual_seed(1)
+    enc = Derenderer().to(dev).train()
+    enc.tensor_core_trunk = True
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 3, 224, 224, generator=g).to(dev)
+    m, d = torch.randn(4, 2, generator=g).to(dev) * 0.1, (0.2 + torch.rand(4, 2, generator=g)).to(dev)
+    import sdn_b200
+    n0 = sdn_b200.launch_count()
+    out = enc(x, m, d)
+    sum(v.float().pow(2).mean() for v in out.values()).backward()
+    assert sdn_b200.launch_count() - n0 > 100            # forward + dgrad + wgrad + BatchNorm kernels
+    assert enc.net.conv1.weight.grad is not None and torch.isfinite(enc.net.conv1.weight.grad).all()
+    assert enc.net.layer3[0].downsample[0].weight.grad.abs().sum() > 0 and enc.fc1.weight.grad is not None
