@@ -841,7 +841,8 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-int pick_patch(int Ho, int Wo, int N, int stride, int* bw, int* bh, int* bn, int rows = 128) {
+int pick_patch(int Ho, int Wo, int N, int stride, int* bw, int* bh, int* bn, int rows = 128, int min_hw = 1) {
+    // min_hw: smallest bh * bw allowed (32 when the epilogue accumulates per-image statistics: a warp's rows in one image)
     // `rows` output pixels per tile as bn x bh x bw; choose the shape that wastes the fewest rows.  TMA boxes are at most
     // 256 elements per dimension before the traversal stride: bw * stride <= 256.
     long best = -1;
@@ -849,6 +850,7 @@ int pick_patch(int Ho, int Wo, int N, int stride, int* bw, int* bh, int* bn, int
         if (w * stride > 256) continue;
         for (int h = rows / w; h >= 1; h >>= 1) {
             if (h * stride > 256) continue;
+            if (w * h < min_hw) continue;
             const int n = rows / (w * h);
             const long tiles = (long)((Wo + w - 1) / w) * ((Ho + h - 1) / h) * ((N + n - 1) / n);
             if (best < 0 || tiles < best) { best = tiles; *bw = w; *bh = h; *bn = n; }
@@ -880,7 +882,7 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
     ConvParams p;
     p.N = c->N; p.H = c->H; p.W = c->W; p.Cin = c->Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = c->Cout;
     p.KH = c->KH; p.KW = c->KW; p.stride = c->stride; p.pad = c->pad;
-    int rc = pick_patch(Ho, Wo, c->N, c->stride, &p.bw, &p.bh, &p.bn);
+    int rc = pick_patch(Ho, Wo, c->N, c->stride, &p.bw, &p.bh, &p.bn, 128, c->stats ? 32 : 1);
     if (rc) return rc;
     p.tiles_w = (Wo + p.bw - 1) / p.bw; p.tiles_h = (Ho + p.bh - 1) / p.bh; p.tiles_n = (c->N + p.bn - 1) / p.bn;
     p.out = (__nv_bfloat16*)c->output; p.scale = c->scale; p.shift = c->shift;

@@ -74,7 +74,10 @@ class Derenderer(Module):
             x = linear_tc(x, self.fc2.weight, self.fc2.bias, relu=True)
             x = linear_tc(x, self._fc3.weight, self._fc3.bias, relu=False)
         else:
-            x = self.relu(self.net(images))
+            if self.tensor_core_trunk and images.is_cuda:       # training: native trunk, fp32 head
+                x = self.relu(self.net.fc(self._trunk(images)))
+            else:
+                x = self.relu(self.net(images))
             x = torch.cat([x.float(), mroi_norms, droi_norms], dim=1)
             x = self.relu(self.fc1(x))
             x = self.relu(self.fc2(x))

@@ -55,3 +55,40 @@ def test_data_gradient_adds_the_skip_gradient(dev):
     got = sdn_b200.conv2d_dgrad_tc(go.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous(), w.to(dev), (12, 20), 1, 1,
                                    residual=skip.to(dev).permute(0, 2, 3, 1).contiguous())
     assert _rel(got.permute(0, 3, 1, 2).float(), want) <= 4e-3
+
+
+@pytest.mark.parametrize('shape,relu,skip', [((4, 28, 28, 128), True, True), ((8, 7, 7, 512), True, False),
+                                             ((3, 10, 18, 64), False, False), ((2, 56, 56, 64), True, True)])
+def test_batch_norm_training_forward_and_backward(dev, shape, relu, skip):
+    """sdn_affine_act_nhwc + sdn_batch_norm_backward_nhwc against torch's BatchNorm2d (training) autograd in fp32 on the
+    same bf16-rounded z / residual / upstream gradient.  The ReLU mask is taken from the stored bf16 output, so elements
+    whose fp32 pre-activation is within bf16 rounding of 0 may differ: compared in rel-L2."""
+    import sdn_b200
+    N, H, W, C = shape
+    g_ = torch.Generator().manual_seed(C + H)
+    z = (torch.randn(N, C, H, W, generator=g_) * 1.5 + 0.3).bfloat16().float().to(dev).requires_grad_(True)
+    res = torch.randn(N, C, H, W, generator=g_).bfloat16().float().to(dev).requires_grad_(True) if skip else None
+    gamma = (1 + 0.2 * torch.randn(C, generator=g_)).to(dev).requires_grad_(True)
+    beta = (0.1 * torch.randn(C, generator=g_)).to(dev).requires_grad_(True)
+    go = torch.randn(N, C, H, W, generator=g_).bfloat16().float().to(dev)
+    y = F.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5)
+    if skip:
+        y = y + res
+    if relu:
+        y = torch.relu(y)
+    y.backward(go)
+
+    nh = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().bfloat16()
+    zz = z.detach()
+    mean = zz.mean(dim=(0, 2, 3))
+    rstd = torch.rsqrt(zz.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    scale = gamma.detach() * rstd
+    yn = sdn_b200.affine_act_nhwc(nh(z), scale, beta.detach() - mean * scale, nh(res) if skip else None, relu)
+    assert _rel(yn.float().permute(0, 3, 1, 2), y) <= 4e-3
+    gz, gg, gb, gs = sdn_b200.batch_norm_backward_nhwc(nh(go), yn if relu else None, nh(z), mean, rstd, gamma, relu, skip)
+    assert _rel(gz.float().permute(0, 3, 1, 2), z.grad) <= 1e-2, _rel(gz.float().permute(0, 3, 1, 2), z.grad)
+    assert _rel(gg, gamma.grad) <= 5e-3 and _rel(gb, beta.grad) <= 5e-3, (_rel(gg, gamma.grad), _rel(gb, beta.grad))
+    if skip:
+        assert _rel(gs.float().permute(0, 3, 1, 2), res.grad) <= 5e-3
+    else:
+        assert gs is None
