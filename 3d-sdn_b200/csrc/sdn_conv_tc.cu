@@ -718,6 +718,70 @@ __global__ void __launch_bounds__(256) k_affine_act(const __nv_bfloat16* __restr
     }
 }
 
+// Batch statistics -> everything the normalising pass and the backward need, in one launch of C threads: the convolution's
+// epilogue left per-(image, channel) sum / sum of squares in stats [N, C, 2]; out [4, C] = (mean, rstd, scale, shift) with
+// scale = gamma * rstd, shift = beta - mean * scale; running statistics updated in place as torch.nn.BatchNorm2d does
+// (momentum, unbiased variance).  The combination sum / count - mean^2 is taken in double.
+__global__ void __launch_bounds__(128) k_bn_finalize(const float* __restrict__ stats, int N, int C, double count, float eps,
+                                                     float momentum, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                     float* __restrict__ running_var, long long* __restrict__ batches,
+                                                     float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && batches) *batches += 1;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int n = 0; n < N; n++) {
+        s += (double)stats[((size_t)n * C + c) * 2];
+        ss += (double)stats[((size_t)n * C + c) * 2 + 1];
+    }
+    const double m = s / count;
+    double v = ss / count - m * m;
+    if (v < 0.0) v = 0.0;
+    const float mean = (float)m, var = (float)v;
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    out[c] = mean; out[C + c] = rstd; out[2 * C + c] = sc; out[3 * C + c] = beta[c] - mean * sc;
+    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
+    if (running_var) {
+        const float unbiased = (float)(v * (count / (count > 1.0 ? count - 1.0 : 1.0)));
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+// Weights for the data gradient: src fp32 [Co, KH, KW, Ci] (the physical layout of a channels-last Conv2d weight) ->
+// bf16 K-major operands of the transposed convolution, through a 32x32 shared-memory transpose (reads coalesced along Ci,
+// writes along Co).  mode 0 (stride 1): one tensor [Ci, KH, KW, Co] with the taps flipped.  mode 1 (3x3, stride 2): the
+// four output-parity phases (ph, pw) in the order (0,0) (0,1) (1,0) (1,1), each [Ci, Ta, Tb, Co] with taps {1} for parity
+// 0 and {2, 0} for parity 1, concatenated (sizes Ci * Co * {1, 2, 2, 4}).
+__global__ void __launch_bounds__(256) k_pack_weight_t(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int Ci,
+                                                       int KH, int KW, int mode) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z, kh = tap / KW, kw = tap % KW;
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int co = co0 + ty + 8 * k, ci = ci0 + tx;
+        tile[ty + 8 * k][tx] = (co < Co && ci < Ci) ? src[(((size_t)co * KH + kh) * KW + kw) * Ci + ci] : 0.0f;
+    }
+    __syncthreads();
+    size_t base = 0;
+    int Ta = KH, Tb = KW, a = KH - 1 - kh, b = KW - 1 - kw;
+    if (mode == 1) {
+        const int ph = kh == 1 ? 0 : 1, pw = kw == 1 ? 0 : 1;
+        Ta = ph ? 2 : 1; Tb = pw ? 2 : 1;
+        a = kh == 0 ? 1 : 0; b = kw == 0 ? 1 : 0;
+        const size_t unit = (size_t)Ci * Co;
+        base = (ph * 2 + pw == 0) ? 0 : (ph * 2 + pw == 1) ? unit : (ph * 2 + pw == 2) ? 3 * unit : 5 * unit;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ci = ci0 + ty + 8 * k, co = co0 + tx;
+        if (ci < Ci && co < Co)
+            dst[base + (((size_t)ci * Ta + a) * Tb + b) * Co + co] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
+    }
+}
+
 // Backward, pass 1: per channel  s1 = sum g^,  s2 = sum g^ * zhat,  g^ = gy * [y > 0] (when the unit ends in a ReLU),
 // zhat = (z - mean) * rstd.  Same block shape as k_inorm_stats (rows of one slab of channels, smem combine, one atomic
 // per channel per block).
@@ -1095,6 +1159,28 @@ extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* 
         sdn_internal::launch_begin("k_conv_wgrad", st);
         k_conv_wgrad<64><<<grid, NTHREADS, smem, st>>>(tmG, tmX, p);
     }
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_batch_norm_finalize(const float* stats, int N, int C, long long pixels, float eps, float momentum,
+                                       const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                       long long* num_batches, float* out, void* stream) {
+    if (!stats || !gamma || !beta || !out || N <= 0 || C <= 0 || pixels <= 0) return SDN_E_ARG;
+    sdn_internal::launch_begin("k_bn_finalize", (cudaStream_t)stream);
+    k_bn_finalize<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, N, C, (double)pixels, eps, momentum, gamma, beta,
+                                                                    running_mean, running_var, num_batches, out);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_pack_conv_weight_transposed(const float* weight, void* packed, int Cout, int Cin, int KH, int KW, int stride,
+                                               void* stream) {
+    if (!weight || !packed || Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0) return SDN_E_ARG;
+    int mode = 0;
+    if (stride == 2 && KH == 3 && KW == 3) mode = 1;
+    else if (stride != 1 && !(KH == 1 && KW == 1)) return SDN_E_ARG;
+    const dim3 grid((unsigned)((Cin + 31) / 32), (unsigned)((Cout + 31) / 32), (unsigned)(KH * KW));
+    sdn_internal::launch_begin("k_pack_weight_t", (cudaStream_t)stream);
+    k_pack_weight_t<<<grid, 256, 0, (cudaStream_t)stream>>>(weight, (__nv_bfloat16*)packed, Cout, Cin, KH, KW, mode);
     return sdn_internal::launch_end();
 }
 

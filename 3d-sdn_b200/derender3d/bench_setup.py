@@ -40,13 +40,15 @@ def template_meshes(faces=72576, real=True):
     return objs, '8 synthetic %d-triangle superellipsoids' % len(objs[0].faces)
 
 
-def train_setup(dev, B=16, S=384, faces=72576, seed=0, real=True, capturable=True):
+def train_setup(dev, B=16, S=384, faces=72576, seed=0, real=True, capturable=True, native_encoder=False):
     """-> dict(model, opt, batch, desc): Derenderer3d(mode full) in train mode, Adam(lr 1e-4, wd 1e-3), one synthetic
     VKITTI-shaped batch of B objects (images ~ N(0,1), ROIs, focals 725, random GT masks, ignores 0, targets full)."""
     torch.manual_seed(0)
     objs, desc = template_meshes(faces, real)
     model = Derenderer3d(TargetType.full, image_size=256, render_size=S, objs=objs).to(dev).train()
     model.derenderer.net = model.derenderer.net.to(memory_format=torch.channels_last)
+    # native_encoder: the ResNet-18 trunk's forward, dgrad, wgrad and BatchNorm on this repo's kernels instead of cuDNN
+    model.derenderer.tensor_core_trunk = bool(native_encoder)
     with torch.no_grad():       # a pose head that puts the objects in view (a real run starts from the pre-trained stage)
         model.derenderer._fc3.weight.mul_(0.01)
         model.derenderer._fc3.bias.zero_()
@@ -69,13 +71,13 @@ def train_setup(dev, B=16, S=384, faces=72576, seed=0, real=True, capturable=Tru
     return {'model': model, 'opt': opt, 'batch': batch, 'templates': desc, 'objs': objs}
 
 
-def measure_train(dev, world, rank, B=16, S=384, steps=10, graph=True, real=True, faces=72576):
+def measure_train(dev, world, rank, B=16, S=384, steps=10, graph=True, real=True, faces=72576, native_encoder=False):
     """Times `steps` training steps (CUDA events; max over ranks).  world > 1: one FlatGradSync all-reduce per step inside
     the timed region (config 4).  -> dict for the bench line (rank 0 fills it; the other ranks return None)."""
     import torch.distributed as dist
     from derender3d.train_step import GraphedTrainStep, geometric_losses
     from sdn_b200.dist import FlatGradSync
-    st = train_setup(dev, B, S, faces, seed=0, real=real)       # same data on every rank: the scaling line measures the
+    st = train_setup(dev, B, S, faces, seed=0, real=real, native_encoder=native_encoder)   # same data on every rank: the scaling line measures the
     model, opt, batch = st['model'], st['opt'], st['batch']      # machine, not the heaviest scene
     sync = FlatGradSync(model, bucket_views=True) if world > 1 else None
     amp = torch.bfloat16
@@ -150,8 +152,10 @@ def measure_train(dev, world, rank, B=16, S=384, steps=10, graph=True, real=True
     if rank != 0:
         return None
     nparam = sum(p.numel() for p in model.parameters())
-    out = {'workload': ('config4' if world > 1 else 'config3') + ': B=%d/GPU, encoder 224x224 bf16 autocast channels-last, %s, '
-                       'render %dx%d 2xSSAA, mode full, Adam' % (B, st['templates'], S, S),
+    out = {'workload': ('config4' if world > 1 else 'config3') + ': B=%d/GPU, encoder 224x224 %s, %s, '
+                       'render %dx%d 2xSSAA, mode full, Adam' % (
+                           B, 'trunk fwd/dgrad/wgrad/BatchNorm on the tcgen05 kernels + tcgen05 head (bf16)' if native_encoder
+                           else 'bf16 autocast channels-last (cuDNN)', st['templates'], S, S),
            'n_gpus': world, 'global_batch': B * world, 'ms_per_step': round(ms, 3),
            'objects_per_s': round(B * world / ms * 1e3, 1), 'launch': launch, 'loss': float(loss),
            'rank_ms': {'min': round(min(ranks_ms), 3), 'median': round(sorted(ranks_ms)[len(ranks_ms) // 2], 3),

@@ -75,21 +75,9 @@ class ResNet18TC(object):
 # ----------------------------------------------------------------------------------------------------------------------
 def _bn_train(z, stats, bn, relu, residual=None):
     """BatchNorm2d (training) of a convolution result z [N,H,W,C] bf16 whose per-(image, channel) sums the convolution's
-    epilogue left in `stats` [N,C,2]: batch mean / biased variance, running-statistics update (momentum, unbiased variance,
-    as torch.nn.BatchNorm2d does), y = relu?(z * scale + shift (+ residual)).  -> (y, mean [C], rstd [C])."""
-    M = z.numel() // z.shape[-1]
-    tot = stats.sum(dim=0)                                  # [C, 2]
-    mean = tot[:, 0] / M
-    var = (tot[:, 1] / M - mean * mean).clamp_min(0.0)
-    rstd = torch.rsqrt(var + bn.eps)
-    if bn.track_running_stats and bn.running_mean is not None:
-        with torch.no_grad():
-            m = bn.momentum if bn.momentum is not None else 0.1
-            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(var * (M / max(M - 1, 1)), alpha=m)
-            bn.num_batches_tracked.add_(1)
-    scale = bn.weight.detach().float() * rstd
-    shift = bn.bias.detach().float() - mean * scale
+    epilogue left in `stats` [N,C,2]: batch mean / biased variance and the running-statistics update in one launch
+    (sdn_batch_norm_finalize), then y = relu?(z * scale + shift (+ residual)).  -> (y, mean [C], rstd [C])."""
+    mean, rstd, scale, shift = sdn_b200.batch_norm_finalize(stats, z.numel() // z.shape[-1], bn)
     return sdn_b200.affine_act_nhwc(z, scale, shift, residual, relu), mean, rstd
 
 

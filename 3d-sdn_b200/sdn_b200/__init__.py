@@ -93,6 +93,9 @@ def lib():
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_conv2d_wgrad.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_affine_act_nhwc.argtypes = [vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
+        L.sdn_batch_norm_finalize.argtypes = [vp, ci, ci, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp,
+                                              vp, vp]
+        L.sdn_pack_conv_weight_transposed.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
         L.sdn_batch_norm_backward_nhwc.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
         L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_reflect_pad_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
@@ -389,6 +392,8 @@ def pack_conv_weight(weight, cin_pad=None, cout_pad=None):
     co, ci, kh, kw = weight.shape
     cin_pad = cin_pad or (ci + 63) // 64 * 64
     cout_pad = cout_pad or (16 if co <= 16 else (co + 63) // 64 * 64)
+    if cin_pad == ci and cout_pad == co:        # nothing to pad: one cast (a channels-last weight is already [Cout,KH,KW,Cin])
+        return weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
     w = torch.zeros(cout_pad, kh, kw, cin_pad, device=weight.device, dtype=torch.bfloat16)
     w[:co, :, :, :ci] = weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16)
     return w.contiguous()
@@ -464,6 +469,46 @@ def conv2d_wgrad_tc(grad_out, x, KH, KW, stride=1, pad=0):
     return gw
 
 
+def pack_conv_weight_transposed(weight, stride=1):
+    """Operands of the data gradient from a Conv2d weight [Cout, Cin, KH, KW] fp32 (sdn_pack_conv_weight_transposed: one
+    launch, shared-memory transpose).  stride 1 / 1x1 -> [packed [Cin,KH,KW,Cout] bf16, taps flipped]; stride 2, 3x3 ->
+    the four parity-phase operands [(0,0), (0,1), (1,0), (1,1)], views of one buffer."""
+    _need_cuda(weight)
+    co, ci, kh, kw = weight.shape
+    if ci % 64 or co % 64:
+        raise SdnError('pack_conv_weight_transposed: channels must be multiples of 64')
+    src = weight.detach().float().contiguous(memory_format=torch.channels_last)    # physical [Cout, KH, KW, Cin]
+    buf = torch.empty(ci * kh * kw * co, device=weight.device, dtype=torch.bfloat16)
+    with torch.cuda.device(weight.device):
+        _check(lib().sdn_pack_conv_weight_transposed(_ptr(src), _ptr(buf), co, ci, kh, kw, int(stride), _stream()))
+    if stride == 2 and kh == 3:
+        unit, out, off = ci * co, [], 0
+        for ta, tb in ((1, 1), (1, 2), (2, 1), (2, 2)):
+            out.append(buf[off:off + unit * ta * tb].view(ci, ta, tb, co))
+            off += unit * ta * tb
+        return out
+    return [buf.view(ci, kh, kw, co)]
+
+
+def batch_norm_finalize(stats, pixels, bn):
+    """Batch statistics [N,C,2] (from conv2d_tc(stats=...)) -> (mean, rstd, scale, shift) fp32 [C] each, and the running
+    statistics / num_batches_tracked of the torch.nn.BatchNorm2d `bn` updated in place (sdn_batch_norm_finalize)."""
+    _need_cuda(stats)
+    N, C, _ = stats.shape
+    out = torch.empty(4, C, device=stats.device, dtype=torch.float32)
+    track = bn.track_running_stats and bn.running_mean is not None
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    gamma, beta = bn.weight.detach(), bn.bias.detach()
+    if gamma.dtype != torch.float32 or not gamma.is_contiguous() or beta.dtype != torch.float32:
+        raise SdnError('batch_norm_finalize: fp32 contiguous BatchNorm parameters expected')
+    with torch.cuda.device(stats.device):
+        _check(lib().sdn_batch_norm_finalize(_ptr(stats.contiguous()), N, C, int(pixels), float(bn.eps), mom, _ptr(gamma),
+                                             _ptr(beta), _ptr(bn.running_mean) if track else None,
+                                             _ptr(bn.running_var) if track else None,
+                                             _ptr(bn.num_batches_tracked) if track else None, _ptr(out), _stream()))
+    return out[0], out[1], out[2], out[3]
+
+
 def conv2d_dgrad_tc(grad_out, weight, in_hw, stride=1, pad=0, residual=None):
     """Data gradient of a convolution with `weight` [Cout, Cin, KH, KW] (fp32 / bf16 torch layout): grad_out
     [N,Ho,Wo,Cout] bf16 -> [N,H,W,Cin] bf16, on the SAME tcgen05 kernel as the forward: stride 1 = a convolution with the
@@ -474,23 +519,19 @@ def conv2d_dgrad_tc(grad_out, weight, in_hw, stride=1, pad=0, residual=None):
     H, W = in_hw
     N = grad_out.shape[0]
     if stride == 1:
-        wt = pack_conv_weight(weight.detach().flip(2, 3).transpose(0, 1))
+        wt, = pack_conv_weight_transposed(weight, 1)
         return conv2d_tc(grad_out, wt, 1, KH - 1 - pad, None, None, residual, False, out_hw=(H, W))
     if stride != 2 or H % 2 or W % 2:
         raise SdnError('conv2d_dgrad_tc: stride %d with input %dx%d is not supported' % (stride, H, W))
     out = torch.empty(N, H, W, Cin, device=grad_out.device, dtype=torch.bfloat16)
-    wT = weight.detach().transpose(0, 1)                    # [Cin(out of the transposed conv), Cout(in), KH, KW]
     if KH == 3 and pad == 1:
-        taps = {0: [1], 1: [2, 0]}
-        for ph in (0, 1):
-            for pw in (0, 1):
-                wk = wT[:, :, taps[ph], :][:, :, :, taps[pw]]
-                conv2d_tc(grad_out, pack_conv_weight(wk.contiguous()), 1, 0, None, None, None, False,
-                          out_hw=(H // 2, W // 2), out=out[:, ph::2, pw::2])
+        ops = pack_conv_weight_transposed(weight, 2)
+        for k, (ph, pw) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+            conv2d_tc(grad_out, ops[k], 1, 0, None, None, None, False, out_hw=(H // 2, W // 2), out=out[:, ph::2, pw::2])
     elif KH == 1 and pad == 0:
         out.zero_()
-        conv2d_tc(grad_out, pack_conv_weight(wT.contiguous()), 1, 0, None, None, None, False, out_hw=(H // 2, W // 2),
-                  out=out[:, 0::2, 0::2])
+        wt, = pack_conv_weight_transposed(weight, 2)
+        conv2d_tc(grad_out, wt, 1, 0, None, None, None, False, out_hw=(H // 2, W // 2), out=out[:, 0::2, 0::2])
     else:
         raise SdnError('conv2d_dgrad_tc: stride-2 kernel %dx%d pad %d is not supported' % (KH, KW, pad))
     if residual is not None:

@@ -458,6 +458,12 @@ def other_configs(renderer, dev, world, rank, fast, args):
     del vc, fc, gc, rc
     torch.cuda.empty_cache()
     out['config3'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph)
+    try:        # the same step with the encoder trunk trained on this repo's kernels (forward, dgrad, wgrad, BatchNorm)
+        out['config3_native_encoder'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph,
+                                                      native_encoder=True)
+    except Exception as e:      # noqa: BLE001
+        out['config3_native_encoder'] = {'failed': repr(e)[:200]}
+        torch.cuda.synchronize()
     return out
 
 

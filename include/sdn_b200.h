@@ -220,6 +220,20 @@ int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, const void* 
                                  const float* gamma, float* sums, void* grad_z, void* grad_skip, long long pixels, int C,
                                  int relu, void* stream);
 
+/* Batch statistics of a convolution result (sdn_conv2d.stats, fp32 [N, C, 2] = per-image sum / sum of squares) -> out
+ * fp32 [4, C] = (mean, rstd, scale = gamma * rstd, shift = beta - mean * scale); running_mean / running_var (optional)
+ * are updated in place with `momentum` and the unbiased variance, *num_batches (optional) is incremented: what
+ * torch.nn.BatchNorm2d does in training mode (reference: torchvision resnet18 inside derenderer.py:25-27). */
+int sdn_batch_norm_finalize(const float* stats, int N, int C, long long pixels, float eps, float momentum, const float* gamma,
+                            const float* beta, float* running_mean, float* running_var, long long* num_batches, float* out,
+                            void* stream);
+
+/* Operand of the data gradient: weight fp32 [Cout, KH, KW, Cin] (physical layout of a channels-last Conv2d weight) ->
+ * bf16.  stride 1 (or 1x1): [Cin, KH, KW, Cout] with flipped taps.  stride 2, 3x3: the four output-parity phases
+ * (0,0) (0,1) (1,0) (1,1) concatenated, each [Cin, Ta, Tb, Cout] (taps {1} for parity 0, {2, 0} for parity 1). */
+int sdn_pack_conv_weight_transposed(const float* weight, void* packed, int Cout, int Cin, int KH, int KW, int stride,
+                                    void* stream);
+
 /* im2col for inputs with few channels (the 7x7 stem, Cin = 3): output [N, Ho, Wo, Kpad] bf16 with
  * output[.., (kh*KW + kw)*Cin + ci] = input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci] (0 outside and beyond
  * KH*KW*Cin); the stem then runs through sdn_conv2d_forward as a 1x1 convolution over Kpad channels. */

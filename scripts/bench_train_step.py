@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--synthetic', action='store_true', help='synthetic templates even when the real OBJ files are present')
     ap.add_argument('--encoder-only', action='store_true')
     ap.add_argument('--graph', action='store_true', help='capture the whole step in a CUDA graph (GraphedTrainStep)')
+    ap.add_argument('--native-encoder', action='store_true', help='encoder trunk trained on the tcgen05 kernels')
     ap.add_argument('--profile', action='store_true', help='torch.profiler table of one step (kernel time vs wall)')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -41,7 +42,8 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     from derender3d.bench_setup import train_setup
     B, S = args.batch, args.render_size
-    st = train_setup(dev, B, S, args.faces, seed=rank, real=not args.synthetic, capturable=bool(args.graph))
+    st = train_setup(dev, B, S, args.faces, seed=rank, real=not args.synthetic, capturable=bool(args.graph),
+                     native_encoder=args.native_encoder)
     model, opt, batch, objs = st['model'], st['opt'], st['batch'], st['objs']
     roi = batch['roi_norms']
     sync = None

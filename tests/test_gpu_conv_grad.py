@@ -92,3 +92,47 @@ def test_batch_norm_training_forward_and_backward(dev, shape, relu, skip):
         assert _rel(gs.float().permute(0, 3, 1, 2), res.grad) <= 5e-3
     else:
         assert gs is None
+
+
+def test_batch_norm_finalize_updates_running_statistics_like_torch(dev):
+    """sdn_batch_norm_finalize: batch mean / rstd / scale / shift and the in-place running statistics against
+    torch.nn.BatchNorm2d in training mode fed the same (bf16-rounded) convolution result."""
+    import sdn_b200
+    g_ = torch.Generator().manual_seed(11)
+    N, H, W, C = 6, 14, 14, 256
+    z = (torch.randn(N, C, H, W, generator=g_) * 2 + 0.5).bfloat16().float().to(dev)
+    bn = torch.nn.BatchNorm2d(C).to(dev).train()
+    mine = torch.nn.BatchNorm2d(C).to(dev).train()
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.1 * torch.randn(C, generator=g_)); bn.bias.copy_(0.1 * torch.randn(C, generator=g_))
+        bn.running_mean.copy_(torch.randn(C, generator=g_)); bn.running_var.copy_(1 + torch.rand(C, generator=g_))
+    mine.load_state_dict(bn.state_dict())
+    y = bn(z)
+    stats = torch.stack([z.sum(dim=(2, 3)), (z * z).sum(dim=(2, 3))], dim=2).contiguous()      # [N, C, 2]
+    mean, rstd, scale, shift = sdn_b200.batch_norm_finalize(stats, N * H * W, mine)
+    assert _rel(mean, z.mean(dim=(0, 2, 3))) <= 1e-5
+    assert _rel(rstd, torch.rsqrt(z.var(dim=(0, 2, 3), unbiased=False) + bn.eps)) <= 1e-5
+    assert _rel(z * scale[None, :, None, None] + shift[None, :, None, None], y) <= 1e-5
+    assert _rel(mine.running_mean, bn.running_mean) <= 1e-6 and _rel(mine.running_var, bn.running_var) <= 1e-5
+    assert int(mine.num_batches_tracked) == int(bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize('co,ci,k,stride,chlast', [(128, 64, 3, 1, True), (64, 192, 3, 1, False), (128, 64, 3, 2, True),
+                                                   (512, 256, 1, 2, False), (64, 64, 1, 1, True)])
+def test_transposed_weight_operands(dev, co, ci, k, stride, chlast):
+    """sdn_pack_conv_weight_transposed against the torch expression of the same operand (bit-exact: one bf16 rounding)."""
+    import sdn_b200
+    w = torch.randn(co, ci, k, k, generator=torch.Generator().manual_seed(co + ci)).to(dev)
+    if chlast:
+        w = w.contiguous(memory_format=torch.channels_last)
+    ops = sdn_b200.pack_conv_weight_transposed(w, stride)
+    wT = w.transpose(0, 1)                                  # [Cin, Cout, KH, KW]
+    if stride == 2 and k == 3:
+        taps = {0: [1], 1: [2, 0]}
+        want = [wT[:, :, taps[ph], :][:, :, :, taps[pw]].permute(0, 2, 3, 1).bfloat16()
+                for ph, pw in ((0, 0), (0, 1), (1, 0), (1, 1))]
+    else:
+        want = [wT.flip(2, 3).permute(0, 2, 3, 1).bfloat16()]
+    assert len(ops) == len(want)
+    for a, b in zip(ops, want):
+        assert a.shape == b.shape and a.is_contiguous() and torch.equal(a, b)
