@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_wgrad(const __grid_constant__
     constexpr int A_B = 2 * 8192, B_B = (TNW / 64) * 8192, STAGE_BYTES = A_B + B_B;
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full[2], s_tmem_empty[2];
     __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_tr[4][32][36];          // per epilogue warp: 32 x 32 transpose, rows padded to 144 B
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cobs = (p.Cout + 127) / 128, cibs = (p.Cin + TNW - 1) / TNW, taps = p.KH * p.KW;
     const int total_work = cobs * cibs * taps * p.splits;
@@ -502,7 +503,6 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_wgrad(const __grid_constant__
             int split, tap, cib, cob;
             decode(w, split, tap, cib, cob);
             const int ab = it & 1;
-            const int co = cob * 128 + q * 32 + lane;
             mbar_wait(&s_tmem_full[ab], (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem + (uint32_t)ab * TNW;
@@ -521,13 +521,28 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_wgrad(const __grid_constant__
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int ci = cib * TNW + c0;
-                if (!empty && co < p.Cout && ci < p.Cin) {
-                    float* o = p.dw + ((size_t)co * taps + tap) * p.Cin + ci;
+                // lane = output channel (row): transpose the 32 x 32 block through shared memory so that a warp instruction
+                // covers four rows of 128 contiguous bytes (16-byte vector reductions / stores instead of 32 scattered words)
+                float* tr = s_tr[q][lane];
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (ci + j < p.Cin) atomicAdd(o + j, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(tr + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+                const int ci = cib * TNW + c0 + 4 * (lane & 7);
+                if (!empty && ci < p.Cin) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; rr++) {
+                        const int r = rr * 4 + (lane >> 3), co = cob * 128 + q * 32 + r;
+                        if (co >= p.Cout) continue;
+                        const float4 val = *reinterpret_cast<const float4*>(&s_tr[q][r][4 * (lane & 7)]);
+                        float* o = p.dw + ((size_t)co * taps + tap) * p.Cin + ci;
+                        if (p.splits == 1) *reinterpret_cast<float4*>(o) = val;
+                        else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                          ::"l"(o), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+                    }
                 }
+                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -788,39 +803,56 @@ __global__ void __launch_bounds__(256) k_pack_weight_t(const float* __restrict__
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
                                                        const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, float* __restrict__ sums, long M, int C,
-                                                       int rows, int pairs, int relu) {
-    __shared__ float s_part[256 * 4];
-    const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs, nrl = 256 / pairs;
-    const int c = (blockIdx.y * pairs + cp) * 2;
+                                                       int rows, int groups, int relu) {
+    // a thread owns 8 consecutive channels (16-byte loads) of every nrl-th row of the block's row range; `groups` = 8-channel
+    // groups per slab (blockIdx.y), a divisor of 256
+    __shared__ float s_part[256 * 17];
+    const int gl = threadIdx.x % groups, rl = threadIdx.x / groups, nrl = 256 / groups;
+    const int c = (blockIdx.y * groups + gl) * 8;
     const long r0 = (long)blockIdx.x * rows, r1 = r0 + rows < M ? r0 + rows : M;
-    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
-    if (c < C && rl < nrl) {
-        const float m0 = mean[c], m1 = mean[c + 1], i0 = rstd[c], i1 = rstd[c + 1];
-#pragma unroll 4
+    float a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a[k] = 0.0f; b[k] = 0.0f; }
+    if (c < C) {
+        float m[8], iv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { m[k] = mean[c + k]; iv[k] = rstd[c + k]; }
+#pragma unroll 2
         for (long r = r0 + rl; r < r1; r += nrl) {
             const size_t e = (size_t)r * C + c;
-            const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(gy + e);
-            const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(z + e);
-            float g0 = __low2float(g2), g1 = __high2float(g2);
-            if (relu) {
-                const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(y + e);
-                if (!(__low2float(y2) > 0.0f)) g0 = 0.0f;
-                if (!(__high2float(y2) > 0.0f)) g1 = 0.0f;
+            const uint4 gv = *reinterpret_cast<const uint4*>(gy + e);
+            const uint4 zv = *reinterpret_cast<const uint4*>(z + e);
+            uint4 yv = make_uint4(0, 0, 0, 0);
+            if (relu) yv = *reinterpret_cast<const uint4*>(y + e);
+            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, zw[4] = {zv.x, zv.y, zv.z, zv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(&gw[k]);
+                const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&zw[k]);
+                float g0 = __low2float(g2), g1 = __high2float(g2);
+                if (relu) {
+                    const __nv_bfloat162 y2 = *reinterpret_cast<const __nv_bfloat162*>(&yw[k]);
+                    if (!(__low2float(y2) > 0.0f)) g0 = 0.0f;
+                    if (!(__high2float(y2) > 0.0f)) g1 = 0.0f;
+                }
+                a[2 * k] += g0; a[2 * k + 1] += g1;
+                b[2 * k] = __fmaf_rn(g0, (__low2float(z2) - m[2 * k]) * iv[2 * k], b[2 * k]);
+                b[2 * k + 1] = __fmaf_rn(g1, (__high2float(z2) - m[2 * k + 1]) * iv[2 * k + 1], b[2 * k + 1]);
             }
-            a0 += g0; a1 += g1;
-            b0 = __fmaf_rn(g0, (__low2float(z2) - m0) * i0, b0);
-            b1 = __fmaf_rn(g1, (__high2float(z2) - m1) * i1, b1);
         }
     }
-    s_part[threadIdx.x * 4] = a0; s_part[threadIdx.x * 4 + 1] = b0; s_part[threadIdx.x * 4 + 2] = a1; s_part[threadIdx.x * 4 + 3] = b1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s_part[threadIdx.x * 17 + 2 * k] = a[k]; s_part[threadIdx.x * 17 + 2 * k + 1] = b[k]; }
     __syncthreads();
-    if (rl == 0 && c < C) {
-        for (int k = 1; k < nrl; k++) {
-            const float* o = s_part + (k * pairs + cp) * 4;
-            a0 += o[0]; b0 += o[1]; a1 += o[2]; b1 += o[3];
+    // 16 values per group of 8 channels: thread t < groups * 16 adds the nrl partials of one value
+    if (threadIdx.x < groups * 16) {
+        const int g = threadIdx.x >> 4, k = threadIdx.x & 15;
+        const int cc = (blockIdx.y * groups + g) * 8;
+        if (cc < C) {
+            float t = 0.0f;
+            for (int j = 0; j < nrl; j++) t += s_part[(j * groups + g) * 17 + k];
+            atomicAdd(sums + (size_t)cc * 2 + k, t);            // (channel cc + k/2, {sum, sum * zhat}[k & 1])
         }
-        float* o = sums + (size_t)c * 2;
-        atomicAdd(o, a0); atomicAdd(o + 1, b0); atomicAdd(o + 2, a1); atomicAdd(o + 3, b1);
     }
 }
 
@@ -964,7 +996,14 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         }
     }
 
-    const int TN = c->Cout == 16 ? 16 : ((c->Cout % 128 == 0) ? 128 : 64);
+    int TN = c->Cout == 16 ? 16 : ((c->Cout % 128 == 0) ? 128 : 64);
+    {   // few output pixels (ResNet layer3 / layer4 at small batch): 128-wide N tiles would occupy less than half of the SMs;
+        // 64-wide ones double the CTAs (the A tile is re-read from L2 by twice as many CTAs, which is cheaper than idle SMs)
+        int dev_ = 0, sms_ = 148;
+        if (cudaGetDevice(&dev_) == cudaSuccess) cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
+        static const bool no_narrow = getenv("SDN_CONV_NO_NARROW") != nullptr;
+        if (TN == 128 && !no_narrow && (long)p.tiles_w * p.tiles_h * p.tiles_n * (c->Cout / 128) * 2 <= sms_) TN = 64;
+    }
     alignas(64) CUtensorMap tmA, tmB;
     {   // activations: dims (fastest first) {C, W, H, N}
         const cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
@@ -1106,8 +1145,7 @@ extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* 
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return (int)cudaErrorNotSupported;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(grad_weight, 0, sizeof(float) * (size_t)Cout * KH * KW * Cin, st);
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t e = cudaSuccess;
 
     WgradParams p;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
@@ -1120,11 +1158,24 @@ extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* 
     const int base_items = ((Cout + 127) / 128) * ((Cin + TNW - 1) / TNW) * KH * KW;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int splits = (3 * sms + base_items - 1) / base_items;           // ~3 work items per SM
-    if (splits < 1) splits = 1;
-    if (splits > patches) splits = patches;
-    p.patches_per_split = (patches + splits - 1) / splits;
-    p.splits = (patches + p.patches_per_split - 1) / p.patches_per_split;     // no empty split
+    // how many pixel ranges: minimise  waves * (K blocks per item + epilogue), the epilogue (128 x TNW fp32 through L2, atomics
+    // when there is more than one range) costing about as much as 4 K blocks; one range = plain stores, no clearing pass
+    {
+        long best_cost = -1; int best = 1;
+        for (int sp = 1; sp <= patches && sp <= 256; sp++) {
+            const int pps = (patches + sp - 1) / sp, real = (patches + pps - 1) / pps;
+            if (real != sp) continue;
+            const long waves = ((long)base_items * sp + sms - 1) / sms;
+            const long cost = waves * (pps + (sp == 1 ? 3 : 4));
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sp; }
+        }
+        p.splits = best;
+        p.patches_per_split = (patches + best - 1) / best;
+    }
+    if (p.splits > 1) {
+        e = cudaMemsetAsync(grad_weight, 0, sizeof(float) * (size_t)Cout * KH * KW * Cin, st);
+        if (e != cudaSuccess) return (int)e;
+    }
 
     alignas(64) CUtensorMap tmG, tmX;
     {
@@ -1146,7 +1197,7 @@ extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* 
             return SDN_E_ARG;
     }
     const long total_work = (long)base_items * p.splits;
-    const size_t smem = (size_t)6 * (16384 + (TNW / 64) * 8192) + 1024;
+    const size_t smem = (size_t)6 * (16384 + (TNW / 64) * 8192) + 1024;     // + 18.6 KB static (barriers, transpose)
     const dim3 grid((unsigned)(total_work < sms ? total_work : sms), 1);
     if (TNW == 128) {
         e = cudaFuncSetAttribute(k_conv_wgrad<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1203,17 +1254,17 @@ extern "C" int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, c
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)C, st);
     if (e != cudaSuccess) return (int)e;
-    int pairs = C / 2;
-    if (pairs > 256) pairs = 256;
-    while (256 % pairs) pairs--;
-    const int slabs = (C / 2 + pairs - 1) / pairs, nrl = 256 / pairs;
-    long want = ((long)pixels * slabs + 148L * 8 - 1) / (148L * 8);
-    int rows = (int)(want < 32L * nrl ? 32L * nrl : (want > 8192 ? 8192 : want));
+    int grp = C / 8;                                    // 8-channel groups per block: a divisor of 256, at most 16
+    if (grp > 16) grp = 16;
+    while (256 % grp || (C / 8) % grp) grp--;
+    const int slabs = (C / 8) / grp, nrl = 256 / grp;
+    long want = ((long)pixels * slabs + 148L * 4 - 1) / (148L * 4);        // ~4 blocks per SM
+    int rows = (int)(want < 4L * nrl ? 4L * nrl : (want > 16384 ? 16384 : want));
     rows = (rows + nrl - 1) / nrl * nrl;
     sdn_internal::launch_begin("k_bn_bwd_reduce", st);
     k_bn_bwd_reduce<<<dim3((unsigned)((pixels + rows - 1) / rows), (unsigned)slabs), 256, 0, st>>>(
         (const __nv_bfloat16*)grad_y, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, rstd, sums, (long)pixels, C, rows,
-        pairs, relu);
+        grp, relu);
     int rc = sdn_internal::launch_end();
     if (rc) return rc;
     const long groups = (long)pixels * (C / 8);
