@@ -586,6 +586,50 @@ __global__ void __launch_bounds__(256) k_im2col_nhwc(const __nv_bfloat16* __rest
     }
 }
 
+// The same, one block per output row (n, ho): the KH input rows it reads are staged in shared memory once (for the 7x7 /
+// stride-2 stem every input element is used ~12 times), then 16-byte stores.  Used when the rows fit in 48 KB.
+__global__ void __launch_bounds__(256) k_im2col_rows(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                     int H, int W, int Cin, int Ho, int Wo, int KH, int KW, int stride, int pad,
+                                                     int Kpad) {
+    extern __shared__ __align__(16) unsigned char s_rows_raw[];
+    __nv_bfloat16* s_rows = reinterpret_cast<__nv_bfloat16*>(s_rows_raw);
+    const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
+    const int rowlen = W * Cin;                                  // elements per input row
+    for (int kh = 0; kh < KH; kh++) {
+        const int hi = ho * stride + kh - pad;
+        __nv_bfloat16* dst = s_rows + (size_t)kh * rowlen;
+        if (hi < 0 || hi >= H) continue;                         // never read: the gather below tests hi again
+        const __nv_bfloat16* src = in + ((size_t)n * H + hi) * rowlen;
+        if ((rowlen & 7) == 0) {
+            for (int i = threadIdx.x; i < (rowlen >> 3); i += 256)
+                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+        } else {
+            for (int i = threadIdx.x; i < rowlen; i += 256) dst[i] = src[i];
+        }
+    }
+    __syncthreads();
+    const int groups = Kpad >> 3, KWC = KW * Cin, K = KH * KWC;
+    __nv_bfloat16* orow = out + (size_t)blockIdx.x * Wo * Kpad;
+    const __nv_bfloat16 zero = __float2bfloat16(0.0f);
+    for (int i = threadIdx.x; i < Wo * groups; i += 256) {
+        const int wo = i / groups, g = i - wo * groups;
+        int k = g * 8, kh = k / KWC, j = k - kh * KWC;
+        const int base = (wo * stride - pad) * Cin;              // element index in the row of (kw = 0, c = 0)
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++, k++) {
+            __nv_bfloat16 x = zero;
+            if (k < K) {
+                const int hi = ho * stride + kh - pad, idx = base + j;
+                if (hi >= 0 && hi < H && idx >= 0 && idx < rowlen) x = s_rows[kh * rowlen + idx];
+            }
+            v[e] = x;
+            if (++j == KWC) { j = 0; kh++; }
+        }
+        *reinterpret_cast<uint4*>(orow + (size_t)i * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 // ---- instance normalisation of an NHWC bf16 tensor (textural/models/networks.py:23-29: InstanceNorm2d, affine=False) ----
 // stats: per (n, c) sum and sum of squares over H*W in fp32.  A block of 256 threads covers `rows` pixels of one image
 // and a slab of up to 512 channels: thread t owns channel pair t % (slab/2) and walks rows t / (slab/2), += 256/(slab/2)
@@ -1066,6 +1110,13 @@ extern "C" int sdn_im2col_nhwc(const void* input, void* output, int N, int H, in
     if (Kpad & 7) return SDN_E_ARG;
     const long total = (long)N * Ho * Wo * (Kpad / 8);
     const unsigned blocks = (unsigned)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    const size_t row_bytes = (size_t)KH * W * Cin * 2;
+    if (row_bytes <= 48 * 1024 && Wo * (Kpad >> 3) >= 256) {
+        sdn_internal::launch_begin("k_im2col_rows", (cudaStream_t)stream);
+        k_im2col_rows<<<(unsigned)(N * Ho), 256, row_bytes, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)input, (__nv_bfloat16*)output, H, W, Cin, Ho, Wo, KH, KW, stride, pad, Kpad);
+        return sdn_internal::launch_end();
+    }
     sdn_internal::launch_begin("k_im2col_nhwc", (cudaStream_t)stream);
     k_im2col_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)input, (__nv_bfloat16*)output, N, H, W, Cin,
                                                             Ho, Wo, KH, KW, stride, pad, Kpad);
@@ -1249,11 +1300,15 @@ extern "C" int sdn_affine_act_nhwc(const void* z, const float* scale, const floa
 extern "C" int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, const void* z, const float* mean, const float* rstd,
                                             const float* gamma, float* sums, void* grad_z, void* grad_skip, long long pixels,
                                             int C, int relu, void* stream) {
-    if (!grad_y || !z || !mean || !rstd || !gamma || !sums || !grad_z || pixels <= 0 || C <= 0 || (C & 7) || (relu && !y))
+    if (!grad_y || !z || !mean || !rstd || !gamma || !sums || !grad_z || pixels <= 0 || C <= 0 || (C & 7) || ((relu & 1) && !y))
         return SDN_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)C, st);
-    if (e != cudaSuccess) return (int)e;
+    const bool precleared = (relu & 2) != 0;             // bit 1: the caller cleared `sums` (one clearing pass for many layers)
+    relu &= 1;
+    if (!precleared) {
+        cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)C, st);
+        if (e != cudaSuccess) return (int)e;
+    }
     int grp = C / 8;                                    // 8-channel groups per block: a divisor of 256, at most 16
     if (grp > 16) grp = 16;
     while (256 % grp || (C / 8) % grp) grp--;

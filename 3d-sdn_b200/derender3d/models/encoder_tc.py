@@ -93,6 +93,10 @@ class _TrunkTrainFunction(torch.autograd.Function):
         N = x.shape[0]
         dev = x.device
         saved = {}
+        convs = [m for m in net.modules() if isinstance(m, torch.nn.Conv2d)]
+        chans = sum(c.out_channels for c in convs)
+        stats_all = torch.zeros(N * chans * 2, device=dev, dtype=torch.float32)     # one clearing pass for all layers
+        cursor = [0]
 
         def conv_bn(xin, conv, bn, relu, residual=None, stem=False):
             if stem:
@@ -106,8 +110,10 @@ class _TrunkTrainFunction(torch.autograd.Function):
             else:
                 w = sdn_b200.pack_conv_weight(conv.weight)
                 stride, pad = int(conv.stride[0]), int(conv.padding[0])
-            stats = torch.empty(N, conv.out_channels, 2, device=dev, dtype=torch.float32)
-            z = sdn_b200.conv2d_tc(xin, w, stride, pad, stats=stats)
+            n_st = N * conv.out_channels * 2
+            stats = stats_all[cursor[0]:cursor[0] + n_st].view(N, conv.out_channels, 2)
+            cursor[0] += n_st
+            z = sdn_b200.conv2d_tc(xin, w, stride, pad, stats=stats, stats_keep=True)
             y, mean, rstd = _bn_train(z, stats, bn, relu, residual)
             return xin, z, y, mean, rstd
 
@@ -135,6 +141,7 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 x = out
         feat = x.float().mean(dim=(1, 2))
         ctx.net, ctx.units, ctx.blocks, ctx.saved, ctx.last_shape = net, units, blocks, saved, x.shape
+        ctx.chans = chans
         ctx.param_ids = [id(p) for p in params]
         return feat
 
@@ -143,11 +150,16 @@ class _TrunkTrainFunction(torch.autograd.Function):
         net = ctx.net
         grads = {}
         N, H, W, C = ctx.last_shape
+        sums_all = torch.zeros(ctx.chans * 2, device=g_feat.device, dtype=torch.float32)     # (grad_beta, grad_gamma) of all layers
+        cursor = [0]
         g = (g_feat.detach().float() / (H * W)).to(torch.bfloat16)[:, None, None, :].expand(N, H, W, C).contiguous()
 
         def bn_conv_backward(gy, y, z, mean, rstd, conv, bn, relu, xin, want_skip=False, need_dx=True, skip_add=None, stem=False):
+            nc = z.shape[-1]
+            sums = sums_all[cursor[0]:cursor[0] + 2 * nc].view(nc, 2)
+            cursor[0] += 2 * nc
             gz, g_gamma, g_beta, g_skip = sdn_b200.batch_norm_backward_nhwc(gy, y if relu else None, z, mean, rstd, bn.weight, relu,
-                                                                              want_skip)
+                                                                              want_skip, sums=sums)
             grads[id(bn.weight)], grads[id(bn.bias)] = g_gamma, g_beta
             if stem:
                 k = int(conv.kernel_size[0])

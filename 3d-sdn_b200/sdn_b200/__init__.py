@@ -554,20 +554,25 @@ def affine_act_nhwc(z, scale, shift, residual=None, relu=False):
     return y
 
 
-def batch_norm_backward_nhwc(grad_y, y, z, mean, rstd, gamma, relu, want_skip=False):
-    """-> (grad_z bf16, grad_gamma [C], grad_beta [C], grad_skip bf16 | None); see include/sdn_b200.h."""
+def batch_norm_backward_nhwc(grad_y, y, z, mean, rstd, gamma, relu, want_skip=False, sums=None):
+    """-> (grad_z bf16, grad_gamma [C], grad_beta [C], grad_skip bf16 | None); see include/sdn_b200.h.
+    sums: an already CLEARED fp32 [C, 2] buffer to accumulate into (saves the per-call clearing pass)."""
     _need_cuda(grad_y, y, z, mean, rstd, gamma)
     grad_y, z = grad_y.contiguous(), z.contiguous()
     y = None if y is None else y.contiguous()
     C = z.shape[-1]
-    sums = torch.empty(C, 2, device=z.device, dtype=torch.float32)
+    precleared = sums is not None
+    if sums is None:
+        sums = torch.empty(C, 2, device=z.device, dtype=torch.float32)
+    elif tuple(sums.shape) != (C, 2) or sums.dtype != torch.float32 or not sums.is_contiguous():
+        raise SdnError('batch_norm_backward_nhwc: sums must be a contiguous fp32 [C, 2] tensor')
     gz = torch.empty_like(z)
     gs = torch.empty_like(z) if want_skip else None
     mean, rstd, gamma = mean.float().contiguous(), rstd.float().contiguous(), gamma.detach().float().contiguous()
     with torch.cuda.device(z.device):
         _check(lib().sdn_batch_norm_backward_nhwc(_ptr(grad_y), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma),
-                                                  _ptr(sums), _ptr(gz), _ptr(gs), z.numel() // C, C, 1 if relu else 0,
-                                                  _stream()))
+                                                  _ptr(sums), _ptr(gz), _ptr(gs), z.numel() // C, C,
+                                                  (1 if relu else 0) | (2 if precleared else 0), _stream()))
     return gz, sums[:, 1], sums[:, 0], gs
 
 

@@ -397,7 +397,8 @@ def other_configs(renderer, dev, world, rank, fast, args):
     from derender3d.models.renderer import Renderer
     out = {}
     if world > 1:
-        out['config4'] = measure_train(dev, world, rank, B=16, S=384, steps=10, graph=not args.no_train_graph)
+        out['config4'] = measure_train(dev, world, rank, B=16, S=384, steps=10, graph=not args.no_train_graph,
+                                       native_encoder=not args.cudnn_encoder)
         return out
     B = args.batch
     verts, faces, grads = make_inputs(B, 0, dev)
@@ -457,12 +458,14 @@ def other_configs(renderer, dev, world, rank, fast, args):
                        'images_per_s': round(Bc / ms * 1e3, 1), 'ms_per_step': round(ms, 3), 'coverage': round(cov, 3)}
     del vc, fc, gc, rc
     torch.cuda.empty_cache()
-    out['config3'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph)
-    try:        # the same step with the encoder trunk trained on this repo's kernels (forward, dgrad, wgrad, BatchNorm)
-        out['config3_native_encoder'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph,
-                                                      native_encoder=True)
+    # the encoder trunk (forward, dgrad, wgrad, BatchNorm) on this repo's tcgen05 kernels; the cuDNN bf16-autocast encoder
+    # of round 1 is kept beside it as the comparator
+    out['config3'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph, native_encoder=True)
+    try:
+        out['config3_cudnn_encoder'] = measure_train(dev, 1, 0, B=16, S=384, steps=10, graph=not args.no_train_graph,
+                                                     native_encoder=False)
     except Exception as e:      # noqa: BLE001
-        out['config3_native_encoder'] = {'failed': repr(e)[:200]}
+        out['config3_cudnn_encoder'] = {'failed': repr(e)[:200]}
         torch.cuda.synchronize()
     return out
 
@@ -617,6 +620,7 @@ def main():
     ap.add_argument('--no-graph', dest='graph', action='store_false', help='time the eager step, not its CUDA graph')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-extra', action='store_true', help='skip the other configs (2b, 2c, 3 / 4) measured after the headline')
+    ap.add_argument('--cudnn-encoder', action='store_true', help='config 4: cuDNN bf16-autocast encoder instead of the native one')
     ap.add_argument('--no-train-graph', action='store_true', help='config 3 / 4: time the eager step, not its CUDA graph')
     ap.add_argument('--rank-seeds', action='store_true', help='N > 1: different synthetic scenes on every rank')
     args = ap.parse_args()

@@ -213,7 +213,8 @@ int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* grad_weight
  *             statistics come from sdn_conv2d.stats); act 0 none / 1 ReLU;
  *   backward: g^ = grad_y * [y > 0] (relu = 1), sums[c] = (sum g^, sum g^ * zhat) -- i.e. (grad_beta, grad_gamma) --,
  *             grad_z = gamma * rstd * (g^ - sums[c,0] / pixels - zhat * sums[c,1] / pixels); grad_skip (optional) = g^,
- *             the gradient entering the block's skip connection.  sums: fp32 [C, 2], cleared by the call. */
+ *             the gradient entering the block's skip connection.  sums: fp32 [C, 2], cleared by the call unless bit 1 of
+ *             `relu` is set (relu = 2 | 3: the caller cleared it, e.g. one clearing pass for all layers of a network). */
 int sdn_affine_act_nhwc(const void* z, const float* scale, const float* shift, const void* residual, void* y,
                         long long pixels, int C, int act, void* stream);
 int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, const void* z, const float* mean, const float* rstd,

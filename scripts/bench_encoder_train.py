@@ -60,6 +60,10 @@ def make(kind):
                 f = enc._trunk(xc)
             (f.float() * t).sum().backward()
     else:
+        enc.net = enc.net.to(memory_format=torch.channels_last)     # [Cout,KH,KW,Cin] in memory: what the kernels read
+        for p in enc.parameters():
+            p.grad = torch.zeros_like(p)
+
         def step():
             (resnet18_trunk_train(enc.net, x) * t).sum().backward()
     return step
