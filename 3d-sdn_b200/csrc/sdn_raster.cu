@@ -600,6 +600,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Early depth rejection in k_raster_tiles.  depth_of's result is 1 / sum_k (w_k / z_k) with w clamped to [0, 1] and
+// normalised: a convex combination of the vertex depths in 1/z, so it cannot be smaller than the smallest vertex depth
+// except by rounding (seven correctly rounded operations: a few ulp).  A face whose smallest vertex depth, less a 1e-5
+// relative margin, is already greater than the depth stored for a sample cannot win that sample's atomicMin, and the
+// seven IEEE divisions are skipped.  Depths that reach the z-buffer are positive, so their bit patterns order like the
+// values; a face with a non-positive vertex depth gets bound 0 (never rejected).  The stored depth only decreases, so a
+// stale read is conservative.  The winner of every sample, hence the face-index map, is unchanged.
+__device__ __forceinline__ unsigned z_lower_bits(const float* f) {
+    const float zmin = fminf(f[2], fminf(f[5], f[8]));
+    return zmin > 0.0f ? __float_as_uint(zmin * 0.99999f) : 0u;
+}
+__device__ __forceinline__ unsigned key_depth_bits(const u64* key) {
+    return reinterpret_cast<const volatile unsigned*>(key)[1];      // high word of (depth bits << 32 | face)
+}
+
 constexpr int BCH = 1024;       // active-list entries per pipeline stage
 
 template <int SS>
@@ -655,9 +670,11 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                 float f[9], inv[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) { f[k] = __ldg(P.faces + fo * 9 + k); inv[k] = __ldg(ws.face_inv + fo * 9 + k); }
+                const unsigned zlo = z_lower_bits(f);
                 for (int yy = by0; yy <= by1; yy++)
                     for (int xx = bx0; xx <= bx1; xx++) {
                         if (!inside_test(f, s_xp[xx - sx0], s_yp[yy - sy0])) continue;
+                        if (zlo > key_depth_bits(&s_key[(yy - sy0) * TW + (xx - sx0)])) continue;      // cannot win
                         float z;
                         if (depth_of(f, inv, (float)xx, (float)yy, P.clip, z))
                             atomicMin(&s_key[(yy - sy0) * TW + (xx - sx0)], ((u64)__float_as_uint(z) << 32) | (unsigned)fn);
@@ -677,14 +694,23 @@ __global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) 
                 const int bx0 = max((int)bb.x, sx0), bx1 = min((int)bb.z, sx1);
                 const int by0 = max((int)bb.y, sy0), by1 = min((int)bb.w, sy1);
                 const int nbx = (bx1 - bx0) / 8 + 1, nby = (by1 - by0) / 4 + 1, nblk = nbx * nby;
+                const unsigned zlo = z_lower_bits(f);
+                int cxa = 0, cya = 0;                      // block (column, row) of n0; n0 + 1 is its successor in row order
                 for (int n0 = 0; n0 < nblk; n0 += 2) {
-                    int xa = bx0 + (n0 % nbx) * 8 + (lane & 7), ya = by0 + (n0 / nbx) * 4 + (lane >> 3);
-                    const int n1 = n0 + 1;
-                    int xb = bx0 + (n1 % nbx) * 8 + (lane & 7), yb = by0 + (n1 / nbx) * 4 + (lane >> 3);
-                    const bool va = xa <= bx1 && ya <= by1, vb = n1 < nblk && xb <= bx1 && yb <= by1;
+                    int cxb = cxa + 1, cyb = cya;
+                    if (cxb == nbx) { cxb = 0; cyb++; }
+                    int xa = bx0 + cxa * 8 + (lane & 7), ya = by0 + cya * 4 + (lane >> 3);
+                    int xb = bx0 + cxb * 8 + (lane & 7), yb = by0 + cyb * 4 + (lane >> 3);
+                    const bool va = xa <= bx1 && ya <= by1, vb = n0 + 1 < nblk && xb <= bx1 && yb <= by1;
+                    cxa = cxb + 1; cya = cyb;
+                    if (cxa == nbx) { cxa = 0; cya++; }
                     xa = min(xa, sx1); ya = min(ya, sy1); xb = min(xb, sx1); yb = min(yb, sy1);
-                    const bool ia = va && inside_test(f, s_xp[xa - sx0], s_yp[ya - sy0]);
-                    const bool ib = vb && inside_test(f, s_xp[xb - sx0], s_yp[yb - sy0]);
+                    // inside the triangle AND not already behind the sample's current depth (the interpolated depth is a
+                    // convex combination of the vertex depths: its minimum, less a rounding margin, bounds it from below)
+                    const bool ia = va && inside_test(f, s_xp[xa - sx0], s_yp[ya - sy0]) &&
+                                    zlo <= key_depth_bits(&s_key[(ya - sy0) * TW + (xa - sx0)]);
+                    const bool ib = vb && inside_test(f, s_xp[xb - sx0], s_yp[yb - sy0]) &&
+                                    zlo <= key_depth_bits(&s_key[(yb - sy0) * TW + (xb - sx0)]);
                     if (!__any_sync(FULL, ia || ib)) continue;
                     float za, zb;
                     const bool oa = depth_of(f, inv, (float)xa, (float)ya, P.clip, za);
