@@ -618,7 +618,7 @@ __device__ __forceinline__ unsigned key_depth_bits(const u64* key) {
 constexpr int BCH = 1024;       // active-list entries per pipeline stage
 
 template <int SS>
-__global__ void __launch_bounds__(NT) k_raster_tiles(FwdParams P, Workspace ws) {
+__global__ void __launch_bounds__(NT, 4) k_raster_tiles(FwdParams P, Workspace ws) {
     __shared__ u64 s_key[TH * TW];
     __shared__ __align__(128) short4 s_bb[2][BCH];
     __shared__ __align__(128) int s_ids[2][BCH];

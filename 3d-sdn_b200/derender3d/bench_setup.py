@@ -55,7 +55,8 @@ def train_setup(dev, B=16, S=384, faces=72576, seed=0, real=True, capturable=Tru
         model.derenderer._fc3.bias[0] = 1.0
         model.derenderer._fc3.bias[4:7] = torch.tensor([1.3, 0.4, 0.5])
         model.derenderer._fc3.bias[7] = 2.2
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3, capturable=capturable)
+    # torch's fused multi-tensor Adam: one kernel over all 62 parameter tensors instead of ~a dozen foreach passes
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=1e-3, capturable=capturable, fused=dev.type == 'cuda')
     g = torch.Generator().manual_seed(seed)
     c = 0.3 * (torch.rand(B, 2, generator=g) - 0.5)
     d = 0.25 + 0.15 * torch.rand(B, 2, generator=g)
