@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
 struct WgradParams {
     int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad;
     int bw, bh, bn, tiles_w, tiles_h, tiles_n;      // 64-pixel patches of the OUTPUT grid
-    int splits, patches_per_split;
+    int splits, patches_per_split, atomic;         // atomic: add into dw (several pixel ranges, or accumulate mode)
     float* dw;                                      // [Cout, KH, KW, Cin] fp32, accumulated into
 };
 
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_wgrad(const __grid_constant__
                         if (co >= p.Cout) continue;
                         const float4 val = *reinterpret_cast<const float4*>(&s_tr[q][r][4 * (lane & 7)]);
                         float* o = p.dw + ((size_t)co * taps + tap) * p.Cin + ci;
-                        if (p.splits == 1) *reinterpret_cast<float4*>(o) = val;
+                        if (!p.atomic) *reinterpret_cast<float4*>(o) = val;
                         else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                                           ::"l"(o), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
                     }
@@ -777,6 +777,95 @@ __global__ void __launch_bounds__(256) k_affine_act(const __nv_bfloat16* __restr
     }
 }
 
+// ---- MaxPool2d (ResNet stem: 3x3, stride 2, padding 1) on NHWC bf16; a thread owns 8 consecutive channels of one pixel.
+// Forward: maximum over the window's in-bounds elements (torch pads with -inf) and, optionally, the position kh * K + kw of
+// the window's FIRST maximum in scan order (one byte per element; the element torch's max_pool2d_with_indices records).
+// Backward: GATHER form -- each INPUT pixel visits the (at most ceil(K/s)^2) windows that contain it and takes a window's
+// gradient when the recorded position is its own; no atomics, every gradient element written exactly once.
+__device__ __forceinline__ void bf8_to_float(const uint4& v, float* f) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        f[2 * k] = __low2float(b); f[2 * k + 1] = __high2float(b);
+    }
+}
+__device__ __forceinline__ uint4 float_to_bf8(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+        w[k] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(256) k_max_pool_nhwc(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                       unsigned char* __restrict__ idx, int N, int H, int W, int C, int Ho,
+                                                       int Wo, int K, int stride, int pad) {
+    const int cg = C >> 3;
+    const long total = (long)N * Ho * Wo * cg;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        long r = i / cg;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int n = (int)(r / Ho);
+        float m[8];
+        unsigned char am[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { m[k] = -INFINITY; am[k] = 255; }
+        for (int kh = 0; kh < K; kh++) {
+            const int hi = ho * stride + kh - pad;
+            if (hi < 0 || hi >= H) continue;
+            for (int kw = 0; kw < K; kw++) {
+                const int wi = wo * stride + kw - pad;
+                if (wi < 0 || wi >= W) continue;
+                float v[8];
+                bf8_to_float(*reinterpret_cast<const uint4*>(x + (((size_t)n * H + hi) * W + wi) * C + g * 8), v);
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (v[k] > m[k]) { m[k] = v[k]; am[k] = (unsigned char)(kh * K + kw); }      // strict: the FIRST maximum
+            }
+        }
+        *reinterpret_cast<uint4*>(y + (size_t)i * 8) = float_to_bf8(m);
+        if (idx) *reinterpret_cast<uint2*>(idx + (size_t)i * 8) = *reinterpret_cast<const uint2*>(am);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_max_pool_bwd_nhwc(const unsigned char* __restrict__ idx, const __nv_bfloat16* __restrict__ gy,
+                                                           __nv_bfloat16* __restrict__ gx, int N, int H, int W, int C, int Ho,
+                                                           int Wo, int K, int stride, int pad) {
+    const int cg = C >> 3;
+    const long total = (long)N * H * W * cg;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        long r = i / cg;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0.0f;
+        // windows (ho, wo) with ho * stride - pad <= h <= ho * stride - pad + K - 1
+        int ho0 = h + pad - (K - 1); ho0 = ho0 <= 0 ? 0 : (ho0 + stride - 1) / stride;
+        int wo0 = w + pad - (K - 1); wo0 = wo0 <= 0 ? 0 : (wo0 + stride - 1) / stride;
+        const int ho1 = min(Ho - 1, (h + pad) / stride), wo1 = min(Wo - 1, (w + pad) / stride);
+        for (int ho = ho0; ho <= ho1; ho++)
+            for (int wo = wo0; wo <= wo1; wo++) {
+                const unsigned char code = (unsigned char)((h - (ho * stride - pad)) * K + (w - (wo * stride - pad)));
+                const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * C + g * 8;
+                const uint2 iv = *reinterpret_cast<const uint2*>(idx + o);
+                const unsigned char* am = reinterpret_cast<const unsigned char*>(&iv);
+                float gv[8];
+                bf8_to_float(*reinterpret_cast<const uint4*>(gy + o), gv);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] += am[k] == code ? gv[k] : 0.0f;
+            }
+        *reinterpret_cast<uint4*>(gx + (size_t)i * 8) = float_to_bf8(acc);
+    }
+}
+
 // Batch statistics -> everything the normalising pass and the backward need, in one launch of C threads: the convolution's
 // epilogue left per-(image, channel) sum / sum of squares in stats [N, C, 2]; out [4, C] = (mean, rstd, scale, shift) with
 // scale = gamma * rstd, shift = beta - mean * scale; running statistics updated in place as torch.nn.BatchNorm2d does
@@ -906,8 +995,11 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* __res
                                                       const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                       const float* __restrict__ sums, __nv_bfloat16* __restrict__ gz,
-                                                      __nv_bfloat16* __restrict__ gres, long groups, int C, float inv_m, int relu) {
+                                                      __nv_bfloat16* __restrict__ gres, long groups, int C, float inv_m, int relu,
+                                                      float* __restrict__ gg_acc, float* __restrict__ gb_acc) {
     const int cg = C >> 3;
+    if (blockIdx.x == 0 && gg_acc)                          // parameter gradients accumulated in place (one block: no race)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { gg_acc[c] += sums[2 * c + 1]; gb_acc[c] += sums[2 * c]; }
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % cg) * 8;
         const uint4 gv = *reinterpret_cast<const uint4*>(gy + i * 8), zv = *reinterpret_cast<const uint4*>(z + i * 8);
@@ -1185,7 +1277,7 @@ extern "C" int sdn_reflect_pad_nhwc(const void* x, void* y, int N, int H, int W,
 }
 
 extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* grad_weight, int N, int H, int W, int Cin,
-                                int Cout, int KH, int KW, int stride, int pad, void* stream) {
+                                int Cout, int KH, int KW, int stride, int pad, int accumulate, void* stream) {
     if (!grad_out || !input || !grad_weight || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 ||
         stride <= 0 || pad < 0)
         return SDN_E_ARG;
@@ -1223,7 +1315,8 @@ extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* 
         p.splits = best;
         p.patches_per_split = (patches + best - 1) / best;
     }
-    if (p.splits > 1) {
+    p.atomic = (p.splits > 1 || accumulate) ? 1 : 0;
+    if (p.splits > 1 && !accumulate) {
         e = cudaMemsetAsync(grad_weight, 0, sizeof(float) * (size_t)Cout * KH * KW * Cin, st);
         if (e != cudaSuccess) return (int)e;
     }
@@ -1264,6 +1357,35 @@ extern "C" int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* 
     return sdn_internal::launch_end();
 }
 
+extern "C" int sdn_max_pool_nhwc(const void* x, void* y, void* argmax, int N, int H, int W, int C, int K, int stride, int pad,
+                                 void* stream) {
+    if (!x || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || K <= 0 || K > 15 || stride <= 0 || pad < 0 || 2 * pad > K)
+        return SDN_E_ARG;
+    const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return SDN_E_ARG;
+    const long total = (long)N * Ho * Wo * (C / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148L * 32 ? 148L * 32 : (total + 255) / 256);
+    sdn_internal::launch_begin("k_max_pool_nhwc", (cudaStream_t)stream);
+    k_max_pool_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (unsigned char*)argmax, N, H,
+                                                              W, C, Ho, Wo, K, stride, pad);
+    return sdn_internal::launch_end();
+}
+
+extern "C" int sdn_max_pool_backward_nhwc(const void* argmax, const void* grad_y, void* grad_x, int N, int H, int W, int C, int K,
+                                          int stride, int pad, void* stream) {
+    if (!argmax || !grad_y || !grad_x || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || K <= 0 || K > 15 || stride <= 0 ||
+        pad < 0 || 2 * pad > K)
+        return SDN_E_ARG;
+    const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return SDN_E_ARG;
+    const long total = (long)N * H * W * (C / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256 > 148L * 32 ? 148L * 32 : (total + 255) / 256);
+    sdn_internal::launch_begin("k_max_pool_bwd_nhwc", (cudaStream_t)stream);
+    k_max_pool_bwd_nhwc<<<blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)argmax, (const __nv_bfloat16*)grad_y,
+                                                                  (__nv_bfloat16*)grad_x, N, H, W, C, Ho, Wo, K, stride, pad);
+    return sdn_internal::launch_end();
+}
+
 extern "C" int sdn_batch_norm_finalize(const float* stats, int N, int C, long long pixels, float eps, float momentum,
                                        const float* gamma, const float* beta, float* running_mean, float* running_var,
                                        long long* num_batches, float* out, void* stream) {
@@ -1298,9 +1420,11 @@ extern "C" int sdn_affine_act_nhwc(const void* z, const float* scale, const floa
 }
 
 extern "C" int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, const void* z, const float* mean, const float* rstd,
-                                            const float* gamma, float* sums, void* grad_z, void* grad_skip, long long pixels,
-                                            int C, int relu, void* stream) {
-    if (!grad_y || !z || !mean || !rstd || !gamma || !sums || !grad_z || pixels <= 0 || C <= 0 || (C & 7) || ((relu & 1) && !y))
+                                            const float* gamma, float* sums, void* grad_z, void* grad_skip,
+                                            float* grad_gamma_acc, float* grad_beta_acc, long long pixels, int C, int relu,
+                                            void* stream) {
+    if (!grad_y || !z || !mean || !rstd || !gamma || !sums || !grad_z || pixels <= 0 || C <= 0 || (C & 7) || ((relu & 1) && !y) ||
+        ((grad_gamma_acc == nullptr) != (grad_beta_acc == nullptr)))
         return SDN_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const bool precleared = (relu & 2) != 0;             // bit 1: the caller cleared `sums` (one clearing pass for many layers)
@@ -1327,6 +1451,6 @@ extern "C" int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, c
     sdn_internal::launch_begin("k_bn_bwd_apply", st);
     k_bn_bwd_apply<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)grad_y, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, mean, rstd,
                                            gamma, sums, (__nv_bfloat16*)grad_z, (__nv_bfloat16*)grad_skip, groups, C,
-                                           1.0f / (float)pixels, relu);
+                                           1.0f / (float)pixels, relu, grad_gamma_acc, grad_gamma_acc ? grad_beta_acc : nullptr);
     return sdn_internal::launch_end();
 }

@@ -9,6 +9,8 @@ the convolution's epilogue (scale / shift), together with the residual add and t
     head   : global average pool (torch) -> [N, 512] fp32
 
 Activations are NHWC bf16, accumulation fp32.  Training (batch statistics + autograd) stays on the torch / cuDNN path."""
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -81,6 +83,16 @@ def _bn_train(z, stats, bn, relu, residual=None):
     return sdn_b200.affine_act_nhwc(z, scale, shift, residual, relu), mean, rstd
 
 
+# Parameter gradients of the trunk are added straight into existing `.grad` tensors by the wgrad / BatchNorm-backward kernels
+# (what Megatron calls gradient-accumulation fusion); SDN_FUSED_GRAD_ACC=0 returns them through autograd instead.
+FUSED_GRAD_ACCUMULATION = os.environ.get('SDN_FUSED_GRAD_ACC', '1') != '0'
+
+
+def _can_accumulate(p):
+    g = p.grad
+    return g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == p.device
+
+
 class _TrunkTrainFunction(torch.autograd.Function):
     """features = ResNet18(images) in training mode; every convolution (forward, data gradient, weight gradient) on the
     tcgen05 kernels of csrc/sdn_conv_tc.cu, BatchNorm forward / backward on sdn_affine_act_nhwc /
@@ -120,11 +132,10 @@ class _TrunkTrainFunction(torch.autograd.Function):
         units = []          # (name, conv, bn, relu, input, z, y, mean, rstd)
         xin, z, y, mean, rstd = conv_bn(x, net.conv1, net.bn1, True, stem=True)
         units.append(('stem', net.conv1, net.bn1, True, xin, z, y, mean, rstd))
-        pool_in = y.permute(0, 3, 1, 2)
-        pooled, pool_idx = F.max_pool2d(pool_in, net.maxpool.kernel_size, net.maxpool.stride, net.maxpool.padding,
-                                        return_indices=True)
-        x = pooled.permute(0, 2, 3, 1).contiguous()
-        saved['pool'] = (pool_in.shape, pool_idx)
+        mp = net.maxpool
+        pool = (int(_pair(mp.kernel_size)[0]), int(_pair(mp.stride)[0]), int(_pair(mp.padding)[0]))
+        x, pool_arg = sdn_b200.max_pool_nhwc(y, *pool, return_argmax=True)
+        saved['pool'] = (pool, pool_arg, (y.shape[1], y.shape[2]))
         blocks = []
         for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
             for blk in layer:
@@ -152,15 +163,22 @@ class _TrunkTrainFunction(torch.autograd.Function):
         N, H, W, C = ctx.last_shape
         sums_all = torch.zeros(ctx.chans * 2, device=g_feat.device, dtype=torch.float32)     # (grad_beta, grad_gamma) of all layers
         cursor = [0]
+        fused_acc = FUSED_GRAD_ACCUMULATION
         g = (g_feat.detach().float() / (H * W)).to(torch.bfloat16)[:, None, None, :].expand(N, H, W, C).contiguous()
 
         def bn_conv_backward(gy, y, z, mean, rstd, conv, bn, relu, xin, want_skip=False, need_dx=True, skip_add=None, stem=False):
             nc = z.shape[-1]
             sums = sums_all[cursor[0]:cursor[0] + 2 * nc].view(nc, 2)
             cursor[0] += 2 * nc
+            # parameters that already hold a gradient get this one ADDED in place by the kernels (no temporary, no add
+            # kernel); the Function then returns None for them
+            acc_bn = None
+            if fused_acc and _can_accumulate(bn.weight) and _can_accumulate(bn.bias):
+                acc_bn = (bn.weight.grad, bn.bias.grad)
             gz, g_gamma, g_beta, g_skip = sdn_b200.batch_norm_backward_nhwc(gy, y if relu else None, z, mean, rstd, bn.weight, relu,
-                                                                              want_skip, sums=sums)
-            grads[id(bn.weight)], grads[id(bn.bias)] = g_gamma, g_beta
+                                                                              want_skip, sums=sums, accumulate_into=acc_bn)
+            if acc_bn is None:
+                grads[id(bn.weight)], grads[id(bn.bias)] = g_gamma, g_beta
             if stem:
                 k = int(conv.kernel_size[0])
                 gw = sdn_b200.conv2d_wgrad_tc(gz, xin, 1, 1, 1, 0)              # [64, 1, 1, Kpad] over the im2col columns
@@ -168,7 +186,11 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 grads[id(conv.weight)] = gw[:, 0, 0, :cols_n].reshape(conv.out_channels, k, k, conv.in_channels).permute(0, 3, 1, 2)
                 return None, g_skip
             k, s, p = int(conv.kernel_size[0]), int(conv.stride[0]), int(conv.padding[0])
-            grads[id(conv.weight)] = sdn_b200.conv2d_wgrad_tc(gz, xin, k, k, s, p).permute(0, 3, 1, 2)
+            wg = conv.weight.grad
+            if fused_acc and wg is not None and wg.dtype == torch.float32 and wg.permute(0, 2, 3, 1).is_contiguous():
+                sdn_b200.conv2d_wgrad_tc(gz, xin, k, k, s, p, accumulate_into=wg.permute(0, 2, 3, 1))
+            else:
+                grads[id(conv.weight)] = sdn_b200.conv2d_wgrad_tc(gz, xin, k, k, s, p).permute(0, 3, 1, 2)
             dx = None
             if need_dx:
                 dx = sdn_b200.conv2d_dgrad_tc(gz, conv.weight, (xin.shape[1], xin.shape[2]), s, p, residual=skip_add)
@@ -187,12 +209,10 @@ class _TrunkTrainFunction(torch.autograd.Function):
                 g_ds, _ = bn_conv_backward(g_id, None, dz, dmean, drstd, dconv, dbn, False, xb)
                 g = g_main + g_ds
         # max-pool backward (torch), then the stem
-        in_shape, idx = ctx.saved['pool']
-        g_pool = torch.ops.aten.max_pool2d_with_indices_backward(
-            g.permute(0, 3, 1, 2), ctx.units[0][6].permute(0, 3, 1, 2), list(_pair(net.maxpool.kernel_size)),
-            list(_pair(net.maxpool.stride)), list(_pair(net.maxpool.padding)), [1, 1], False, idx)
+        pool, pool_arg, pool_hw = ctx.saved['pool']
+        g_pool = sdn_b200.max_pool_backward_nhwc(pool_arg, g, pool_hw, *pool)
         _, conv, bn, relu, xin, z, y, mean, rstd = ctx.units[0]
-        bn_conv_backward(g_pool.permute(0, 2, 3, 1).contiguous(), y, z, mean, rstd, conv, bn, True, xin, stem=True)
+        bn_conv_backward(g_pool, y, z, mean, rstd, conv, bn, True, xin, stem=True)
         out = [None, None]
         for pid in ctx.param_ids:
             gp = grads.get(pid)

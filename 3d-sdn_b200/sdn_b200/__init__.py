@@ -91,12 +91,14 @@ def lib():
         L.sdn_linear_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
         L.sdn_conv2d_forward.argtypes = [ctypes.POINTER(_Conv2d), vp]
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
-        L.sdn_conv2d_wgrad.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.sdn_conv2d_wgrad.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_affine_act_nhwc.argtypes = [vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
         L.sdn_batch_norm_finalize.argtypes = [vp, ci, ci, ctypes.c_longlong, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp,
                                               vp, vp]
         L.sdn_pack_conv_weight_transposed.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
-        L.sdn_batch_norm_backward_nhwc.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
+        L.sdn_max_pool_nhwc.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.sdn_max_pool_backward_nhwc.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
+        L.sdn_batch_norm_backward_nhwc.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
         L.sdn_instance_norm_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
         L.sdn_reflect_pad_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_instance_norm_apply_nhwc.argtypes = [vp, vp, vp, vp, ci, ci, ci, ctypes.c_float, ci, vp]
@@ -448,11 +450,12 @@ def conv2d_tc(x, w_packed, stride=1, pad=0, scale=None, shift=None, residual=Non
     return out
 
 
-def conv2d_wgrad_tc(grad_out, x, KH, KW, stride=1, pad=0):
+def conv2d_wgrad_tc(grad_out, x, KH, KW, stride=1, pad=0, accumulate_into=None):
     """Weight gradient of conv2d_tc: grad_out [N,Ho,Wo,Cout] bf16, x [N,H,W,Cin] bf16 -> fp32 [Cout,KH,KW,Cin]
     (sdn_conv2d_wgrad: tcgen05 GEMM over pixels, MN-major operands straight from the NHWC tensors, split over pixel
-    ranges with fp32 atomics)."""
-    _need_cuda(grad_out, x)
+    ranges with fp32 atomics).  accumulate_into: a contiguous fp32 [Cout,KH,KW,Cin] tensor the result is ADDED to (e.g. the
+    channels-last storage of a parameter's .grad); it is returned."""
+    _need_cuda(grad_out, x, accumulate_into)
     if grad_out.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
         raise SdnError('conv2d_wgrad_tc: bf16 NHWC tensors expected')
     grad_out, x = grad_out.contiguous(), x.contiguous()
@@ -462,10 +465,15 @@ def conv2d_wgrad_tc(grad_out, x, KH, KW, stride=1, pad=0):
     if tuple(grad_out.shape) != (N, Ho, Wo, Cout) or Cin % 64 or Cout % 64:
         raise SdnError('conv2d_wgrad_tc: grad_out %s does not match x %s (channels must be multiples of 64)'
                        % (tuple(grad_out.shape), tuple(x.shape)))
-    gw = torch.empty(Cout, KH, KW, Cin, device=x.device, dtype=torch.float32)
+    if accumulate_into is not None:
+        gw = accumulate_into
+        if tuple(gw.shape) != (Cout, KH, KW, Cin) or gw.dtype != torch.float32 or not gw.is_contiguous():
+            raise SdnError('conv2d_wgrad_tc: accumulate_into must be a contiguous fp32 [Cout,KH,KW,Cin] tensor')
+    else:
+        gw = torch.empty(Cout, KH, KW, Cin, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device):
         _check(lib().sdn_conv2d_wgrad(_ptr(grad_out), _ptr(x), _ptr(gw), N, H, W, Cin, Cout, KH, KW, int(stride), int(pad),
-                                      _stream()))
+                                      1 if accumulate_into is not None else 0, _stream()))
     return gw
 
 
@@ -554,9 +562,10 @@ def affine_act_nhwc(z, scale, shift, residual=None, relu=False):
     return y
 
 
-def batch_norm_backward_nhwc(grad_y, y, z, mean, rstd, gamma, relu, want_skip=False, sums=None):
+def batch_norm_backward_nhwc(grad_y, y, z, mean, rstd, gamma, relu, want_skip=False, sums=None, accumulate_into=None):
     """-> (grad_z bf16, grad_gamma [C], grad_beta [C], grad_skip bf16 | None); see include/sdn_b200.h.
-    sums: an already CLEARED fp32 [C, 2] buffer to accumulate into (saves the per-call clearing pass)."""
+    sums: an already CLEARED fp32 [C, 2] buffer to accumulate into (saves the per-call clearing pass).
+    accumulate_into = (grad_gamma, grad_beta): contiguous fp32 [C] tensors the parameter gradients are ADDED to in place."""
     _need_cuda(grad_y, y, z, mean, rstd, gamma)
     grad_y, z = grad_y.contiguous(), z.contiguous()
     y = None if y is None else y.contiguous()
@@ -569,11 +578,42 @@ def batch_norm_backward_nhwc(grad_y, y, z, mean, rstd, gamma, relu, want_skip=Fa
     gz = torch.empty_like(z)
     gs = torch.empty_like(z) if want_skip else None
     mean, rstd, gamma = mean.float().contiguous(), rstd.float().contiguous(), gamma.detach().float().contiguous()
+    acc_g, acc_b = accumulate_into if accumulate_into is not None else (None, None)
+    for a in (acc_g, acc_b):
+        if a is not None and (a.dtype != torch.float32 or not a.is_contiguous() or a.numel() != C):
+            raise SdnError('batch_norm_backward_nhwc: accumulate_into needs contiguous fp32 [C] tensors')
     with torch.cuda.device(z.device):
         _check(lib().sdn_batch_norm_backward_nhwc(_ptr(grad_y), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma),
-                                                  _ptr(sums), _ptr(gz), _ptr(gs), z.numel() // C, C,
+                                                  _ptr(sums), _ptr(gz), _ptr(gs), _ptr(acc_g), _ptr(acc_b), z.numel() // C, C,
                                                   (1 if relu else 0) | (2 if precleared else 0), _stream()))
     return gz, sums[:, 1], sums[:, 0], gs
+
+
+def max_pool_nhwc(x, k=3, stride=2, pad=1, return_argmax=False):
+    """nn.MaxPool2d(k, stride, pad) on x [N,H,W,C] bf16 NHWC (sdn_max_pool_nhwc).  return_argmax: also the uint8 tensor of
+    window positions that max_pool_backward_nhwc needs."""
+    _need_cuda(x)
+    x = x.contiguous()
+    N, H, W, C = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty(N, Ho, Wo, C, device=x.device, dtype=torch.bfloat16)
+    am = torch.empty(N, Ho, Wo, C, device=x.device, dtype=torch.uint8) if return_argmax else None
+    with torch.cuda.device(x.device):
+        _check(lib().sdn_max_pool_nhwc(_ptr(x), _ptr(y), _ptr(am), N, H, W, C, int(k), int(stride), int(pad), _stream()))
+    return (y, am) if return_argmax else y
+
+
+def max_pool_backward_nhwc(argmax, grad_y, in_hw, k=3, stride=2, pad=1):
+    """Gradient of max_pool_nhwc with respect to its input [N, H, W, C] (sdn_max_pool_backward_nhwc: gather form)."""
+    _need_cuda(argmax, grad_y)
+    argmax, grad_y = argmax.contiguous(), grad_y.contiguous()
+    N, _, _, C = grad_y.shape
+    H, W = in_hw
+    gx = torch.empty(N, H, W, C, device=grad_y.device, dtype=torch.bfloat16)
+    with torch.cuda.device(grad_y.device):
+        _check(lib().sdn_max_pool_backward_nhwc(_ptr(argmax), _ptr(grad_y), _ptr(gx), N, H, W, C, int(k), int(stride), int(pad),
+                                                _stream()))
+    return gx
 
 
 def reflect_pad_nhwc(x, pad, cpad=None):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDN_VERSION 200            /* 0.2.0: sdn_composite_scene takes frame masks */
+#define SDN_VERSION 201            /* 0.2.0: sdn_composite_scene takes frame masks */
 
 /* what to render: rasterize.py:21-22 return_rgb / return_alpha / return_depth */
 #define SDN_RGB    1
@@ -203,10 +203,11 @@ int sdn_conv2d_forward(const sdn_conv2d* c, void* stream);
  * torch.autograd for the convolutions of derenderer.py:25-27):
  *   grad_weight[co, kh, kw, ci] = sum_{n,ho,wo} grad_out[n,ho,wo,co] * input[n, ho*stride + kh - pad, wo*stride + kw - pad, ci]
  * grad_out [N,Ho,Wo,Cout] bf16, input [N,H,W,Cin] bf16 (Cin, Cout multiples of 64), grad_weight fp32 [Cout,KH,KW,Cin]
- * (overwritten).  The data gradient needs no entry point of its own: it is sdn_conv2d_forward of grad_out with the
+ * (overwritten; with accumulate = 1 the result is ADDED to what grad_weight holds -- e.g. straight into a parameter's .grad --
+ * by vector reductions, no clearing pass).  The data gradient needs no entry point of its own: it is sdn_conv2d_forward of grad_out with the
  * spatially flipped, channel-transposed weights (stride 1) or, for stride 2, its four output-parity phases. */
 int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* grad_weight, int N, int H, int W, int Cin, int Cout,
-                     int KH, int KW, int stride, int pad, void* stream);
+                     int KH, int KW, int stride, int pad, int accumulate, void* stream);
 
 /* BatchNorm2d in training mode around those convolutions (torchvision BasicBlock), NHWC bf16, `pixels` = N*H*W:
  *   forward : y = act(z * scale[c] + shift[c] (+ residual)), scale = gamma * rstd, shift = beta - mean * scale (the batch
@@ -214,12 +215,23 @@ int sdn_conv2d_wgrad(const void* grad_out, const void* input, float* grad_weight
  *   backward: g^ = grad_y * [y > 0] (relu = 1), sums[c] = (sum g^, sum g^ * zhat) -- i.e. (grad_beta, grad_gamma) --,
  *             grad_z = gamma * rstd * (g^ - sums[c,0] / pixels - zhat * sums[c,1] / pixels); grad_skip (optional) = g^,
  *             the gradient entering the block's skip connection.  sums: fp32 [C, 2], cleared by the call unless bit 1 of
- *             `relu` is set (relu = 2 | 3: the caller cleared it, e.g. one clearing pass for all layers of a network). */
+ *             `relu` is set (relu = 2 | 3: the caller cleared it, e.g. one clearing pass for all layers of a network).
+ *             grad_gamma_acc / grad_beta_acc (optional, fp32 [C]): sums[c,1] / sums[c,0] are added to them (parameter
+ *             gradients accumulated in place). */
 int sdn_affine_act_nhwc(const void* z, const float* scale, const float* shift, const void* residual, void* y,
                         long long pixels, int C, int act, void* stream);
 int sdn_batch_norm_backward_nhwc(const void* grad_y, const void* y, const void* z, const float* mean, const float* rstd,
-                                 const float* gamma, float* sums, void* grad_z, void* grad_skip, long long pixels, int C,
-                                 int relu, void* stream);
+                                 const float* gamma, float* sums, void* grad_z, void* grad_skip, float* grad_gamma_acc,
+                                 float* grad_beta_acc, long long pixels, int C, int relu, void* stream);
+
+/* nn.MaxPool2d(K, stride, pad) of the ResNet stem on NHWC bf16 (derenderer.py:25-27 -> torchvision resnet18.maxpool), C a
+ * multiple of 8, floor mode, y [N, Ho, Wo, C]; argmax (optional, uint8 [N, Ho, Wo, C]) receives kh * K + kw of each window's
+ * first maximum in scan order -- the element torch's max_pool2d_with_indices records.  Backward: grad_x [N,H,W,C] (every
+ * element written) from grad_y and argmax; gather form, no atomics. */
+int sdn_max_pool_nhwc(const void* x, void* y, void* argmax, int N, int H, int W, int C, int K, int stride, int pad,
+                      void* stream);
+int sdn_max_pool_backward_nhwc(const void* argmax, const void* grad_y, void* grad_x, int N, int H, int W, int C, int K,
+                               int stride, int pad, void* stream);
 
 /* Batch statistics of a convolution result (sdn_conv2d.stats, fp32 [N, C, 2] = per-image sum / sum of squares) -> out
  * fp32 [4, C] = (mean, rstd, scale = gamma * rstd, shift = beta - mean * scale); running_mean / running_var (optional)

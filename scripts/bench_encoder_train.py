@@ -69,6 +69,13 @@ def make(kind):
     return step
 
 
+ONLY = os.environ.get('ONLY')
+if ONLY:                                # profiling runs: a few eager steps of one variant, nothing else
+    step = make(ONLY)
+    for _ in range(int(os.environ.get('STEPS', 2))):
+        step()
+    torch.cuda.synchronize()
+    sys.exit(0)
 for kind in ('fp32', 'autocast', 'native'):
     step = make(kind)
     out[kind + '_eager_ms'] = round(time_ms(step), 4)

@@ -22,7 +22,7 @@ def test_header_symbols_exported():
     assert len(names) >= 9
     for n in names:
         assert hasattr(lib, n), 'libsdn_b200.so does not export %s' % n
-    assert lib.sdn_version() == 200
+    assert lib.sdn_version() == 201
     assert sdn_b200.launch_count() >= 0
 
 

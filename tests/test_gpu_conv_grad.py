@@ -136,3 +136,51 @@ def test_transposed_weight_operands(dev, co, ci, k, stride, chlast):
     assert len(ops) == len(want)
     for a, b in zip(ops, want):
         assert a.shape == b.shape and a.is_contiguous() and torch.equal(a, b)
+
+
+@pytest.mark.parametrize('shape,k,s,p', [((4, 112, 112, 64), 3, 2, 1), ((2, 17, 23, 64), 3, 2, 1), ((3, 12, 12, 128), 2, 2, 0),
+                                         ((2, 9, 9, 64), 3, 1, 1)])
+def test_max_pool_forward_and_backward_match_torch_exactly(dev, shape, k, s, p):
+    """sdn_max_pool_nhwc / sdn_max_pool_backward_nhwc against torch's max_pool2d + autograd on the same bf16 tensor with MANY
+    ties (post-ReLU values on a coarse grid): the gradient of a window must go to the same element torch picks."""
+    import sdn_b200
+    N, H, W, C = shape
+    g_ = torch.Generator().manual_seed(H * W + C)
+    x = (torch.relu(torch.randn(N, C, H, W, generator=g_)) * 4).round().div(4).bfloat16().to(dev)       # ties, zeros
+    xr = x.clone().float().requires_grad_(True)
+    y = F.max_pool2d(xr, k, s, p)
+    go = torch.randn(y.shape, generator=g_).bfloat16().to(dev)
+    y.backward(go.float())
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    yn, am = sdn_b200.max_pool_nhwc(xn, k, s, p, return_argmax=True)
+    assert torch.equal(sdn_b200.max_pool_nhwc(xn, k, s, p), yn)
+    assert torch.equal(yn.permute(0, 3, 1, 2).float(), y.detach())
+    gx = sdn_b200.max_pool_backward_nhwc(am, go.permute(0, 2, 3, 1).contiguous(), (H, W), k, s, p)
+    want = xr.grad.bfloat16()          # sums of at most 4 bf16 values in fp32, rounded once
+    assert torch.equal(gx.permute(0, 3, 1, 2), want), float((gx.permute(0, 3, 1, 2).float() - want.float()).abs().max())
+
+
+def test_gradients_accumulated_in_place(dev):
+    """accumulate_into: the weight gradient (vector reductions into an existing tensor, one and several pixel ranges) and
+    BatchNorm's parameter gradients are ADDED to what the targets hold."""
+    import sdn_b200
+    g_ = torch.Generator().manual_seed(5)
+    for (N, H, W, Cin, Cout, K, s, p) in [(4, 28, 28, 128, 128, 3, 1, 1), (6, 7, 7, 512, 512, 3, 1, 1), (4, 56, 56, 64, 128, 1, 2, 0)]:
+        x = torch.randn(N, H, W, Cin, generator=g_).bfloat16().to(dev)
+        Ho, Wo = (H + 2 * p - K) // s + 1, (W + 2 * p - K) // s + 1
+        go = torch.randn(N, Ho, Wo, Cout, generator=g_).bfloat16().to(dev)
+        base = torch.randn(Cout, K, K, Cin, generator=g_).to(dev)
+        fresh = sdn_b200.conv2d_wgrad_tc(go, x, K, K, s, p)
+        acc = base.clone()
+        out = sdn_b200.conv2d_wgrad_tc(go, x, K, K, s, p, accumulate_into=acc)
+        assert out.data_ptr() == acc.data_ptr()
+        assert _rel(acc - base, fresh) <= 2e-4, _rel(acc - base, fresh)
+    C, M = 128, 4 * 14 * 14
+    z = torch.randn(4, 14, 14, C, generator=g_).bfloat16().to(dev)
+    gy = torch.randn(4, 14, 14, C, generator=g_).bfloat16().to(dev)
+    mean, rstd, gamma = z.float().mean(dim=(0, 1, 2)), torch.ones(C, device=dev), torch.ones(C, device=dev)
+    gz0, gg0, gb0, _ = sdn_b200.batch_norm_backward_nhwc(gy, None, z, mean, rstd, gamma, False)
+    ag, ab = torch.full((C,), 2.0, device=dev), torch.full((C,), -1.0, device=dev)
+    gz1, _, _, _ = sdn_b200.batch_norm_backward_nhwc(gy, None, z, mean, rstd, gamma, False, accumulate_into=(ag, ab))
+    assert _rel(gz1, gz0) <= 2e-3           # the per-channel sums are float atomics: bf16 roundings of gz may flip
+    assert _rel(ag - 2.0, gg0) <= 1e-5 and _rel(ab + 1.0, gb0) <= 1e-5

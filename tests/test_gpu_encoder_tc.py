@@ -127,3 +127,34 @@ def test_derenderer_trains_through_the_native_trunk(dev):
     assert sdn_b200.launch_count() - n0 > 100            # forward + dgrad + wgrad + BatchNorm kernels
     assert enc.net.conv1.weight.grad is not None and torch.isfinite(enc.net.conv1.weight.grad).all()
     assert enc.net.layer3[0].downsample[0].weight.grad.abs().sum() > 0 and enc.fc1.weight.grad is not None
+
+
+def test_training_trunk_accumulates_into_existing_gradients(dev):
+    """Backward with `.grad` present: the wgrad / BatchNorm-backward kernels add in place (fused accumulation) and autograd
+    receives None.  Model a starts from gradients filled with the constant 0.5 and accumulates in place; models b and c (same
+    weights) get their gradients through autograd.  The batch statistics are summed with float atomics, so two identical
+    runs differ (bf16 roundings flip and train-mode BatchNorm at random initialisation amplifies that): the b-vs-c difference
+    is the noise floor, and (a.grad - 0.5) must agree with b.grad to within twice that floor + 1e-2 for every parameter."""
+    import copy
+    from derender3d.models import encoder_tc
+    from derender3d.models.derenderer import Derenderer
+    torch.manual_seed(2)
+    a = Derenderer().to(dev).train()
+    a.net = a.net.to(memory_format=torch.channels_last)
+    b, c = copy.deepcopy(a), copy.deepcopy(a)
+    x = torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(7)).to(dev)
+    t = torch.randn(8, 512, generator=torch.Generator().manual_seed(8)).to(dev)
+    for p in a.parameters():
+        p.grad = torch.full_like(p, 0.5)                 # channels-last weights get channels-last gradients
+    for m in (a, b, c):
+        (encoder_tc.resnet18_trunk_train(m.net, x) * t).sum().backward()
+    worst_noise = 0.0
+    for (n, p), (_, q), (_, r) in zip(a.net.named_parameters(), b.net.named_parameters(), c.net.named_parameters()):
+        if n.startswith('fc.'):
+            continue
+        noise = _rel(r.grad, q.grad)
+        worst_noise = max(worst_noise, noise)
+        e = _rel(p.grad - 0.5, q.grad)
+        assert e <= 2 * noise + 1e-2, (n, e, noise)
+        assert float((p.grad - 0.5).abs().mean()) > 0, n
+    assert worst_noise < 0.5
