@@ -47,7 +47,7 @@ def main():
     model, opt, batch, objs = st['model'], st['opt'], st['batch'], st['objs']
     roi = batch['roi_norms']
     sync = None
-    if world > 1:
+    if world > 1 or args.native_encoder:
         from sdn_b200.dist import FlatGradSync
         sync = FlatGradSync(model, bucket_views=True)
     amp = not args.fp32
