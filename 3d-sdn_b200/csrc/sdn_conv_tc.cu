@@ -40,7 +40,7 @@ constexpr int TM = 128;                 // output pixels per tile (= TMEM lanes)
 constexpr int TK = 64;                  // K block: 64 bf16 = 128 bytes = one swizzle row
 // operand ring depth: 128-wide tiles run one persistent CTA per SM with ~190 KB of operands in flight; narrower tiles
 // (N = 64 halves the work per tcgen05.mma, so one issuing thread cannot keep the tensor pipe busy) run two CTAs per SM
-template <int TN> struct Ring { static constexpr int STAGES = TN >= 128 ? 6 : 4; };      // TN <= 64: two CTAs per SM (two MMA issuers)
+template <int TN> struct Ring { static constexpr int STAGES = TN == 128 ? 6 : 4; };      // 256: 4 x 48 KB      // TN <= 64: two CTAs per SM (two MMA issuers)
 constexpr int A_BYTES = TM * TK * 2;    // 16 KB
 constexpr int NTHREADS = 192;
 
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full[2], s_tmem_empty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_stat[2 * 128];                   // per-CTA (sum, sum of squares) of the current (image, channel block)
+    __shared__ float s_stat[2 * 256];                   // per-CTA (sums | sums of squares) of the current (image, channel block)
     constexpr uint32_t TNA = TN < 32 ? 32 : TN;         // accumulator columns per buffer (TMEM allocations are >= 32)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -214,7 +214,10 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         const bool cta_stats = p.stats && p.bn == 1;
         const int et = tid - 64;                            // 0..127 within the four epilogue warps
         int key_n = -1, key_c = -1;
-        if (cta_stats) { s_stat[et] = 0.0f; s_stat[et + 128] = 0.0f; asm volatile("bar.sync 1, 128;" ::: "memory"); }
+        if (cta_stats) {
+            for (int c = et; c < 2 * 256; c += 128) s_stat[c] = 0.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         int it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
         const int ab = it & 1;
@@ -229,11 +232,12 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         const size_t opix = (size_t)((long)n * p.osn + (long)ho * p.osh + (long)wo * p.osw);
         if (cta_stats && (n0 != key_n || co0 != key_c)) {
             asm volatile("bar.sync 1, 128;" ::: "memory");      // every warp has finished adding the previous item
-            if (key_n >= 0 && et < TN && key_c + et < p.Cout) {
-                float* o = p.stats + ((size_t)key_n * p.Cout + key_c + et) * 2;
-                atomicAdd(o, s_stat[et]); atomicAdd(o + 1, s_stat[et + 128]);
-            }
-            s_stat[et] = 0.0f; s_stat[et + 128] = 0.0f;
+            if (key_n >= 0)
+                for (int c = et; c < TN && key_c + c < p.Cout; c += 128) {
+                    float* o = p.stats + ((size_t)key_n * p.Cout + key_c + c) * 2;
+                    atomicAdd(o, s_stat[c]); atomicAdd(o + 1, s_stat[c + 256]);
+                }
+            for (int c = et; c < 2 * 256; c += 128) s_stat[c] = 0.0f;
             key_n = n0; key_c = co0;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
 #pragma unroll
                         for (int r = 0; r < 32; r++) { const float v1 = sT[r * 17 + lane]; sm += v1; sq = __fmaf_rn(v1, v1, sq); }
                         if (cta_stats) {
-                            atomicAdd(&s_stat[c0 + h + lane], sm); atomicAdd(&s_stat[c0 + h + lane + 128], sq);
+                            atomicAdd(&s_stat[c0 + h + lane], sm); atomicAdd(&s_stat[c0 + h + lane + 256], sq);
                         } else {
                             const int nimg = n0 + (q * 32) / per_img;
                             if (nimg < p.N) {
@@ -354,10 +358,11 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         }
         if (cta_stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (key_n >= 0 && et < TN && key_c + et < p.Cout) {
-                float* o = p.stats + ((size_t)key_n * p.Cout + key_c + et) * 2;
-                atomicAdd(o, s_stat[et]); atomicAdd(o + 1, s_stat[et + 128]);
-            }
+            if (key_n >= 0)
+                for (int c = et; c < TN && key_c + c < p.Cout; c += 128) {
+                    float* o = p.stats + ((size_t)key_n * p.Cout + key_c + c) * 2;
+                    atomicAdd(o, s_stat[c]); atomicAdd(o + 1, s_stat[c + 256]);
+                }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1139,6 +1144,15 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         if (cudaGetDevice(&dev_) == cudaSuccess) cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
         static const bool no_narrow = getenv("SDN_CONV_NO_NARROW") != nullptr;
         if (TN == 128 && !no_narrow && (long)p.tiles_w * p.tiles_h * p.tiles_n * (c->Cout / 128) * 2 <= sms_) TN = 64;
+        // many output channels: 256-wide tiles read the activation tile half as often; taken when they also save a wave
+        // (e.g. 1024 channels on 24 m tiles: 96 items in one wave instead of 192 in two)
+        static const char* force_tn = getenv("SDN_CONV_TN");
+        const long items128 = (long)p.tiles_w * p.tiles_h * p.tiles_n * (c->Cout / 128);
+        if (TN == 128 && c->Cout % 256 == 0 && (items128 + sms_ - 1) / sms_ > (items128 / 2 + sms_ - 1) / sms_ &&
+            (items128 + sms_ - 1) / sms_ <= 4)
+            TN = 256;
+        if (force_tn && atoi(force_tn) == 128 && TN == 256) TN = 128;
+        if (force_tn && atoi(force_tn) == 256 && TN == 128 && c->Cout % 256 == 0) TN = 256;
     }
     alignas(64) CUtensorMap tmA, tmB;
     {   // activations: dims (fastest first) {C, W, H, N}
@@ -1166,14 +1180,19 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
     }
     cudaStream_t st = (cudaStream_t)stream;
     const long total_work = (long)p.tiles_w * p.tiles_h * p.tiles_n * (c->Cout / TN);
-    const int stages = TN >= 128 ? Ring<128>::STAGES : Ring<64>::STAGES;
+    const int stages = TN == 128 ? Ring<128>::STAGES : Ring<64>::STAGES;
     const size_t smem = (size_t)stages * (A_BYTES + TN * TK * 2) + 4 * 32 * 17 * sizeof(float) + 1024;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;      // CTAs that fit one SM's shared memory
     const dim3 grid((unsigned)(total_work < (long)sms * per_sm ? total_work : (long)sms * per_sm), 1);
     cudaError_t e;
-    if (TN == 128) {
+    if (TN == 256) {
+        e = cudaFuncSetAttribute(k_conv_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return (int)e;
+        sdn_internal::launch_begin("k_conv_tc", st);
+        k_conv_tc<256><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+    } else if (TN == 128) {
         e = cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e) return (int)e;
         sdn_internal::launch_begin("k_conv_tc", st);
