@@ -103,14 +103,41 @@ __device__ __forceinline__ constexpr uint32_t idesc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
+// CTA-pair (tcgen05 cta_group::2) forms: the load lands in THIS CTA's shared memory, its bytes are counted on the LEADER's
+// barrier (same offset in the even CTA of the pair: the peer bit, bit 24 of a shared::cluster address, cleared)
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+// instruction descriptor of the pair form: M = 256 (128 rows per CTA), N = TN
 template <int TN>
+__device__ __forceinline__ constexpr uint32_t idesc_pair() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// PAIR = true: the CTA PAIR form (cluster of 2, tcgen05 cta_group::2).  The two CTAs of a cluster own two consecutive m tiles
+// (M = 256 output pixels) and share one 256-wide block of output channels: each loads its own 128-pixel A tile and HALF of
+// the weight tile (128 of the 256 output channels), the leader (cluster rank 0) issues ONE tcgen05.mma.cta_group::2 of
+// M256 x N256 x K16 that reads both CTAs' shared memory and writes each CTA's 128 accumulator rows into its own tensor
+// memory.  Per SM and K block that is 32 KB of operands for 128 x 256 x 64 MACs -- half the L2 -> SM bytes per MAC of the
+// single-CTA 128 x 128 tile, which sits at the 64 B/clk port of the SM.  Barriers: the `full` barriers live in the leader
+// (both CTAs' TMA loads complete_tx on it: .cta_group::2 with the peer bit of the barrier address cleared); `empty` and
+// `tmem_full` are signalled in both CTAs by multicast commits; the follower's epilogue warps arrive on the leader's
+// `tmem_empty` through mapa.
+template <int TN, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ unsigned char smem_raw[];
     // the swizzle pattern is a function of the address bits [4,10): tiles must start on 1024-byte boundaries
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int STAGES = Ring<TN>::STAGES;
-    constexpr int B_BYTES = TN * TK * 2;
+    constexpr int STAGES = PAIR ? 6 : Ring<TN>::STAGES;
+    constexpr int B_BYTES = (PAIR ? TN / 2 : TN) * TK * 2;      // PAIR: this CTA's half of the weight tile
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_tmem_full[2], s_tmem_empty[2];
     __shared__ uint32_t s_tmem;
@@ -122,23 +149,37 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
     // weight block and neighbouring input patches in L2.  The accumulator is double-buffered in tensor memory: the
     // epilogue of item i drains buffer i & 1 while the MMA warp already fills the other one for item i + 1.
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int total_work = tiles_m * (p.Cout / TN);
+    uint32_t rank = 0;
+    if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tiles_mw = PAIR ? (tiles_m + 1) / 2 : tiles_m;             // m work units (pairs of tiles)
+    const int total_work = tiles_mw * (p.Cout / TN);
+    const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int cblocks = p.Cin / TK;
     const int kblocks = p.KH * p.KW * cblocks;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&s_tmem_full[s], 1); mbar_init(&s_tmem_empty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&s_tmem_full[s], 1); mbar_init(&s_tmem_empty[s], PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {        // the MMA warp owns the accumulator columns in tensor memory
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"(2u * TNA));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                         "r"(2u * TNA));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                         "r"(2u * TNA));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if constexpr (PAIR) {       // both CTAs' barriers are initialised before either signals the other's
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     const uint32_t tmem = s_tmem;
 
     if (warp == 0) {
@@ -147,9 +188,10 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
             int kbg = 0;                                     // K blocks issued by this CTA so far (ring position)
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                int t = w % tiles_m;
-                const int co0 = (w / tiles_m) * TN;
+            for (int w = w_first; w < total_work; w += w_step) {
+                int t = w % tiles_mw;
+                const int co0 = (w / tiles_mw) * TN;
+                if (PAIR) t = t * 2 + (int)rank;             // an odd tile count leaves the last follower a tile beyond N: zeros
                 const int tw = t % p.tiles_w; t /= p.tiles_w;
                 const int th = t % p.tiles_h; t /= p.tiles_h;
                 const int wo0 = tw * p.bw, ho0 = th * p.bh, n0 = t * p.bn;
@@ -160,17 +202,23 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
                     unsigned char* sA = smem + st * STAGE_BYTES;
                     unsigned char* sB = sA + A_BYTES;
-                    mbar_expect_tx(&s_full[st], (uint32_t)STAGE_BYTES);
-                    tma_load_4d(sA, &tmA, &s_full[st], cb * TK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, n0);
-                    tma_load_2d(sB, &tmB, &s_full[st], kb * TK, co0);
+                    if constexpr (PAIR) {
+                        if (rank == 0) mbar_expect_tx(&s_full[st], 2u * (uint32_t)STAGE_BYTES);       // both CTAs' bytes
+                        tma_load_4d_pair(sA, &tmA, &s_full[st], cb * TK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, n0);
+                        tma_load_2d_pair(sB, &tmB, &s_full[st], kb * TK, co0 + (int)rank * (TN / 2));
+                    } else {
+                        mbar_expect_tx(&s_full[st], (uint32_t)STAGE_BYTES);
+                        tma_load_4d(sA, &tmA, &s_full[st], cb * TK, wo0 * p.stride + kw - p.pad, ho0 * p.stride + kh - p.pad, n0);
+                        tma_load_2d(sB, &tmB, &s_full[st], kb * TK, co0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (lane == 0 && (!PAIR || rank == 0)) {
             int kbg = 0, it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+            for (int w = w_first; w < total_work; w += w_step, it++) {
                 const int ab = it & 1;
                 if (it >= 2) {      // the epilogue must have drained this accumulator buffer (two items ago)
                     mbar_wait(&s_tmem_empty[ab], (uint32_t)(((it >> 1) - 1) & 1));
@@ -186,18 +234,35 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
                     for (int j = 0; j < TK / 16; j++) {     // K = 16 per UMMA = 32 bytes along the swizzled row
                         const uint64_t da = make_desc_sw128(a0 + j * 32), db = make_desc_sw128(b0 + j * 32);
                         const uint32_t accumulate = (kb > 0 || j > 0) ? 1u : 0u;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                            ::"r"(acc), "l"(da), "l"(db), "r"(idesc<TN>()), "r"(accumulate) : "memory");
+                        if constexpr (PAIR) {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(acc), "l"(da), "l"(db), "r"(idesc_pair<TN>()), "r"(accumulate) : "memory");
+                        } else {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(acc), "l"(da), "l"(db), "r"(idesc<TN>()), "r"(accumulate) : "memory");
+                        }
                     }
-                    // frees the stage when every UMMA issued so far has completed (implies fence::before_thread_sync)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                                 ::"r"(smem_u32(&s_empty[st])) : "memory");
+                    // frees the stage when every UMMA issued so far has completed (implies fence::before_thread_sync);
+                    // PAIR: in both CTAs
+                    if constexpr (PAIR)
+                        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                     ::"r"(smem_u32(&s_empty[st])), "h"((uint16_t)3) : "memory");
+                    else
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                     ::"r"(smem_u32(&s_empty[st])) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             ::"r"(smem_u32(&s_tmem_full[ab])) : "memory");
+                if constexpr (PAIR)
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(smem_u32(&s_tmem_full[ab])), "h"((uint16_t)3) : "memory");
+                else
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 ::"r"(smem_u32(&s_tmem_full[ab])) : "memory");
             }
         }
     } else {
@@ -219,10 +284,11 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         int it = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+        for (int w = w_first; w < total_work; w += w_step, it++) {
         const int ab = it & 1;
-        int t = w % tiles_m;
-        const int co0 = (w / tiles_m) * TN;
+        int t = w % tiles_mw;
+        const int co0 = (w / tiles_mw) * TN;
+        if (PAIR) t = t * 2 + (int)rank;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int wo0 = tw * p.bw, ho0 = th * p.bh, n0 = t * p.bn;
@@ -232,7 +298,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         const size_t opix = (size_t)((long)n * p.osn + (long)ho * p.osh + (long)wo * p.osw);
         if (cta_stats && (n0 != key_n || co0 != key_c)) {
             asm volatile("bar.sync 1, 128;" ::: "memory");      // every warp has finished adding the previous item
-            if (key_n >= 0)
+            if (key_n >= 0 && key_n < p.N)
                 for (int c = et; c < TN && key_c + c < p.Cout; c += 128) {
                     float* o = p.stats + ((size_t)key_n * p.Cout + key_c + c) * 2;
                     atomicAdd(o, s_stat[c]); atomicAdd(o + 1, s_stat[c + 256]);
@@ -354,11 +420,20 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
         // this accumulator buffer is drained: hand it back to the MMA warp (one arrival per epilogue warp)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tmem_empty[ab])) : "memory");
+        if (lane == 0) {
+            if (PAIR && rank != 0)      // the follower's epilogue reports to the leader's barrier (the MMA issuer waits there)
+                asm volatile(
+                    "{\n\t.reg .b32 ra;\n\t"
+                    "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+                    "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+                    ::"r"(smem_u32(&s_tmem_empty[ab])) : "memory");
+            else
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tmem_empty[ab])) : "memory");
+        }
         }
         if (cta_stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (key_n >= 0)
+            if (key_n >= 0 && key_n < p.N)
                 for (int c = et; c < TN && key_c + c < p.Cout; c += 128) {
                     float* o = p.stats + ((size_t)key_n * p.Cout + key_c + c) * 2;
                     atomicAdd(o, s_stat[c]); atomicAdd(o + 1, s_stat[c + 256]);
@@ -367,8 +442,15 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * TNA));
+    if constexpr (PAIR) {       // neither CTA may leave (or free tensor memory) while the other's MMAs / commits can still touch it
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (warp == 1)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * TNA));
+    } else {
+        if (warp == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * TNA));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1154,6 +1236,16 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         if (force_tn && atoi(force_tn) == 128 && TN == 256) TN = 128;
         if (force_tn && atoi(force_tn) == 256 && TN == 128 && c->Cout % 256 == 0) TN = 256;
     }
+    // CTA-pair form (cta_group::2): a 256 x 256 tile over two SMs, each loading its own pixels and half of the weight tile
+    bool pair = false;
+    {
+        static const char* pair_env = getenv("SDN_CONV_PAIR");
+        const long tiles_m_ = (long)p.tiles_w * p.tiles_h * p.tiles_n;
+        const bool can = c->Cout % 256 == 0 && tiles_m_ >= 2;
+        const bool want = pair_env ? atoi(pair_env) != 0 : (TN == 256);
+        pair = can && want;
+        if (pair) TN = 256;
+    }
     alignas(64) CUtensorMap tmA, tmB;
     {   // activations: dims (fastest first) {C, W, H, N}
         const cuuint64_t dims[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
@@ -1171,7 +1263,7 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         const cuuint64_t K = (cuuint64_t)c->KH * c->KW * c->Cin;
         const cuuint64_t dims[2] = {K, (cuuint64_t)c->Cout};
         const cuuint64_t strides[1] = {K * 2};
-        const cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TN};
+        const cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)(pair ? TN / 2 : TN)};     // pair: each CTA loads half
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c->weight, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1179,34 +1271,53 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         if (r != CUDA_SUCCESS) return SDN_E_ARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const long total_work = (long)p.tiles_w * p.tiles_h * p.tiles_n * (c->Cout / TN);
-    const int stages = TN == 128 ? Ring<128>::STAGES : Ring<64>::STAGES;
-    const size_t smem = (size_t)stages * (A_BYTES + TN * TK * 2) + 4 * 32 * 17 * sizeof(float) + 1024;
+    const long tiles_m_all = (long)p.tiles_w * p.tiles_h * p.tiles_n;
+    const long total_work = (pair ? (tiles_m_all + 1) / 2 : tiles_m_all) * (c->Cout / TN);
+    const int stages = pair ? 6 : (TN == 128 ? Ring<128>::STAGES : Ring<64>::STAGES);
+    const size_t smem = (size_t)stages * (A_BYTES + (pair ? TN / 2 : TN) * TK * 2) + 4 * 32 * 17 * sizeof(float) + 1024;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;      // CTAs that fit one SM's shared memory
     const dim3 grid((unsigned)(total_work < (long)sms * per_sm ? total_work : (long)sms * per_sm), 1);
     cudaError_t e;
+    if (pair) {
+        e = cudaFuncSetAttribute(k_conv_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e) return (int)e;
+        const long pairs = total_work < sms / 2 ? total_work : sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+        cfg.blockDim = dim3(NTHREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        sdn_internal::launch_begin("k_conv_tc_pair", st);
+        e = cudaLaunchKernelEx(&cfg, k_conv_tc<256, true>, tmA, tmB, p);
+        if (e != cudaSuccess) { sdn_internal::launch_end(); return (int)e; }
+        return sdn_internal::launch_end();
+    }
     if (TN == 256) {
-        e = cudaFuncSetAttribute(k_conv_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_conv_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e) return (int)e;
         sdn_internal::launch_begin("k_conv_tc", st);
-        k_conv_tc<256><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+        k_conv_tc<256, false><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
     } else if (TN == 128) {
-        e = cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_conv_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e) return (int)e;
         sdn_internal::launch_begin("k_conv_tc", st);
-        k_conv_tc<128><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+        k_conv_tc<128, false><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
     } else if (TN == 64) {
-        e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_conv_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e) return (int)e;
         sdn_internal::launch_begin("k_conv_tc", st);
-        k_conv_tc<64><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+        k_conv_tc<64, false><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
     } else {
-        e = cudaFuncSetAttribute(k_conv_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_conv_tc<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e) return (int)e;
         sdn_internal::launch_begin("k_conv_tc", st);
-        k_conv_tc<16><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
+        k_conv_tc<16, false><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p);
     }
     return sdn_internal::launch_end();
 }

@@ -615,3 +615,48 @@ def test_batch_of_one_tiny_raster_and_single_face(dev, oracle):
         cfg = sdn_b200.RasterConfig((H, W), ss == 2, return_alpha=True)
         sdn_b200.RasterizeFunction.apply(torch.tensor(faces, device=dev), None, cfg)
         assert np.array_equal(cfg.last_face_index.cpu().numpy(), st.face_index_map), (H, W, ss)
+
+
+@pytest.mark.parametrize('H,W,ss,bg', [(70, 131, 1, (0.2, 0.5, 0.9)), (66, 130, 2, (0.3, 0.3, 0.3)), (37, 129, 2, 'per_image'),
+                                       (96, 200, 1, (0.0, 0.0, 0.0))])
+def test_background_outside_the_tile_rectangle_and_resolve_inside(dev, oracle, H, W, ss, bg):
+    """Every output element is written exactly by one of two kernels: k_fill_background outside each image's tile rectangle
+    (rows / columns not multiples of the vector width, flipped output rows, three-channel colours), k_raster_tiles' resolve
+    inside it (pairs of output pixels, 8- / 16-byte stores).  Small objects in a corner, one image without a visible face,
+    non-uniform and per-image backgrounds; the allocator is primed with NaN-filled blocks of the output sizes so that an
+    element nobody writes cannot pass by luck."""
+    import sdn_b200
+    rng = np.random.RandomState(H + W)
+    B, F = 3, 40
+    faces = random_faces(rng, B, F, size=0.2)
+    faces[..., 0] = faces[..., 0] * 0.35 - 0.55        # a small cluster left of centre
+    faces[..., 1] = faces[..., 1] * 0.35 + 0.45
+    faces[1, :, :, 2] = -5.0                           # image 1: everything behind the camera
+    tex = rng.uniform(0, 1, (B, F, 2, 2, 2, 3)).astype(np.float32)
+    if bg == 'per_image':
+        bg_t = torch.tensor([[0.1, 0.2, 0.3], [0.9, 0.8, 0.7], [0.4, 0.0, 0.6]])
+        bg_o = bg_t.numpy()
+    else:
+        bg_t, bg_o = bg, bg
+    for shape in ((B, 3, H, W), (B, H, W), (B, H, W), (B, H * ss, W * ss, 3)):     # poison the caching allocator's free blocks
+        x = torch.full(shape, float('nan'), device=dev)
+        del x
+    poison = torch.full((B, H * ss, W * ss), 12345, device=dev, dtype=torch.int32)
+    del poison
+    st = oracle.raster_forward(faces, tex, H * ss, W * ss, 0.1, 100, 1e-3, bg_o if bg != 'per_image' else (0, 0, 0), True, True, True)
+    r = _sdn_raster(faces, tex, H, W, ss, 0.1, 100, 1e-3, bg_t, (1, 1, 1), dev)
+    assert np.array_equal(r['face_index'], st.face_index_map)
+    assert (st.face_index_map[1] < 0).all() and 0.005 < (st.face_index_map[0] >= 0).mean() < 0.3
+    for k in ('rgb', 'alpha', 'depth'):
+        assert torch.isfinite(r[k]).all(), k
+    if bg != 'per_image':
+        out = oracle.rasterize_rgbad(torch.tensor(faces), torch.tensor(tex), (H, W), ss == 2, 0.1, 100, 1e-3, bg_o)
+        assert torch.equal(out['alpha'], r['alpha'].cpu())
+        assert rel_l2(r['depth'], out['depth']) <= TOL and rel_l2(r['rgb'], out['rgb']) <= TOL
+    else:       # per-image background: one oracle call per image with that image's colour
+        for b in range(B):
+            out = oracle.rasterize_rgbad(torch.tensor(faces[b:b + 1]), torch.tensor(tex[b:b + 1]), (H, W), ss == 2, 0.1, 100, 1e-3,
+                                         tuple(float(v) for v in bg_o[b]))
+            assert torch.equal(out['alpha'][0], r['alpha'][b].cpu())
+            assert rel_l2(r['rgb'][b], out['rgb'][0]) <= TOL and rel_l2(r['depth'][b], out['depth'][0]) <= TOL
+        assert torch.allclose(r['rgb'][1].cpu(), bg_t[1][:, None, None].expand(3, H, W))
