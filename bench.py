@@ -344,8 +344,11 @@ def run_ours(args):
         'e2e': {'value': round(images / (ms_e2e * 1e-3), 1), 'unit': 'images/s',
                 'h2d_bytes_per_step': int(verts.numel() * 4), 'd2h_bytes_per_step': int(verts.numel() * 4 + 4),
                 'launch': e2e_launch,
-                'pipeline': 'two steps in flight; every step copies its vertices from pinned host memory and its '
-                            'loss + vertex gradients back, each read on the host inside the timed region'},
+                'pipeline': 'two independent steps in flight, each slot replaying on its own stream: every step copies its '
+                            'vertices from pinned host memory, renders forward + backward, computes loss = <outputs, '
+                            'upstream> and copies loss + vertex gradients back; each result is read on the host inside the '
+                            'timed region.  The copies AND the kernel tails of one step overlap the other step, which is why '
+                            'this number can exceed `value` (steps strictly one after another on one stream)'},
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
     }
