@@ -454,6 +454,293 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tc(const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Row-ring form for LARGE filters (the 7x7 layers of the generator; stride 1, input already padded, Cin = 64).  The tile
+// form above fetches one 16 KB activation box per tap: 49 boxes per 128-pixel tile, 784 KB through the SM's L2 port for
+// 128 x TN outputs -- the 7x7 layers ran exactly at that port's rate.  Here a persistent CTA walks DOWN a strip of 128
+// output columns: every input row of the strip (128 + KW - 1 pixels x 64 channels, one 3-D TMA box) is loaded ONCE into a
+// ring of row slots and serves all KH x KW taps of the output rows that touch it: the A operand of tap (kh, kw) for output
+// row ho is the slot of input row ho + kh, its start address advanced by kw pixels (kw x 128 B; the 128-byte swizzle is a
+// function of the shared-memory address bits, so a row-shifted start stays consistent with what TMA wrote into the
+// 1024-byte-aligned slot).  Two output rows share each weight tap (two accumulators in tensor memory, double-buffered), so
+// per output row the SM pulls one input row (17 KB) + half a filter (KH*KW*TN*64 B) instead of KH*KW x 16 KB + a filter.
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // high word of make_desc_sw128: SBO, version, layout
+constexpr int RW_PX = 128;              // output pixels per strip row = TMEM lanes
+constexpr int RW_RG = 2;                // output rows per weight pass
+constexpr int RW_BST = 4;               // weight-tap ring depth
+constexpr int RW_SEG = 16;              // output rows per work item (a vertical segment of a strip)
+constexpr int RW_MAXSLOTS = 12;
+
+template <int TN>
+__global__ void __launch_bounds__(NTHREADS) k_conv_rows(const __grid_constant__ CUtensorMap tmA,
+                                                        const __grid_constant__ CUtensorMap tmB, const ConvParams p,
+                                                        const int slot_bytes, const int nslots) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int B_BYTES = TN * TK * 2;
+    constexpr uint32_t TNA = TN < 32 ? 32 : TN;
+    __shared__ __align__(8) uint64_t s_rfull[RW_MAXSLOTS], s_rempty[RW_MAXSLOTS], s_bfull[RW_BST], s_bempty[RW_BST],
+        s_tmem_full[2], s_tmem_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_stat[2 * 64];
+    unsigned char* ring = smem;
+    unsigned char* bring = smem + (size_t)nslots * slot_bytes;
+    float* sT_all = reinterpret_cast<float*>(bring + RW_BST * B_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int taps = p.KH * p.KW;
+    const int strips = (p.Wo + RW_PX - 1) / RW_PX, segs = (p.Ho + RW_SEG - 1) / RW_SEG;
+    const int total_work = p.N * strips * segs;
+
+    if (tid == 0) {
+        for (int s = 0; s < nslots; s++) { mbar_init(&s_rfull[s], 1); mbar_init(&s_rempty[s], 1); }
+        for (int s = 0; s < RW_BST; s++) { mbar_init(&s_bfull[s], 1); mbar_init(&s_bempty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&s_tmem_full[s], 1); mbar_init(&s_tmem_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"(2u * RW_RG * TNA));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    // work item -> (image, strip, segment); segments of one strip are consecutive items (their halo rows are L2-hot)
+    auto decode = [&](int w, int& n, int& wo0, int& ho0, int& nrows) {
+        const int seg = w % segs; w /= segs;
+        const int strip = w % strips; n = w / strips;
+        wo0 = strip * RW_PX; ho0 = seg * RW_SEG; nrows = min(RW_SEG, p.Ho - ho0);
+    };
+
+    // The producer and the MMA issuer are single threads: their per-tap code must stay a handful of instructions (a 64-bit
+    // modulo per tap made the first version of this kernel issue-latency-bound at ~1800 clk per tap).  Ring positions are
+    // (slot, lap) pairs advanced by compare-and-wrap; laps give the mbarrier parities.
+    struct RingPos { int slot; uint32_t lap; };
+    auto advance = [&](RingPos& r) { if (++r.slot == nslots) { r.slot = 0; r.lap++; } };
+    const uint32_t row_bytes = (uint32_t)((RW_PX + p.KW - 1) * 128);
+    if (warp == 0) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+            RingPos ld = {0, 0};            // next row slot to fill
+            uint32_t tcount = 0;            // weight taps issued so far
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                int n, wo0, ho0, nrows;
+                decode(w, n, wo0, ho0, nrows);
+                const int nin = nrows + p.KH - 1;           // input rows of this item
+                int loaded = 0;
+                auto load_rows_upto = [&](int upto) {       // rows [loaded, upto) of the item
+                    for (; loaded < upto && loaded < nin; loaded++) {
+                        if (ld.lap > 0) mbar_wait(&s_rempty[ld.slot], (ld.lap - 1) & 1);
+                        mbar_expect_tx(&s_rfull[ld.slot], row_bytes);
+                        tma_load_4d(ring + (size_t)ld.slot * slot_bytes, &tmA, &s_rfull[ld.slot], 0, wo0, ho0 + loaded, n);
+                        advance(ld);
+                    }
+                };
+                const int groups = (nrows + RW_RG - 1) / RW_RG;
+                load_rows_upto(RW_RG + p.KH - 1);           // the first group's rows
+                for (int g = 0; g < groups; g++) {
+                    for (int t = 0; t < taps; t++, tcount++) {
+                        if (t == (taps >> 1)) load_rows_upto((g + 2) * RW_RG + p.KH - 1);      // next group's rows, early
+                        const int st = (int)(tcount & (RW_BST - 1));
+                        if (tcount >= RW_BST) mbar_wait(&s_bempty[st], ((tcount / RW_BST) - 1) & 1);
+                        mbar_expect_tx(&s_bfull[st], (uint32_t)B_BYTES);
+                        tma_load_2d(bring + st * B_BYTES, &tmB, &s_bfull[st], t * TK, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            RingPos wt = {0, 0};            // next row to wait for
+            RingPos gr = {0, 0};            // first row of the current group
+            uint32_t tcount = 0, gcount = 0;
+            const uint32_t ring_u32 = smem_u32(ring), bring_u32 = smem_u32(bring);
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                int n, wo0, ho0, nrows;
+                decode(w, n, wo0, ho0, nrows);
+                const int nin = nrows + p.KH - 1;
+                const int groups = (nrows + RW_RG - 1) / RW_RG;
+                int waited = 0;                             // input rows of this item known to have landed
+                for (int g = 0; g < groups; g++, gcount++) {
+                    const int ab = (int)(gcount & 1);
+                    if (gcount >= 2) {
+                        mbar_wait(&s_tmem_empty[ab], ((gcount >> 1) - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    const int rows_here = min(RW_RG, nrows - g * RW_RG);
+                    const int need = g * RW_RG + rows_here + p.KH - 1;
+                    for (; waited < need; waited++) { mbar_wait(&s_rfull[wt.slot], wt.lap & 1); advance(wt); }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t acc0 = tmem + (uint32_t)(ab * RW_RG) * TNA;
+                    int t = 0;
+                    for (int kh = 0; kh < p.KH; kh++) {
+                        // shared-memory addresses of the input rows that tap row kh pairs with output rows 0 / 1 of the group
+                        int s0 = gr.slot + kh; if (s0 >= nslots) s0 -= nslots;
+                        int s1 = s0 + 1; if (s1 >= nslots) s1 -= nslots;
+                        // descriptor low words (start address >> 4; + 8 per pixel of kw shift, + 2 per K = 16 step): the
+                        // issuing thread spends a handful of instructions per tcgen05.mma, not a descriptor build
+                        const uint32_t r0 = ((ring_u32 + (uint32_t)s0 * (uint32_t)slot_bytes) & 0x3FFFFu) >> 4;
+                        const uint32_t r1 = ((ring_u32 + (uint32_t)s1 * (uint32_t)slot_bytes) & 0x3FFFFu) >> 4;
+                        for (int kw = 0; kw < p.KW; kw++, t++, tcount++) {
+                            const int st = (int)(tcount & (RW_BST - 1));
+                            mbar_wait(&s_bfull[st], (tcount / RW_BST) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint32_t b_lo = ((bring_u32 + (uint32_t)st * B_BYTES) & 0x3FFFFu) >> 4;
+#pragma unroll
+                            for (int j = 0; j < RW_RG; j++) {
+                                if (j < rows_here) {
+                                    const uint32_t a_lo = (j ? r1 : r0) + (uint32_t)kw * 8u;
+                                    const uint32_t acc = acc0 + (uint32_t)j * TNA;
+#pragma unroll
+                                    for (int q = 0; q < TK / 16; q++) {
+                                        const uint32_t accumulate = (t > 0 || q > 0) ? 1u : 0u;
+                                        asm volatile(
+                                            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                                            "mov.b64 da, {%1, %5};\n\t"
+                                            "mov.b64 db, {%2, %5};\n\t"
+                                            "setp.ne.b32 p, %4, 0;\n\t"
+                                            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                                            ::"r"(acc), "r"(a_lo + 2u * q), "r"(b_lo + 2u * q), "r"(idesc<TN>()), "r"(accumulate),
+                                              "r"(DESC_HI_SW128) : "memory");
+                                    }
+                                }
+                            }
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                         ::"r"(smem_u32(&s_bempty[st])) : "memory");
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 ::"r"(smem_u32(&s_tmem_full[ab])) : "memory");
+                    // input rows no later group needs: the group's own first rows; after the last group also the halo
+                    const int retire = (g == groups - 1) ? nin - g * RW_RG : RW_RG;
+                    for (int i = 0; i < retire; i++) {
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                     ::"r"(smem_u32(&s_rempty[gr.slot])) : "memory");
+                        advance(gr);
+                    }
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float* sT = sT_all + q * (32 * 17);
+        const bool cta_stats = p.stats != nullptr;
+        const int et = tid - 64;
+        int key_n = -1;
+        if (cta_stats) { if (et < 2 * 64) s_stat[et] = 0.0f; asm volatile("bar.sync 1, 128;" ::: "memory"); }
+        long gcount = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            int n, wo0, ho0, nrows;
+            decode(w, n, wo0, ho0, nrows);
+            if (cta_stats && n != key_n) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (key_n >= 0 && et < TN && et < p.Cout) {
+                    float* o = p.stats + ((size_t)key_n * p.Cout + et) * 2;
+                    atomicAdd(o, s_stat[et]); atomicAdd(o + 1, s_stat[et + 64]);
+                }
+                if (et < 2 * 64) s_stat[et] = 0.0f;
+                key_n = n;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            const int groups = (nrows + RW_RG - 1) / RW_RG;
+            const int wo = wo0 + q * 32 + lane;
+            for (int g = 0; g < groups; g++, gcount++) {
+                const int ab = (int)(gcount & 1);
+                mbar_wait(&s_tmem_full[ab], (uint32_t)((gcount >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int rows_here = min(RW_RG, nrows - g * RW_RG);
+                for (int j = 0; j < rows_here; j++) {
+                    const int ho = ho0 + g * RW_RG + j;
+                    const bool valid = wo < p.Wo;
+                    const size_t opix = (size_t)((long)n * p.osn + (long)ho * p.osh + (long)wo * p.osw);
+                    constexpr int CW = TN >= 32 ? 32 : 16;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < TN; c0 += CW) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem + (uint32_t)(ab * RW_RG + j) * TNA + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                        if (CW == 32) {
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                : "r"(taddr));
+                        } else {
+                            asm volatile(
+                                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                : "r"(taddr));
+                        }
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float y[CW];
+#pragma unroll
+                        for (int k = 0; k < CW; k++) {
+                            float t = __uint_as_float(v[k]);
+                            if (p.scale) t *= __ldg(p.scale + c0 + k);
+                            if (p.shift) t += __ldg(p.shift + c0 + k);
+                            y[k] = t;
+                        }
+                        if (p.stats) {
+#pragma unroll
+                            for (int h = 0; h < CW; h += 16) {
+#pragma unroll
+                                for (int k = 0; k < 16; k++) sT[lane * 17 + k] = valid ? y[h + k] : 0.0f;
+                                __syncwarp();
+                                if (lane < 16) {
+                                    float sm = 0.0f, sq = 0.0f;
+#pragma unroll
+                                    for (int r = 0; r < 32; r++) { const float v1 = sT[r * 17 + lane]; sm += v1; sq = __fmaf_rn(v1, v1, sq); }
+                                    atomicAdd(&s_stat[c0 + h + lane], sm); atomicAdd(&s_stat[c0 + h + lane + 64], sq);
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        if (valid) {
+                            uint4* op = reinterpret_cast<uint4*>(p.out + opix + c0);
+#pragma unroll
+                            for (int gq = 0; gq < CW / 8; gq++) {
+                                uint32_t w4[4];
+#pragma unroll
+                                for (int h = 0; h < 4; h++) {
+                                    float a = y[gq * 8 + h * 2], b = y[gq * 8 + h * 2 + 1];
+                                    if (p.relu == 1) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                                    else if (p.relu == 2) { a = tanhf(a); b = tanhf(b); }
+                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+                                    w4[h] = *reinterpret_cast<const uint32_t*>(&b2);
+                                }
+                                op[gq] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_tmem_empty[ab])) : "memory");
+            }
+        }
+        if (cta_stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (key_n >= 0 && et < TN && et < p.Cout) {
+                float* o = p.stats + ((size_t)key_n * p.Cout + et) * 2;
+                atomicAdd(o, s_stat[et]); atomicAdd(o + 1, s_stat[et + 64]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2u * RW_RG * TNA));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Weight gradient of the convolution (training path of the encoder trunk):
 //     dW[co, kh, kw, ci] = sum_{n, ho, wo} g[n, ho, wo, co] * x[n, ho*s + kh - p, wo*s + kw - p, ci]
 // as a GEMM whose REDUCTION runs over pixels:  D[co, ci] (+)= G^T[co, pix] . X_tap[pix, ci], one (tap, channel blocks,
@@ -1219,6 +1506,58 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         }
     }
 
+    // large filters on pre-padded 64-channel inputs (the generator's 7x7 layers): row-ring form.  OPT-IN (SDN_CONV_ROWS=1):
+    // correct, but at 457 / 438 us for the two 7x7 layers against 380 / 293 us in the tile form it does not pay yet (the
+    // single MMA-issuing thread and the 4-deep weight-tap ring bound it at ~850 clk per tap)
+    {
+        const char* rows_env = getenv("SDN_CONV_ROWS");
+        const bool rows_ok = c->KH == c->KW && c->KH * c->KW >= 25 && c->KW <= 9 && c->stride == 1 && c->pad == 0 && c->Cin == 64 &&
+                             !c->residual && c->out_stride_w <= 0 && c->out_h <= 0 && c->out_w <= 0 &&
+                             (c->Cout == 64 || c->Cout == 16) && Wo >= RW_PX && rows_env && atoi(rows_env) != 0;
+        if (rows_ok) {
+            const int rowpx = RW_PX + c->KW - 1;
+            const int slot_bytes = (rowpx * 128 + 1023) / 1024 * 1024;
+            const int nslots = c->KH + 2 * RW_RG - 1;
+            const int TNr = c->Cout;
+            const size_t smem_r = (size_t)nslots * slot_bytes + (size_t)RW_BST * TNr * TK * 2 + 4 * 32 * 17 * sizeof(float) + 1024;
+            if (nslots <= RW_MAXSLOTS && smem_r <= 220 * 1024) {
+                alignas(64) CUtensorMap tmAr, tmBr;
+                const cuuint64_t dimsA[4] = {(cuuint64_t)c->Cin, (cuuint64_t)c->W, (cuuint64_t)c->H, (cuuint64_t)c->N};
+                const cuuint64_t strA[3] = {(cuuint64_t)c->Cin * 2, (cuuint64_t)c->W * c->Cin * 2, (cuuint64_t)c->H * c->W * c->Cin * 2};
+                const cuuint32_t boxA[4] = {(cuuint32_t)TK, (cuuint32_t)rowpx, 1, 1};
+                const cuuint32_t one4[4] = {1, 1, 1, 1};
+                if (enc(&tmAr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)c->input, dimsA, strA, boxA, one4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return SDN_E_ARG;
+                const cuuint64_t Kr = (cuuint64_t)c->KH * c->KW * c->Cin;
+                const cuuint64_t dimsB[2] = {Kr, (cuuint64_t)c->Cout};
+                const cuuint64_t strB[1] = {Kr * 2};
+                const cuuint32_t boxB[2] = {(cuuint32_t)TK, (cuuint32_t)TNr};
+                const cuuint32_t one2[2] = {1, 1};
+                if (enc(&tmBr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)c->weight, dimsB, strB, boxB, one2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return SDN_E_ARG;
+                int dev_r = 0, sms_r = 148;
+                if (cudaGetDevice(&dev_r) == cudaSuccess) cudaDeviceGetAttribute(&sms_r, cudaDevAttrMultiProcessorCount, dev_r);
+                const long work = (long)c->N * ((Wo + RW_PX - 1) / RW_PX) * ((Ho + RW_SEG - 1) / RW_SEG);
+                const dim3 grid_r((unsigned)(work < sms_r ? work : sms_r), 1);
+                cudaStream_t st_r = (cudaStream_t)stream;
+                cudaError_t er;
+                if (TNr == 64) {
+                    er = cudaFuncSetAttribute(k_conv_rows<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+                    if (er) return (int)er;
+                    sdn_internal::launch_begin("k_conv_rows", st_r);
+                    k_conv_rows<64><<<grid_r, NTHREADS, smem_r, st_r>>>(tmAr, tmBr, p, slot_bytes, nslots);
+                } else {
+                    er = cudaFuncSetAttribute(k_conv_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+                    if (er) return (int)er;
+                    sdn_internal::launch_begin("k_conv_rows", st_r);
+                    k_conv_rows<16><<<grid_r, NTHREADS, smem_r, st_r>>>(tmAr, tmBr, p, slot_bytes, nslots);
+                }
+                return sdn_internal::launch_end();
+            }
+        }
+    }
     int TN = c->Cout == 16 ? 16 : ((c->Cout % 128 == 0) ? 128 : 64);
     {   // few output pixels (ResNet layer3 / layer4 at small batch): 128-wide N tiles would occupy less than half of the SMs;
         // 64-wide ones double the CTAs (the A tile is re-read from L2 by twice as many CTAs, which is cheaper than idle SMs)

@@ -162,3 +162,41 @@ def test_argument_errors(dev):
     with pytest.raises(sdn_b200.SdnError):
         sdn_b200.conv2d_tc(x.cpu(), w.cpu())                       # no CPU fallback
     assert sdn_b200.conv2d_tc(x, w, 1, 1).abs().sum() == 0
+
+
+@pytest.mark.parametrize('N,H,W,Cout,K,act,stats', [(1, 40, 300, 64, 7, None, True), (2, 39, 200, 3, 7, 'tanh', False),
+                                                    (1, 24, 134, 64, 5, 'relu', True), (1, 70, 518, 64, 7, None, False)])
+def test_large_filters_row_ring_form(dev, N, H, W, Cout, K, act, stats, monkeypatch):
+    """k_conv_rows (opt-in with SDN_CONV_ROWS=1; 7x7 / 5x5, stride 1, pre-padded 64-channel input): every input row of a 128-column strip is loaded once
+    into a ring of shared-memory row slots and all K x K taps address it through row-shifted UMMA descriptors.  Strips
+    with a ragged last column block, odd output heights (a last group of one row), several images, bias + tanh / ReLU,
+    InstanceNorm statistics from the epilogue; against torch fp32 on the same bf16-rounded operands."""
+    import sdn_b200
+    monkeypatch.setenv('SDN_CONV_ROWS', '1')
+    g = torch.Generator().manual_seed(H + W + Cout)
+    x = torch.randn(N, 64, H, W, generator=g)
+    w = torch.randn(Cout, 64, K, K, generator=g) / (64 * K * K) ** 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), bias)
+    if act == 'tanh':
+        refa = torch.tanh(ref)
+    elif act == 'relu':
+        refa = ref.clamp_min(0)
+    else:
+        refa = ref
+    xn = x.to(dev).bfloat16().permute(0, 2, 3, 1).contiguous()
+    wp = sdn_b200.pack_conv_weight(w.to(dev))
+    b = F.pad(bias, (0, wp.shape[0] - Cout)).to(dev)
+    st = torch.full((N, wp.shape[0], 2), float('nan'), device=dev) if stats else None
+    sdn_b200.timing_enable(True); sdn_b200.timing_read()
+    out = sdn_b200.conv2d_tc(xn, wp, 1, 0, None, b, None, {'tanh': 'tanh', 'relu': True, None: False}[act], stats=st)
+    torch.cuda.synchronize()
+    names = set(sdn_b200.timing_read())
+    sdn_b200.timing_enable(False)
+    assert 'k_conv_rows' in names, names
+    got = out[..., :Cout].permute(0, 3, 1, 2).float().cpu()
+    assert got.shape == refa.shape
+    assert _rel(got, refa) <= 5e-3, _rel(got, refa)
+    if stats:
+        s = st[:, :Cout].cpu()
+        assert _rel(s[..., 0], ref.sum(dim=(2, 3))) <= 2e-3 and _rel(s[..., 1], (ref * ref).sum(dim=(2, 3))) <= 2e-3
