@@ -469,9 +469,10 @@ constexpr int RW_RG = 2;                // output rows per weight pass
 constexpr int RW_BST = 4;               // weight-tap ring depth
 constexpr int RW_SEG = 16;              // output rows per work item (a vertical segment of a strip)
 constexpr int RW_MAXSLOTS = 12;
+constexpr int RW_THREADS = 224;         // producer, MMA issuer (row 0), 4 epilogue warps, MMA issuer (row 1)
 
 template <int TN>
-__global__ void __launch_bounds__(NTHREADS) k_conv_rows(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(RW_THREADS) k_conv_rows(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB, const ConvParams p,
                                                         const int slot_bytes, const int nslots) {
     extern __shared__ unsigned char smem_raw[];
@@ -492,9 +493,10 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_rows(const __grid_constant__ 
     const int total_work = p.N * strips * segs;
 
     if (tid == 0) {
-        for (int s = 0; s < nslots; s++) { mbar_init(&s_rfull[s], 1); mbar_init(&s_rempty[s], 1); }
-        for (int s = 0; s < RW_BST; s++) { mbar_init(&s_bfull[s], 1); mbar_init(&s_bempty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&s_tmem_full[s], 1); mbar_init(&s_tmem_empty[s], 4); }
+        // two MMA issuers (one per output row of a group): what they release needs both of their commits
+        for (int s = 0; s < nslots; s++) { mbar_init(&s_rfull[s], 1); mbar_init(&s_rempty[s], RW_RG); }
+        for (int s = 0; s < RW_BST; s++) { mbar_init(&s_bfull[s], 1); mbar_init(&s_bempty[s], RW_RG); }
+        for (int s = 0; s < 2; s++) { mbar_init(&s_tmem_full[s], RW_RG); mbar_init(&s_tmem_empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -552,7 +554,10 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_rows(const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 6) {
+        // ONE issuing thread per output row of the group: a tcgen05.mma costs its issuer ~100 clk (descriptor moves into
+        // uniform registers), 8 of them per tap from one thread were the bound at ~850 clk per tap
+        const int jrow = warp == 1 ? 0 : 1;
         if (lane == 0) {
             RingPos wt = {0, 0};            // next row to wait for
             RingPos gr = {0, 0};            // first row of the current group
@@ -589,8 +594,8 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_rows(const __grid_constant__ 
                             mbar_wait(&s_bfull[st], (tcount / RW_BST) & 1);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint32_t b_lo = ((bring_u32 + (uint32_t)st * B_BYTES) & 0x3FFFFu) >> 4;
-#pragma unroll
-                            for (int j = 0; j < RW_RG; j++) {
+                            {
+                                const int j = jrow;
                                 if (j < rows_here) {
                                     const uint32_t a_lo = (j ? r1 : r0) + (uint32_t)kw * 8u;
                                     const uint32_t acc = acc0 + (uint32_t)j * TNA;
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_rows(const __grid_constant__ 
                 }
             }
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         const int q = warp & 3;
         float* sT = sT_all + q * (32 * 17);
         const bool cta_stats = p.stats != nullptr;
@@ -1506,14 +1511,17 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
         }
     }
 
-    // large filters on pre-padded 64-channel inputs (the generator's 7x7 layers): row-ring form.  OPT-IN (SDN_CONV_ROWS=1):
-    // correct, but at 457 / 438 us for the two 7x7 layers against 380 / 293 us in the tile form it does not pay yet (the
-    // single MMA-issuing thread and the 4-deep weight-tap ring bound it at ~850 clk per tap)
+    // large filters on pre-padded 64-channel inputs (the generator's 7x7 layers): row-ring form, OPT-IN (SDN_CONV_ROWS=1).
+    // Correct (tests/test_gpu_conv_tc.py::test_large_filters_row_ring_form) and, with two MMA-issuing threads, 348 us against
+    // 380 us in the tile form for the 64-channel stem in isolation, but 332 against 293 us for the 16-column head and no
+    // gain inside the network (statistics epilogue): the tile form stays the default.
     {
         const char* rows_env = getenv("SDN_CONV_ROWS");
+        const int rows_mode = rows_env ? atoi(rows_env) : 0;
         const bool rows_ok = c->KH == c->KW && c->KH * c->KW >= 25 && c->KW <= 9 && c->stride == 1 && c->pad == 0 && c->Cin == 64 &&
                              !c->residual && c->out_stride_w <= 0 && c->out_h <= 0 && c->out_w <= 0 &&
-                             (c->Cout == 64 || c->Cout == 16) && Wo >= RW_PX && rows_env && atoi(rows_env) != 0;
+                             (c->Cout == 64 || c->Cout == 16) && Wo >= RW_PX &&
+                             rows_mode == 1;
         if (rows_ok) {
             const int rowpx = RW_PX + c->KW - 1;
             const int slot_bytes = (rowpx * 128 + 1023) / 1024 * 1024;
@@ -1547,12 +1555,12 @@ extern "C" int sdn_conv2d_forward(const sdn_conv2d* c, void* stream) {
                     er = cudaFuncSetAttribute(k_conv_rows<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
                     if (er) return (int)er;
                     sdn_internal::launch_begin("k_conv_rows", st_r);
-                    k_conv_rows<64><<<grid_r, NTHREADS, smem_r, st_r>>>(tmAr, tmBr, p, slot_bytes, nslots);
+                    k_conv_rows<64><<<grid_r, RW_THREADS, smem_r, st_r>>>(tmAr, tmBr, p, slot_bytes, nslots);
                 } else {
                     er = cudaFuncSetAttribute(k_conv_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
                     if (er) return (int)er;
                     sdn_internal::launch_begin("k_conv_rows", st_r);
-                    k_conv_rows<16><<<grid_r, NTHREADS, smem_r, st_r>>>(tmAr, tmBr, p, slot_bytes, nslots);
+                    k_conv_rows<16><<<grid_r, RW_THREADS, smem_r, st_r>>>(tmAr, tmBr, p, slot_bytes, nslots);
                 }
                 return sdn_internal::launch_end();
             }
