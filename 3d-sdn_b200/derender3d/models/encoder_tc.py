@@ -1,4 +1,5 @@
-"""ResNet-18 trunk of the image encoder on the hand-written tcgen05 convolution (csrc/sdn_conv_tc.cu) -- inference form.
+"""ResNet-18 trunk of the image encoder on the hand-written tcgen05 kernels (csrc/sdn_conv_tc.cu): an inference form
+(`ResNet18TC`, BatchNorm folded) and a training form (`resnet18_trunk_train`, batch statistics, forward AND backward).
 
 Reference: geometric/derender3d/models/derenderer.py:25-27,35-43 (torchvision resnet18, `net.avgpool` replaced by
 AdaptiveAvgPool2d(1), `net.fc` by Linear(512, 256)).  In eval mode BatchNorm is a per-channel affine map, folded here into
@@ -8,7 +9,14 @@ the convolution's epilogue (scale / shift), together with the residual add and t
     block  : y = ReLU(bn1(conv3x3_s(x)));  x = ReLU(bn2(conv3x3(y)) + (downsample: bn(conv1x1_s(x)) | x))
     head   : global average pool (torch) -> [N, 512] fp32
 
-Activations are NHWC bf16, accumulation fp32.  Training (batch statistics + autograd) stays on the torch / cuDNN path."""
+Activations are NHWC bf16, accumulation fp32.
+
+Training form (second half of this file): one torch.autograd.Function for the whole trunk.  Forward per unit: convolution with
+the per-(image, channel) sums from its epilogue -> sdn_batch_norm_finalize (batch mean / rstd, running statistics) ->
+sdn_affine_act_nhwc (normalise, + identity, ReLU); the stem's max-pool is sdn_max_pool_nhwc.  Backward per unit:
+sdn_batch_norm_backward_nhwc -> sdn_conv2d_wgrad (weight gradient, accumulated in place when the parameter already holds a
+gradient) -> data gradient on the forward kernel with transposed operands (sdn_pack_conv_weight_transposed).  The global
+average pool and its backward are the only torch kernels on activations."""
 import os
 
 import torch
@@ -95,9 +103,10 @@ def _can_accumulate(p):
 
 class _TrunkTrainFunction(torch.autograd.Function):
     """features = ResNet18(images) in training mode; every convolution (forward, data gradient, weight gradient) on the
-    tcgen05 kernels of csrc/sdn_conv_tc.cu, BatchNorm forward / backward on sdn_affine_act_nhwc /
-    sdn_batch_norm_backward_nhwc, max-pool / average-pool through torch.  Activations and activation gradients are bf16
-    NHWC, parameter gradients fp32."""
+    tcgen05 kernels of csrc/sdn_conv_tc.cu, BatchNorm forward / backward on sdn_batch_norm_finalize / sdn_affine_act_nhwc /
+    sdn_batch_norm_backward_nhwc, the stem's max-pool on sdn_max_pool_nhwc / sdn_max_pool_backward_nhwc, the average pool
+    through torch.  Activations and activation gradients are bf16 NHWC, parameter gradients fp32.  The intermediate
+    activations live on `ctx` (no double backward)."""
 
     @staticmethod
     def forward(ctx, images, net, *params):
