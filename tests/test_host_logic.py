@@ -91,3 +91,23 @@ def test_mesh_module_batches_and_parameter_groups(tmp_path):
     assert {id(p) for p in mesh.parameters()} == {id(mesh.vertices), id(mesh.textures)}
     opt = torch.optim.Adam(mesh.set_lr(0.01, 0.1))
     assert [g['lr'] for g in opt.param_groups] == [0.01, 0.1]
+
+
+def test_pack_conv_weight_layouts_agree():
+    """pack_conv_weight: the one-cast fast path (no padding needed) and the padded path give the same [Cout,KH,KW,Cin] bf16
+    operand for contiguous and channels-last weights (host logic of the convolution boundary, no GPU)."""
+    import torch
+    import sdn_b200
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(128, 64, 3, 3, generator=g)
+    a = sdn_b200.pack_conv_weight(w)
+    b = sdn_b200.pack_conv_weight(w.contiguous(memory_format=torch.channels_last))
+    want = w.permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert a.shape == (128, 3, 3, 64) and a.is_contiguous() and b.is_contiguous()
+    assert torch.equal(a, want) and torch.equal(b, want)
+    # channel padding: Cin 48 -> 64, Cout 3 -> 16 (the generator's stem / head), zero rows and channels
+    w2 = torch.randn(3, 48, 7, 7, generator=g)
+    p = sdn_b200.pack_conv_weight(w2)
+    assert p.shape == (16, 7, 7, 64)
+    assert torch.equal(p[:3, :, :, :48], w2.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert float(p[3:].abs().sum()) == 0.0 and float(p[:, :, :, 48:].abs().sum()) == 0.0
