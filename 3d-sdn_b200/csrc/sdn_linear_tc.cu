@@ -209,3 +209,121 @@ extern "C" int sdn_linear_forward(const float* x, const float* weight, const flo
     k_linear_tc<<<grid, 128, smem, (cudaStream_t)stream>>>(x, weight, bias, y, M, N, K, relu);
     return sdn_internal::launch_end();
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// The whole encoder head in ONE launch (derender3d/models/derenderer.py:26-32,35-43: net.fc -> ReLU -> cat(mroi, droi) ->
+// fc1 -> ReLU -> fc2 -> ReLU -> fc3).  At the encoder's batch sizes (M = 16 objects; M <= 64 here) a 128-row tensor-core
+// tile is an eighth full and each of the four k_linear_tc launches is ~37 us of latency, so this path does not use tensor
+// cores at all: it is fp32 FMA work spread over 32 CTAs, a warp per output feature, the 16-row activation chunk in
+// shared memory, the four layers separated by grid-wide barriers (all CTAs are co-resident: 32 CTAs on 148 SMs).  fp32
+// operands and accumulation -- the reference's arithmetic, not bf16.  The layer outputs are written to caller buffers (the
+// backward needs them).
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int HEAD_CTAS = 32;
+constexpr int HEAD_ROWS = 16;           // activation rows staged per pass
+constexpr int HEAD_MAXK = 1024;         // widest layer input (net.fc output 1000 + 4 extras)
+
+__device__ __forceinline__ void head_grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// out[m, f] = act(sum_k in[m, k] * W[f, k] + b[f]) for all m < M, features strided over the grid's warps
+__device__ void head_layer(const float* in, int ldi, int K, const float* __restrict__ W, const float* __restrict__ b,
+                           float* __restrict__ out, int ldo, int N, int M, bool relu, float* s_in) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int m0 = 0; m0 < M; m0 += HEAD_ROWS) {
+        const int rows = min(HEAD_ROWS, M - m0);
+        __syncthreads();                                        // the previous chunk's readers are done
+        for (int i = threadIdx.x; i < HEAD_ROWS * K; i += blockDim.x) {
+            const int r = i / K, k = i - r * K;
+            // L2 loads: for layers 1..3 `in` was written by other CTAs of this launch (before the grid barrier)
+            s_in[i] = r < rows ? __ldcg(in + (size_t)(m0 + r) * ldi + k) : 0.0f;
+        }
+        __syncthreads();
+        for (int f = blockIdx.x * nwarps + warp; f < N; f += gridDim.x * nwarps) {
+            float acc[HEAD_ROWS];
+#pragma unroll
+            for (int r = 0; r < HEAD_ROWS; r++) acc[r] = 0.0f;
+            const float* w = W + (size_t)f * K;
+            for (int k = lane; k < K; k += 32) {
+                const float wv = __ldg(w + k);
+#pragma unroll
+                for (int r = 0; r < HEAD_ROWS; r++) acc[r] = __fmaf_rn(wv, s_in[r * K + k], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < HEAD_ROWS; r++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+            }
+            if (lane < rows) {
+                float v = 0.0f;
+#pragma unroll
+                for (int r = 0; r < HEAD_ROWS; r++) if (r == lane) v = acc[r];
+                v += b ? b[f] : 0.0f;
+                if (relu) v = fmaxf(v, 0.0f);
+                out[(size_t)(m0 + lane) * ldo + f] = v;
+            }
+        }
+    }
+}
+
+struct HeadParams {
+    const float* x; const float* extra;
+    int M, K0, N0, E, N1, N2, N3;
+    const float *W0, *b0, *W1, *b1, *W2, *b2, *W3, *b3;
+    float *cat, *h1, *h2, *y;
+    unsigned* barrier;
+};
+
+__global__ void __launch_bounds__(256) k_mlp_head(const HeadParams p) {
+    extern __shared__ float s_head_in[];
+    const unsigned G = gridDim.x;
+    // layer 0 -> cat[:, :N0]; the extras go to cat[:, N0:]
+    head_layer(p.x, p.K0, p.K0, p.W0, p.b0, p.cat, p.N0 + p.E, p.N0, p.M, true, s_head_in);
+    if (p.E > 0)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.M * p.E; i += gridDim.x * blockDim.x) {
+            const int m = i / p.E, e = i - m * p.E;
+            p.cat[(size_t)m * (p.N0 + p.E) + p.N0 + e] = p.extra[i];
+        }
+    head_grid_barrier(p.barrier, G);
+    head_layer(p.cat, p.N0 + p.E, p.N0 + p.E, p.W1, p.b1, p.h1, p.N1, p.N1, p.M, true, s_head_in);
+    head_grid_barrier(p.barrier, 2 * G);
+    head_layer(p.h1, p.N1, p.N1, p.W2, p.b2, p.h2, p.N2, p.N2, p.M, true, s_head_in);
+    head_grid_barrier(p.barrier, 3 * G);
+    head_layer(p.h2, p.N2, p.N2, p.W3, p.b3, p.y, p.N3, p.N3, p.M, false, s_head_in);
+}
+
+}  // namespace
+
+extern "C" int sdn_mlp_head_forward(const float* x, const float* extra, int M, int K0, int N0, int E, int N1, int N2, int N3,
+                                    const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                                    const float* b2, const float* W3, const float* b3, float* cat, float* h1, float* h2, float* y,
+                                    unsigned* barrier, void* stream) {
+    if (!x || !W0 || !W1 || !W2 || !W3 || !cat || !h1 || !h2 || !y || !barrier || M <= 0 || K0 <= 0 || N0 <= 0 || E < 0 ||
+        N1 <= 0 || N2 <= 0 || N3 <= 0 || (E > 0 && !extra))
+        return SDN_E_ARG;
+    int kmax = K0;
+    if (N0 + E > kmax) kmax = N0 + E;
+    if (N1 > kmax) kmax = N1;
+    if (N2 > kmax) kmax = N2;
+    if (kmax > HEAD_MAXK) return SDN_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(barrier, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return (int)e;
+    const size_t smem = (size_t)HEAD_ROWS * kmax * sizeof(float);
+    e = cudaFuncSetAttribute(k_mlp_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    HeadParams p = {x, extra, M, K0, N0, E, N1, N2, N3, W0, b0, W1, b1, W2, b2, W3, b3, cat, h1, h2, y, barrier};
+    sdn_internal::launch_begin("k_mlp_head", st);
+    k_mlp_head<<<HEAD_CTAS, 256, smem, st>>>(p);
+    return sdn_internal::launch_end();
+}

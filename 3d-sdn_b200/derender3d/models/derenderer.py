@@ -41,6 +41,8 @@ class Derenderer(Module):
         self.fc2 = torch.nn.Linear(self.hidden_size, self.hidden_size)
         self._fc3 = torch.nn.Linear(self.hidden_size, sum(self.out_sizes.values()))
         self.tensor_core_head = os.environ.get('SDN_TC_HEAD', '0') == '1'
+        # the four FC layers as ONE fp32 launch (sdn_b200.mlp_head; opt-in: SDN_FUSED_HEAD=1 or `fused_head = True`)
+        self.fused_head = os.environ.get('SDN_FUSED_HEAD', '0') == '1'
         # eval-mode trunk on the hand-written tcgen05 convolution (encoder_tc.ResNet18TC: bf16 operands, BatchNorm folded
         # into the epilogue).  Opt-in like the head (SDN_TC_TRUNK=1 or `tensor_core_trunk = True`): the reference is fp32.
         self.tensor_core_trunk = os.environ.get('SDN_TC_TRUNK', '0') == '1'
@@ -65,7 +67,11 @@ class Derenderer(Module):
         return torch.flatten(n.avgpool(x), 1)
 
     def forward(self, images, mroi_norms, droi_norms):
-        if images.is_cuda and (self.tensor_core_head or torch.is_autocast_enabled() or
+        if images.is_cuda and self.fused_head:
+            from sdn_b200 import mlp_head
+            extra = torch.cat([mroi_norms.float(), droi_norms.float()], dim=1)
+            x = mlp_head(self._trunk(images).float(), extra, self.net.fc, self.fc1, self.fc2, self._fc3)
+        elif images.is_cuda and (self.tensor_core_head or torch.is_autocast_enabled() or
                                (self.tensor_core_trunk and not self.training)):
             from sdn_b200 import linear_tc
             x = linear_tc(self._trunk(images), self.net.fc.weight, self.net.fc.bias, relu=True)

@@ -90,6 +90,7 @@ def lib():
         L.sdn_rasterize_forward.argtypes = [ctypes.POINTER(_Raster), vp]
         L.sdn_linear_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, vp]
         L.sdn_conv2d_forward.argtypes = [ctypes.POINTER(_Conv2d), vp]
+        L.sdn_mlp_head_forward.argtypes = [vp, vp] + [ci] * 7 + [vp] * 8 + [vp] * 4 + [vp, vp]
         L.sdn_im2col_nhwc.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_conv2d_wgrad.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
         L.sdn_affine_act_nhwc.argtypes = [vp, vp, vp, vp, vp, ctypes.c_longlong, ci, ci, vp]
@@ -379,6 +380,63 @@ class LinearTCFunction(torch.autograd.Function):
         gw = g.t() @ x2 if ctx.needs_input_grad[1] else None
         gb = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return gx, gw, gb, None
+
+
+def mlp_head_backward(grad_y, x, cat, h1, h2, W0, W1, W2, W3, n0):
+    """Gradients of the fused encoder head (pure torch: five small matmul pairs).  cat = [relu(x W0^T + b0) | extra],
+    h1 = relu(cat W1^T + b1), h2 = relu(h1 W2^T + b2), y = h2 W3^T + b3.
+    -> dict(x, extra, W0, b0, W1, b1, W2, b2, W3, b3)."""
+    g3 = grad_y.float()
+    out = {'W3': g3.t() @ h2, 'b3': g3.sum(0)}
+    g2 = (g3 @ W3) * (h2 > 0).to(g3.dtype)
+    out['W2'], out['b2'] = g2.t() @ h1, g2.sum(0)
+    g1 = (g2 @ W2) * (h1 > 0).to(g3.dtype)
+    out['W1'], out['b1'] = g1.t() @ cat, g1.sum(0)
+    gcat = g1 @ W1
+    out['extra'] = gcat[:, n0:]
+    g0 = gcat[:, :n0] * (cat[:, :n0] > 0).to(g3.dtype)
+    out['W0'], out['b0'] = g0.t() @ x, g0.sum(0)
+    out['x'] = g0 @ W0
+    return out
+
+
+class MlpHeadFunction(torch.autograd.Function):
+    """The encoder head (net.fc, fc1, fc2, fc3 of derender3d/models/derenderer.py:26-32,35-43) as ONE launch
+    (sdn_mlp_head_forward: fp32 FMA, a warp per output feature, grid-wide barriers between the layers).  Backward: torch."""
+
+    @staticmethod
+    def forward(ctx, x, extra, W0, b0, W1, b1, W2, b2, W3, b3):
+        _need_cuda(x, extra, W0, b0, W1, b1, W2, b2, W3, b3)
+        ts = [_f32c(t) for t in (x, extra, W0, b0, W1, b1, W2, b2, W3, b3)]
+        x2, ex, w0, c0, w1, c1, w2, c2, w3, c3 = ts
+        if any(t.device != x2.device for t in ts):
+            raise SdnError('mlp_head: all operands must be on the input\'s device')
+        M, K0 = x2.shape
+        N0, N1, N2, N3, E = w0.shape[0], w1.shape[0], w2.shape[0], w3.shape[0], ex.shape[1]
+        if w0.shape[1] != K0 or w1.shape[1] != N0 + E or w2.shape[1] != N1 or w3.shape[1] != N2 or ex.shape[0] != M:
+            raise SdnError('mlp_head: layer shapes do not chain')
+        dev = x2.device
+        cat = torch.empty(M, N0 + E, device=dev)
+        h1, h2, y = torch.empty(M, N1, device=dev), torch.empty(M, N2, device=dev), torch.empty(M, N3, device=dev)
+        bar = torch.empty(1, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            _check(lib().sdn_mlp_head_forward(_ptr(x2), _ptr(ex), M, K0, N0, E, N1, N2, N3, _ptr(w0), _ptr(c0), _ptr(w1), _ptr(c1),
+                                              _ptr(w2), _ptr(c2), _ptr(w3), _ptr(c3), _ptr(cat), _ptr(h1), _ptr(h2), _ptr(y),
+                                              _ptr(bar), _stream()))
+        ctx.save_for_backward(x2, cat, h1, h2, w0, w1, w2, w3)
+        ctx.n0 = N0
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, cat, h1, h2, w0, w1, w2, w3 = ctx.saved_tensors
+        g = mlp_head_backward(gy, x2, cat, h1, h2, w0, w1, w2, w3, ctx.n0)
+        return (g['x'], g['extra'], g['W0'], g['b0'], g['W1'], g['b1'], g['W2'], g['b2'], g['W3'], g['b3'])
+
+
+def mlp_head(x, extra, fc0, fc1, fc2, fc3):
+    """relu(fc0(x)) | extra -> relu(fc1) -> relu(fc2) -> fc3 with torch.nn.Linear modules fc0..fc3, one kernel launch."""
+    return MlpHeadFunction.apply(x, extra, fc0.weight, fc0.bias, fc1.weight, fc1.bias, fc2.weight, fc2.bias, fc3.weight, fc3.bias)
 
 
 def linear_tc(x, weight, bias=None, relu=False):

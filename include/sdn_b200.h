@@ -313,6 +313,16 @@ long long sdn_launch_count(void);
 int sdn_linear_forward(const float* x, const float* weight, const float* bias, float* y, int M, int N, int K,
                        int relu, void* stream);
 
+/* The whole encoder head in one launch (derenderer.py:26-32,35-43), fp32 operands and accumulation, for small batches (any
+ * M; meant for M <= 64):  cat = [relu(x . W0^T + b0) | extra],  h1 = relu(cat . W1^T + b1),  h2 = relu(h1 . W2^T + b2),
+ * y = h2 . W3^T + b3.   x [M,K0], extra [M,E] (E may be 0), W_i row-major [N_i, K_i] as torch.nn.Linear stores them; cat
+ * [M, N0+E], h1 [M,N1], h2 [M,N2], y [M,N3] are written (the backward needs them); K0, N0+E, N1, N2 <= 1024.
+ * `barrier`: one device word used by the grid-wide barriers between the layers (cleared by the call). */
+int sdn_mlp_head_forward(const float* x, const float* extra, int M, int K0, int N0, int E, int N1, int N2, int N3,
+                         const float* W0, const float* b0, const float* W1, const float* b1, const float* W2, const float* b2,
+                         const float* W3, const float* b3, float* cat, float* h1, float* h2, float* y, unsigned* barrier,
+                         void* stream);
+
 /* Diagnostics: when enabled, every kernel launch is bracketed by CUDA events on the launching stream;
  * sdn_timing_read() drains them as "kernel_name total_ms launches\n" lines (returns bytes written).  Off by default. */
 int sdn_timing_enable(int on);

@@ -111,3 +111,29 @@ def test_pack_conv_weight_layouts_agree():
     assert p.shape == (16, 7, 7, 64)
     assert torch.equal(p[:3, :, :, :48], w2.permute(0, 2, 3, 1).to(torch.bfloat16))
     assert float(p[3:].abs().sum()) == 0.0 and float(p[:, :, :, 48:].abs().sum()) == 0.0
+
+
+def test_mlp_head_backward_formulas_match_autograd():
+    """sdn_b200.mlp_head_backward (the torch backward of the fused encoder head) against autograd through the same head
+    written with torch.nn.functional.linear (no GPU: the forward kernel is tested in tests/test_gpu_linear_tc.py)."""
+    import torch
+    import torch.nn.functional as F
+    import sdn_b200
+    g = torch.Generator().manual_seed(1)
+    M, K0, N0, E, N1, N2, N3 = 7, 32, 50, 4, 24, 24, 11
+    mk = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64).requires_grad_(True)
+    x, extra = mk(M, K0), mk(M, E)
+    W0, b0, W1, b1, W2, b2, W3, b3 = mk(N0, K0), mk(N0), mk(N1, N0 + E), mk(N1), mk(N2, N1), mk(N2), mk(N3, N2), mk(N3)
+    cat = torch.cat([F.relu(F.linear(x, W0, b0)), extra], dim=1)
+    h1 = F.relu(F.linear(cat, W1, b1))
+    h2 = F.relu(F.linear(h1, W2, b2))
+    y = F.linear(h2, W3, b3)
+    gy = torch.randn(M, N3, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    got = sdn_b200.mlp_head_backward(gy.float(), x.detach().float(), cat.detach().float(), h1.detach().float(), h2.detach().float(),
+                                     W0.detach().float(), W1.detach().float(), W2.detach().float(), W3.detach().float(), N0)
+    want = {'x': x.grad, 'extra': extra.grad, 'W0': W0.grad, 'b0': b0.grad, 'W1': W1.grad, 'b1': b1.grad, 'W2': W2.grad,
+            'b2': b2.grad, 'W3': W3.grad, 'b3': b3.grad}
+    for k, v in want.items():
+        assert got[k].shape == v.shape, k
+        assert float((got[k].double() - v).norm() / (v.norm() + 1e-30)) < 1e-5, k
